@@ -1,0 +1,139 @@
+/* maf.h -- C ABI of the B200-native audio front-end (spectral-gating denoise, BS.1770 loudness, Whisper log-mel).
+ *
+ * The reference (AndersonGACFilho/Modular-Audio-Pipeline) is pure Python and has no FFI for this path: its
+ * "plugin interface" is the PreprocessorProtocol / TranscriberProtocol seam (audio_pipeline/protocols.py:68-90,
+ * :119-133).  These entry points are what a ctypes binding behind that seam calls; every one cites the reference
+ * code it replaces.  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions: every function returns 0 on success or a negative MAF_ERR_* code (text via maf_last_error()).
+ * All `*_dev` pointers are caller-owned DEVICE pointers (e.g. torch.Tensor.data_ptr()); `stream` is a cudaStream_t
+ * passed as void*.  Nothing allocates device memory after maf_plan_create(); the scratch `workspace_dev` is
+ * caller-allocated with maf_plan_workspace_bytes() bytes (256-byte aligned).  All calls are asynchronous on `stream`
+ * unless noted.  A ctx / plan may be used from one thread at a time.
+ */
+#ifndef MAF_H_
+#define MAF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAF_OK 0
+#define MAF_ERR_INVALID (-1)      /* bad argument */
+#define MAF_ERR_CUDA (-2)         /* CUDA runtime error */
+#define MAF_ERR_UNSUPPORTED (-3)  /* geometry the kernels do not cover */
+#define MAF_ERR_TOO_SHORT (-4)    /* audio shorter than one 400 ms loudness block (pyloudnorm raises ValueError) */
+
+typedef struct maf_ctx maf_ctx;    /* per-device constant tables (windows, twiddles, mel banks) */
+typedef struct maf_plan maf_plan;  /* geometry of one batch: item / chunk tables, workspace layout */
+
+/* One recording of a batch -- or one time shard of a long recording (whole 600 000-sample denoise chunks). */
+typedef struct maf_item_desc {
+    int64_t buf_len;   /* samples in the item's local PCM buffer (own range plus supplied halo)               */
+    int64_t origin;    /* local index of the first own sample (0 for a whole recording)                      */
+    int64_t own_len;   /* samples this item produces output for                                              */
+    int64_t g0;        /* index of the first own sample in the full recording (0 for a whole recording)      */
+    int64_t n_global;  /* length of the full recording                                                       */
+    int32_t lo_avail;  /* denoised halo samples the caller will provide before / after the own range         */
+    int32_t hi_avail;  /* (sharded mode only; 0 for a whole recording)                                       */
+} maf_item_desc;
+
+typedef struct maf_params {
+    int32_t sample_rate;             /* config.audio.sample_rate (config.py:52-57)                            */
+    int32_t stationary;              /* 1 = stationary gate (what preprocessor.py:200-206 calls), 0 = non-stationary */
+    float prop_decrease;             /* 0.8 (preprocessor.py:204)                                            */
+    int32_t auto_detect_noise;       /* NoiseReductionConfig.auto_detect_noise (config.py:76-82)             */
+    float noise_sample_duration_s;   /* NoiseReductionConfig.noise_sample_duration_s                          */
+    int32_t external_noise;          /* 1 = thresholds come from maf_set_noise_clips() (noise_sample_path)    */
+    int32_t peak_normalize;          /* 1 = pydub normalize between denoise and loudness (pipeline.py:346)    */
+    float target_lufs;               /* -16.0 (preprocessor.py:244)                                           */
+    int32_t n_mels;                  /* 80 / 128; 0 = no log-mel                                              */
+    int32_t mel_padding;             /* zero samples appended: 480000 whisper.transcribe, 160 faster-whisper, 0 bare */
+} maf_params;
+
+typedef struct maf_layout {           /* per-item offsets into the caller's arrays (filled by maf_plan_layout) */
+    int64_t pcm_off;                  /* int16 samples: input buffer of the item                              */
+    int64_t out_off;                  /* int16 samples: output (own range) of the item                        */
+    int64_t mel_off;                  /* floats: [n_mels, mel_frames] block of the item                       */
+    int32_t mel_frames;
+    int32_t n_chunks;
+} maf_layout;
+
+int maf_version(void);
+const char* maf_last_error(void);
+
+int maf_create(int device, maf_ctx** out);
+void maf_destroy(maf_ctx* ctx);
+
+/* Geometry of a batch.  Replaces the per-file Python set-up of AudioPreprocessor.__init__ / from_config
+ * (preprocessor.py:42-69) plus noisereduce's chunk bookkeeping (get_traces).  Synchronous (uploads small tables). */
+int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf_item_desc* items, int32_t n_items, maf_plan** out);
+void maf_plan_destroy(maf_plan* plan);
+size_t maf_plan_workspace_bytes(const maf_plan* plan);
+int maf_plan_layout(const maf_plan* plan, int32_t item, maf_layout* out);
+int64_t maf_plan_total_pcm(const maf_plan* plan);   /* int16 samples the pcm array must hold   */
+int64_t maf_plan_total_out(const maf_plan* plan);   /* int16 samples the output array must hold */
+int64_t maf_plan_total_mel(const maf_plan* plan);   /* floats the mel array must hold           */
+int64_t maf_plan_launches(const maf_plan* plan);    /* kernels launched by this library through the plan so far */
+
+/* Explicit noise clips (reduce_stationary_noise(input_wav, noise_sample_path), preprocessor.py:174-178):
+ * clip i is noise_pcm_dev[offsets[i] .. offsets[i] + lengths[i]).  Host arrays, copied synchronously. */
+int maf_set_noise_clips(maf_plan* plan, const int64_t* offsets, const int32_t* lengths);
+
+/* ---- the fused hot path: denoise -> (peak normalise) -> loudness normalise -> log-mel ------------------------
+ * pipeline.py:331-347 followed by the transcriber front-end (transcriber.py:229-238).
+ * out_pcm_dev : final int16 PCM (what `_loudnorm.wav` holds)            [maf_plan_total_out]
+ * mel_dev     : float32 [n_mels, frames] per item                        [maf_plan_total_mel]  (NULL iff n_mels = 0)
+ * lufs_dev    : float64 per item, loudness measured BEFORE the gain      (may be NULL)
+ * clip_dev    : int32 [n_items][2] detected noise clip (start, end) in samples (may be NULL)
+ * noise_pcm_dev: only when params.external_noise                                                              */
+int maf_process(maf_plan* plan, const int16_t* pcm_dev, const int16_t* noise_pcm_dev, void* workspace_dev,
+                int16_t* out_pcm_dev, float* mel_dev, double* lufs_dev, int32_t* clip_dev, void* stream);
+
+/* Same call with HOST buffers: copies in, runs maf_process, copies out, and returns when the results are in host
+ * memory.  Device staging buffers are allocated on first use and cached in the plan. */
+int maf_process_host(maf_plan* plan, const int16_t* pcm_host, const int16_t* noise_pcm_host, int64_t noise_len,
+                     int16_t* out_pcm_host, float* mel_host, double* lufs_host, int32_t* clip_host);
+
+/* ---- stage entry points (the Protocol methods call these one at a time) ----------------------------------------
+ * maf_denoise        AudioPreprocessor.reduce_stationary_noise   preprocessor.py:149-214 (incl. _detect_noise_segments :92-147)
+ * maf_peak_normalize AudioPreprocessor.normalize_audio           preprocessor.py:216-242 (16-bit mono same-rate case)
+ * maf_loudness       AudioPreprocessor.normalize_loudness        preprocessor.py:244-288
+ * maf_logmel         whisper.audio.log_mel_spectrogram           transcriber.py:229-238 / :421-427
+ * in/out int16 arrays use the plan layout (pcm_off for inputs, out_off for outputs).                              */
+int maf_denoise(maf_plan* plan, const int16_t* pcm_dev, const int16_t* noise_pcm_dev, void* workspace_dev,
+                int16_t* out_pcm_dev, float* out_f32_dev /* may be NULL */, int32_t* clip_dev /* may be NULL */, void* stream);
+int maf_peak_normalize(maf_plan* plan, const int16_t* pcm_dev, void* workspace_dev, int16_t* out_pcm_dev, void* stream);
+int maf_loudness(maf_plan* plan, const int16_t* pcm_dev, void* workspace_dev, int16_t* out_pcm_dev, double* lufs_dev,
+                 void* stream);
+int maf_logmel(maf_plan* plan, const int16_t* pcm_dev, void* workspace_dev, float* mel_dev, void* stream);
+
+/* ---- pieces for time-sharded recordings (one rank per GPU; the caller runs the NCCL collectives between them) ---
+ * maf_frame_stats      per-frame energy (float32) / zero-crossing count (int32) of the own range -> all-gather
+ * maf_select_clip      selection over the gathered statistics of ONE recording -> seg_dev[2] (global sample range)
+ * maf_sharded_denoise  thresholds from the broadcast clip + K1..K3 -> workspace den16 (own range) and local peak
+ * maf_sharded_energy   after the caller all-reduced the peak and exchanged den16 halos: sub-block energies
+ * maf_gate             gating over the gathered sub-block energies of ONE recording -> gate_dev (opaque 24 bytes)
+ * maf_sharded_logmel   gain + log-mel of the own frames (un-clamped), local max; maf_mel_finalize after all-reduce   */
+int maf_frame_stats(maf_plan* plan, const int16_t* pcm_dev, float* energy_dev, int32_t* zc_dev, void* stream);
+int maf_select_clip(maf_ctx* ctx, const float* energy_dev, const int32_t* zc_dev, int64_t n_frames, int64_t n_global,
+                    int32_t sample_rate, float noise_sample_duration_s, int32_t* seg_dev, void* stream);
+int maf_sharded_denoise(maf_plan* plan, const int16_t* pcm_dev, const int16_t* noise_pcm_dev, void* workspace_dev, void* stream);
+int maf_sharded_energy(maf_plan* plan, void* workspace_dev, void* stream);
+int maf_gate(maf_ctx* ctx, const double* sub_energy_dev, int64_t n_tiles, int64_t n_blocks, int32_t sample_rate,
+             float target_lufs, const int32_t* peak_norm_dev, void* gate_dev, void* stream);
+int maf_sharded_logmel(maf_plan* plan, void* workspace_dev, const void* gate_dev, int16_t* out_pcm_dev, float* mel_dev, void* stream);
+int maf_mel_finalize(maf_plan* plan, void* workspace_dev, float* mel_dev, void* stream);
+/* byte offset / size of a named workspace buffer, so the host can view it as a tensor for a collective:
+ * "peak" int32[n_items], "peak_norm" int32[n_items], "mel_max" int32[n_items] (ordered-int float),
+ * "sub_energy" float64[tiles], "den16" int16 (own range preceded / followed by 2048 halo samples per item)      */
+int maf_plan_buffer(const maf_plan* plan, const char* name, int64_t* offset_bytes, int64_t* size_bytes);
+int64_t maf_plan_den_offset(const maf_plan* plan, int32_t item);   /* int16 index of own sample 0 inside "den16" */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAF_H_ */

@@ -1,0 +1,690 @@
+// C ABI (include/maf.h): context, batch plan (item / chunk tables, workspace layout) and the stage sequencing.
+// No kernel lives here; see noise_detect.cu, stft_denoise.cu, loudness.cu, logmel.cu.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <stddef.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/maf.h"
+#include "maf_common.cuh"
+
+using namespace maf;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(x)                                                                                           \
+    do {                                                                                                \
+        cudaError_t e_ = (x);                                                                           \
+        if (e_ != cudaSuccess) return fail(MAF_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+static inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+
+// ---- context --------------------------------------------------------------------------------------------------
+struct MelHost { std::vector<int> start, count, woff; std::vector<float> w; };
+
+struct maf_ctx {
+    int device = 0;
+    void* blob = nullptr;                // one allocation holding every constant table
+    void* scratch = nullptr;             // 1 KB of device scratch for the single-recording helpers
+    Consts c{};
+    MelBank mel80{}, mel128{};
+};
+
+static double hz_to_mel(double f) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = 1000.0 / f_sp, logstep = log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_mel + log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz(double m) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = 1000.0 / f_sp, logstep = log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+// librosa.filters.mel(sr=16000, n_fft=400, n_mels, htk=False, norm='slaney') as sparse rows (whisper's mel_filters.npz)
+static MelHost build_mel(int n_mels) {
+    MelHost h;
+    std::vector<double> mel_f(n_mels + 2);
+    const double m0 = hz_to_mel(0.0), m1 = hz_to_mel(8000.0);
+    for (int i = 0; i < n_mels + 2; ++i) mel_f[i] = mel_to_hz(m0 + (m1 - m0) * i / (n_mels + 1));
+    for (int m = 0; m < n_mels; ++m) {
+        const double enorm = 2.0 / (mel_f[m + 2] - mel_f[m]);
+        int st = -1, cnt = 0;
+        std::vector<float> row;
+        for (int k = 0; k < W_NBIN; ++k) {
+            const double fk = k * (16000.0 / W_NFFT);
+            const double lower = (fk - mel_f[m]) / (mel_f[m + 1] - mel_f[m]);
+            const double upper = (mel_f[m + 2] - fk) / (mel_f[m + 2] - mel_f[m + 1]);
+            const double wv = fmax(0.0, fmin(lower, upper)) * enorm;
+            const float wf = (float)wv;
+            if (wf != 0.0f) {
+                if (st < 0) st = k;
+                while (st + (int)row.size() < k) row.push_back(0.0f);     // keep the run contiguous
+                row.push_back(wf);
+            }
+        }
+        cnt = (int)row.size();
+        h.start.push_back(st < 0 ? 0 : st); h.count.push_back(cnt); h.woff.push_back((int)h.w.size());
+        h.w.insert(h.w.end(), row.begin(), row.end());
+    }
+    return h;
+}
+
+extern "C" int maf_version(void) { return 1; }
+extern "C" const char* maf_last_error(void) { return g_err.c_str(); }
+
+extern "C" int maf_create(int device, maf_ctx** out) {
+    if (!out) return fail(MAF_ERR_INVALID, "maf_create: out is NULL");
+    CU(cudaSetDevice(device));
+    const double PI = 3.14159265358979323846;
+    std::vector<unsigned char> host;
+    auto put = [&](const void* p, size_t bytes) { size_t off = align_up((long long)host.size(), 256); host.resize(off + bytes); memcpy(host.data() + off, p, bytes); return off; };
+    std::vector<float> win(NFFT), winv(NFFT), win4(W_NFFT);
+    for (int i = 0; i < NFFT; ++i) { const double w = 0.5 - 0.5 * cos(2.0 * PI * i / NFFT); win[i] = (float)(w / 512.0); winv[i] = (float)(w * 0.5); }
+    for (int i = 0; i < W_NFFT; ++i) win4[i] = (float)(0.5 - 0.5 * cos(2.0 * PI * i / W_NFFT));
+    std::vector<c32> t512(512), t1024(513), t200(200), t400(201);
+    for (int e = 0; e < 512; ++e) t512[e] = mk((float)cos(2 * PI * e / 512), (float)-sin(2 * PI * e / 512));
+    for (int e = 0; e <= 512; ++e) t1024[e] = mk((float)cos(2 * PI * e / 1024), (float)-sin(2 * PI * e / 1024));
+    for (int e = 0; e < 200; ++e) t200[e] = mk((float)cos(2 * PI * e / 200), (float)-sin(2 * PI * e / 200));
+    for (int e = 0; e <= 200; ++e) t400[e] = mk((float)cos(2 * PI * e / 400), (float)-sin(2 * PI * e / 400));
+    MelHost m80 = build_mel(80), m128 = build_mel(128);
+    size_t o_win = put(win.data(), win.size() * 4), o_winv = put(winv.data(), winv.size() * 4), o_win4 = put(win4.data(), win4.size() * 4);
+    size_t o_t512 = put(t512.data(), t512.size() * 8), o_t1024 = put(t1024.data(), t1024.size() * 8);
+    size_t o_t200 = put(t200.data(), t200.size() * 8), o_t400 = put(t400.data(), t400.size() * 8);
+    size_t o80[4] = {put(m80.start.data(), 80 * 4), put(m80.count.data(), 80 * 4), put(m80.woff.data(), 80 * 4), put(m80.w.data(), m80.w.size() * 4)};
+    size_t o128[4] = {put(m128.start.data(), 128 * 4), put(m128.count.data(), 128 * 4), put(m128.woff.data(), 128 * 4), put(m128.w.data(), m128.w.size() * 4)};
+    maf_ctx* ctx = new maf_ctx();
+    ctx->device = device;
+    cudaError_t e = cudaMalloc(&ctx->blob, host.size());
+    if (e != cudaSuccess) { delete ctx; return fail(MAF_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    e = cudaMemcpy(ctx->blob, host.data(), host.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(ctx->blob); delete ctx; return fail(MAF_ERR_CUDA, std::string("cudaMemcpy: ") + cudaGetErrorString(e)); }
+    if (cudaMalloc(&ctx->scratch, 1024) != cudaSuccess) { cudaFree(ctx->blob); delete ctx; return fail(MAF_ERR_CUDA, "cudaMalloc scratch"); }
+    unsigned char* b = (unsigned char*)ctx->blob;
+    ctx->c.win1024 = (const float*)(b + o_win); ctx->c.winv1024 = (const float*)(b + o_winv); ctx->c.win400 = (const float*)(b + o_win4);
+    ctx->c.tw512 = (const c32*)(b + o_t512); ctx->c.tw1024 = (const c32*)(b + o_t1024);
+    ctx->c.tw200 = (const c32*)(b + o_t200); ctx->c.tw400 = (const c32*)(b + o_t400);
+    ctx->mel80 = MelBank{80, (const int*)(b + o80[0]), (const int*)(b + o80[1]), (const int*)(b + o80[2]), (const float*)(b + o80[3])};
+    ctx->mel128 = MelBank{128, (const int*)(b + o128[0]), (const int*)(b + o128[1]), (const int*)(b + o128[2]), (const float*)(b + o128[3])};
+    *out = ctx;
+    return MAF_OK;
+}
+
+extern "C" void maf_destroy(maf_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->blob);
+    cudaFree(ctx->scratch);
+    delete ctx;
+}
+
+// ---- plan -----------------------------------------------------------------------------------------------------
+struct WsBuf { long long off = 0, bytes = 0; };
+
+struct maf_plan {
+    maf_ctx* ctx = nullptr;
+    maf_params p{};
+    int n_items = 0, n_chunks = 0;
+    std::vector<Item> items;           // den_off = workspace den16 layout
+    std::vector<Chunk> chunks;
+    std::vector<maf_layout> layout;
+    std::vector<int> seg_fixed;        // (start, end) of the fixed noise clip per item
+    void* tables = nullptr;            // device: Item[n] (ws layout) | Item[n] (io layout) | Chunk[] | foff | fcount | Clip[n] (fixed)
+    Item* d_items = nullptr; Item* d_items_io = nullptr; Chunk* d_chunks = nullptr;
+    long long* d_foff = nullptr; int* d_fcount = nullptr; Clip* d_clips_fixed = nullptr;
+    long long total_pcm = 0, total_out = 0, total_mel = 0, total_rows = 0, total_sframes = 0, total_den = 0;
+    int total_ktiles = 0, max_chunk_frames = 0, max_sframes = 0, max_ktiles = 0, max_mel_tiles = 0, max_mel_frames = 0;
+    long long max_own = 0;
+    int frame_len = 0, frame_hop = 0, tile_len = 0, n_slices = 1;
+    bool too_short = false, sharded = false, have_noise_clips = false;
+    double target_peak = 0.0, inv_block = 0.0;
+    KWeight kw{};
+    SmoothTaps taps{};
+    WsBuf S, M, M0, bits, rowflag, T2, T2hi, nmax, partial, E, ZC, clips, seg, den16, peak, peak_norm, mel_max, sub, gates;
+    long long ws_bytes = 0;
+    long long launches = 0;
+    // host-path staging (maf_process_host)
+    cudaStream_t hstream = nullptr;
+    void* h_ws = nullptr; int16_t* h_pcm = nullptr; int16_t* h_out = nullptr; float* h_mel = nullptr; double* h_lufs = nullptr;
+    int* h_clip = nullptr; int16_t* h_noise = nullptr; long long h_noise_cap = 0;
+};
+
+static void design_kweight(double rate, KWeight& kw) {
+    const double PI = 3.141592653589793;
+    {   // high shelf: G = 4 dB, Q = 1/sqrt(2), fc = 1500 Hz
+        const double G = 4.0, Q = 1.0 / sqrt(2.0), fc = 1500.0;
+        const double A = pow(10.0, G / 40.0), w0 = 2.0 * PI * (fc / rate), alpha = sin(w0) / (2.0 * Q);
+        const double b0 = A * ((A + 1) + (A - 1) * cos(w0) + 2 * sqrt(A) * alpha);
+        const double b1 = -2 * A * ((A - 1) + (A + 1) * cos(w0));
+        const double b2 = A * ((A + 1) + (A - 1) * cos(w0) - 2 * sqrt(A) * alpha);
+        const double a0 = (A + 1) - (A - 1) * cos(w0) + 2 * sqrt(A) * alpha;
+        const double a1 = 2 * ((A - 1) - (A + 1) * cos(w0));
+        const double a2 = (A + 1) - (A - 1) * cos(w0) - 2 * sqrt(A) * alpha;
+        kw.b1[0] = b0 / a0; kw.b1[1] = b1 / a0; kw.b1[2] = b2 / a0; kw.a1[0] = 1.0; kw.a1[1] = a1 / a0; kw.a1[2] = a2 / a0;
+    }
+    {   // high pass: G = 0, Q = 0.5, fc = 38 Hz
+        const double Q = 0.5, fc = 38.0;
+        const double w0 = 2.0 * PI * (fc / rate), alpha = sin(w0) / (2.0 * Q);
+        const double b0 = (1 + cos(w0)) / 2, b1 = -(1 + cos(w0)), b2 = (1 + cos(w0)) / 2;
+        const double a0 = 1 + alpha, a1 = -2 * cos(w0), a2 = 1 - alpha;
+        kw.b2[0] = b0 / a0; kw.b2[1] = b1 / a0; kw.b2[2] = b2 / a0; kw.a2[0] = 1.0; kw.a2[1] = a1 / a0; kw.a2[2] = a2 / a0;
+    }
+}
+
+static int design_taps(int sr, SmoothTaps& t) {
+    // noisereduce: n_grad_freq = int(500 / (sr / (n_fft / 2))), n_grad_time = int(50 / ((hop / sr) * 1000))
+    const int nf = (int)(500.0 / ((double)sr / (NFFT / 2)));
+    const int nt = (int)(50.0 / (((double)HOP / sr) * 1000.0));
+    if (nf > MAX_NF || nt > MAX_NT || nf < 0 || nt < 0) return -1;
+    // concat(linspace(0, 1, n + 1, endpoint=False), linspace(1, 0, n + 2))[1:-1], normalised per axis
+    auto tri = [](int n, float* out) {
+        std::vector<double> v;
+        for (int i = 1; i <= n; ++i) v.push_back((double)i / (n + 1));
+        for (int i = 0; i <= n; ++i) v.push_back(1.0 - (double)i / (n + 1));
+        double s = 0; for (double x : v) s += x;
+        for (size_t i = 0; i < v.size(); ++i) out[i] = (float)(v[i] / s);
+    };
+    t.nf = nf; t.nt = nt;
+    memset(t.vf, 0, sizeof(t.vf)); memset(t.vt, 0, sizeof(t.vt));
+    tri(nf, t.vf); tri(nt, t.vt);
+    return 0;
+}
+
+static WsBuf carve(long long& cursor, long long bytes) {
+    WsBuf b; b.off = align_up(cursor, 256); b.bytes = bytes; cursor = b.off + bytes; return b;
+}
+
+extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf_item_desc* descs, int32_t n_items, maf_plan** out) {
+    if (!ctx || !params || !descs || !out || n_items <= 0) return fail(MAF_ERR_INVALID, "maf_plan_create: bad argument");
+    const maf_params& p = *params;
+    if (p.sample_rate < 4000 || p.sample_rate > 96000) return fail(MAF_ERR_INVALID, "sample_rate out of range");
+    if (p.n_mels != 0 && p.n_mels != 80 && p.n_mels != 128) return fail(MAF_ERR_INVALID, "n_mels must be 0, 80 or 128");
+    if (p.n_mels && p.sample_rate != 16000) return fail(MAF_ERR_UNSUPPORTED, "Whisper log-mel is defined at 16 kHz");
+    if (p.mel_padding < 0 || (p.mel_padding > 0 && p.mel_padding < W_HOP)) return fail(MAF_ERR_INVALID, "mel_padding must be 0 or >= 160");
+    CU(cudaSetDevice(ctx->device));
+    maf_plan* pl = new maf_plan();
+    pl->ctx = ctx; pl->p = p; pl->n_items = n_items;
+    if (design_taps(p.sample_rate, pl->taps)) { delete pl; return fail(MAF_ERR_UNSUPPORTED, "smoothing taps exceed kernel limits for this rate"); }
+    design_kweight((double)p.sample_rate, pl->kw);
+    pl->target_peak = 32768.0 * pow(10.0, -0.1 / 20.0);
+    pl->inv_block = 1.0 / (0.4 * (double)p.sample_rate);
+    pl->frame_len = (int)(p.sample_rate * 0.025);
+    pl->frame_hop = (int)(p.sample_rate * 0.010);
+    if (pl->frame_len >= 2048) { delete pl; return fail(MAF_ERR_UNSUPPORTED, "frame length too large for the ZCR histogram"); }
+    pl->tile_len = (int)(0.4 * (1 * 0.25) * (double)p.sample_rate);
+    std::vector<Clip> fixed(n_items);
+    std::vector<long long> foff(n_items); std::vector<int> fcount(n_items);
+    long long pcm_cur = 0, out_cur = 0, den_cur = 0, mel_cur = 0, row_cur = 0, sf_cur = 0; int kt_cur = 0;
+    for (int i = 0; i < n_items; ++i) {
+        const maf_item_desc& d = descs[i];
+        const bool whole = d.g0 == 0 && d.own_len == d.n_global;
+        if (d.own_len <= 0 || d.n_global <= 0 || d.origin < 0 || d.origin + d.own_len > d.buf_len || d.g0 < 0 || d.g0 + d.own_len > d.n_global)
+            { delete pl; return fail(MAF_ERR_INVALID, "maf_plan_create: inconsistent item descriptor"); }
+        if (d.n_global > 2000000000LL) { delete pl; return fail(MAF_ERR_UNSUPPORTED, "recordings above 2^31 samples are not supported"); }
+        if (!whole) {
+            pl->sharded = true;
+            if (d.n_global <= CHUNK || d.g0 % CHUNK != 0 || (d.g0 + d.own_len != d.n_global && d.own_len % CHUNK != 0))
+                { delete pl; return fail(MAF_ERR_INVALID, "time shards must be whole 600000-sample chunks of a multi-chunk recording"); }
+            if (d.g0 % pl->frame_hop != 0 || d.g0 % W_HOP != 0 || d.g0 % pl->tile_len != 0)
+                { delete pl; return fail(MAF_ERR_UNSUPPORTED, "shard boundary is not aligned to the frame / block hops at this rate"); }
+        }
+        Item it{};
+        it.pcm_off = pcm_cur; pcm_cur += align_up(d.buf_len, 8);
+        it.buf_len = d.buf_len; it.origin = d.origin; it.own_len = d.own_len; it.g0 = d.g0; it.n_global = d.n_global;
+        it.lo_avail = whole ? 0 : d.lo_avail; it.hi_avail = whole ? 0 : d.hi_avail;
+        if (it.lo_avail > KW_WARM || it.hi_avail > KW_WARM || it.lo_avail < 0 || it.hi_avail < 0)
+            { delete pl; return fail(MAF_ERR_INVALID, "halo larger than 2048 samples"); }
+        it.den_off = den_cur + KW_WARM; den_cur += align_up(d.own_len + 2 * KW_WARM, 8);
+        maf_layout lay{}; lay.pcm_off = it.pcm_off; lay.out_off = out_cur; out_cur += align_up(d.own_len, 8);
+        it.out_off = lay.out_off;
+        // denoise chunks
+        it.chunk_first = (int)pl->chunks.size();
+        const bool multi = d.n_global > CHUNK;
+        const int nch = multi ? (int)((d.own_len + CHUNK - 1) / CHUNK) : 1;
+        it.n_chunks = nch;
+        for (int k = 0; k < nch; ++k) {
+            Chunk c{};
+            c.item = i;
+            c.L = multi ? CHUNK + 2 * PADS : (int)d.n_global + 2 * PADS;
+            c.n_frames = c.L / HOP + 1;
+            c.keep = multi ? (int)std::min<long long>(CHUNK, d.own_len - (long long)k * CHUNK) : (int)d.n_global;
+            c.s_local = d.origin + (long long)k * CHUNK;
+            c.row0 = row_cur; row_cur += c.n_frames;
+            c.out_off = (long long)k * CHUNK;
+            pl->chunks.push_back(c);
+            pl->max_chunk_frames = std::max(pl->max_chunk_frames, c.n_frames);
+        }
+        // S0 frames
+        {
+            const long long Fg = d.n_global >= pl->frame_len ? (d.n_global - pl->frame_len) / pl->frame_hop + 1 : 0;
+            const long long first = (d.g0 + pl->frame_hop - 1) / pl->frame_hop;
+            const long long last = std::min<long long>(Fg, (d.g0 + d.own_len + pl->frame_hop - 1) / pl->frame_hop);
+            it.n_sframes = (int)std::max<long long>(0, last - first);
+            it.sframe_off = sf_cur; sf_cur += it.n_sframes;
+            if (it.n_sframes > 0 && d.origin + (long long)(it.n_sframes - 1) * pl->frame_hop + pl->frame_len > d.buf_len)
+                { delete pl; return fail(MAF_ERR_INVALID, "item buffer lacks the right halo needed by the noise detector"); }
+            foff[i] = it.sframe_off; fcount[i] = it.n_sframes;
+            pl->max_sframes = std::max(pl->max_sframes, it.n_sframes);
+        }
+        // fixed noise clip: first noise_sample_duration_s of the recording (preprocessor.py:189-197)
+        {
+            long long len = std::min<long long>((long long)(p.sample_rate * (double)p.noise_sample_duration_s), d.n_global);
+            if (len > CHUNK) len = CHUNK;
+            fixed[i].start = it.pcm_off + d.origin - d.g0;       // absolute offset in the pcm array of global sample 0
+            fixed[i].len = (int)len; fixed[i].n_frames = (int)(len / HOP) + 1;
+            pl->seg_fixed.push_back(0); pl->seg_fixed.push_back((int)len);
+        }
+        // loudness tiles / blocks
+        {
+            it.ktile_first = kt_cur;
+            it.n_ktiles = (int)((d.own_len + pl->tile_len - 1) / pl->tile_len);
+            kt_cur += it.n_ktiles;
+            pl->max_ktiles = std::max(pl->max_ktiles, it.n_ktiles);
+            const double T = (double)d.n_global / (double)p.sample_rate;
+            if ((double)d.n_global < 0.4 * (double)p.sample_rate) { pl->too_short = true; it.n_blocks = 0; }
+            else {
+                const long long nb = (long long)(nearbyint((T - 0.4) / (0.4 * 0.25)) + 1);
+                it.n_blocks = (int)nb;
+                for (long long j = 0; j < nb; ++j) {       // the tile decomposition needs pyloudnorm's bounds to be regular
+                    const long long l = (long long)(0.4 * (j * 0.25) * (double)p.sample_rate);
+                    const long long u = (long long)(0.4 * (j * 0.25 + 1) * (double)p.sample_rate);
+                    if (l != j * pl->tile_len || u != l + 4LL * pl->tile_len)
+                        { delete pl; return fail(MAF_ERR_UNSUPPORTED, "irregular loudness block grid at this rate / length"); }
+                }
+            }
+        }
+        // log-mel frames
+        if (p.n_mels) {
+            it.mel_frames_global = (int)((d.n_global + p.mel_padding) / W_HOP);
+            it.mel_f0 = (int)(d.g0 / W_HOP);
+            const bool last = d.g0 + d.own_len == d.n_global;
+            it.mel_frames = last ? it.mel_frames_global - it.mel_f0 : (int)(d.own_len / W_HOP);
+            if (d.n_global + p.mel_padding <= W_NFFT / 2) { delete pl; return fail(MAF_ERR_TOO_SHORT, "recording too short for reflect padding"); }
+            it.mel_off = mel_cur; mel_cur += align_up((long long)p.n_mels * it.mel_frames, 4);
+            pl->max_mel_frames = std::max(pl->max_mel_frames, it.mel_frames);
+            pl->max_mel_tiles = std::max(pl->max_mel_tiles, (it.mel_frames + MEL_TILE - 1) / MEL_TILE);
+        }
+        lay.mel_off = it.mel_off; lay.mel_frames = it.mel_frames; lay.n_chunks = nch;
+        pl->max_own = std::max<long long>(pl->max_own, d.own_len);
+        pl->items.push_back(it); pl->layout.push_back(lay);
+    }
+    pl->n_chunks = (int)pl->chunks.size();
+    pl->total_pcm = pcm_cur; pl->total_out = out_cur; pl->total_mel = mel_cur; pl->total_rows = row_cur;
+    pl->total_sframes = sf_cur; pl->total_den = den_cur; pl->total_ktiles = kt_cur;
+    pl->n_slices = std::max(1, std::min(32, (592 + n_items - 1) / n_items));
+    // workspace layout
+    long long cur = 0;
+    pl->S = carve(cur, pl->total_rows * S_PITCH * (long long)sizeof(c32));
+    pl->M = carve(cur, pl->total_rows * M_PITCH * 4LL);
+    pl->M0 = carve(cur, p.stationary ? 0 : pl->total_rows * M_PITCH * 4LL);
+    pl->bits = carve(cur, p.stationary ? pl->total_rows * B_PITCH * 4LL : 0);
+    pl->rowflag = carve(cur, (long long)pl->n_chunks * M_PITCH);
+    pl->T2 = carve(cur, (long long)n_items * T_PITCH * 4);
+    pl->T2hi = carve(cur, (long long)n_items * T_PITCH * 4);
+    pl->nmax = carve(cur, (long long)n_items * T_PITCH * 4);
+    pl->partial = carve(cur, (long long)n_items * pl->n_slices * 4 * 2 * T_PITCH * 8);
+    pl->E = carve(cur, std::max<long long>(1, pl->total_sframes) * 4);
+    pl->ZC = carve(cur, std::max<long long>(1, pl->total_sframes) * 4);
+    pl->clips = carve(cur, (long long)n_items * sizeof(Clip));
+    pl->seg = carve(cur, (long long)n_items * 2 * 4);
+    pl->den16 = carve(cur, pl->total_den * 2);
+    pl->peak = carve(cur, (long long)n_items * 4);
+    pl->peak_norm = carve(cur, (long long)n_items * 4);
+    pl->mel_max = carve(cur, (long long)n_items * 4);
+    pl->sub = carve(cur, std::max(1, pl->total_ktiles) * 8LL);
+    pl->gates = carve(cur, (long long)n_items * sizeof(Gate));
+    pl->ws_bytes = align_up(cur, 256);
+    // device tables
+    std::vector<Item> io = pl->items;
+    for (int i = 0; i < n_items; ++i) { io[i].den_off = io[i].pcm_off + io[i].origin; io[i].lo_avail = 0; io[i].hi_avail = 0; }
+    std::vector<unsigned char> host;
+    auto put = [&](const void* ptr, size_t bytes) { size_t off = align_up((long long)host.size(), 256); host.resize(off + bytes); memcpy(host.data() + off, ptr, bytes); return off; };
+    const size_t o_it = put(pl->items.data(), sizeof(Item) * n_items), o_io = put(io.data(), sizeof(Item) * n_items);
+    const size_t o_ch = put(pl->chunks.data(), sizeof(Chunk) * pl->chunks.size());
+    const size_t o_fo = put(foff.data(), 8 * n_items), o_fc = put(fcount.data(), 4 * n_items), o_cl = put(fixed.data(), sizeof(Clip) * n_items);
+    cudaError_t e = cudaMalloc(&pl->tables, host.size());
+    if (e == cudaSuccess) e = cudaMemcpy(pl->tables, host.data(), host.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { if (pl->tables) cudaFree(pl->tables); delete pl; return fail(MAF_ERR_CUDA, std::string("plan tables: ") + cudaGetErrorString(e)); }
+    unsigned char* b = (unsigned char*)pl->tables;
+    pl->d_items = (Item*)(b + o_it); pl->d_items_io = (Item*)(b + o_io); pl->d_chunks = (Chunk*)(b + o_ch);
+    pl->d_foff = (long long*)(b + o_fo); pl->d_fcount = (int*)(b + o_fc); pl->d_clips_fixed = (Clip*)(b + o_cl);
+    *out = pl;
+    return MAF_OK;
+}
+
+extern "C" void maf_plan_destroy(maf_plan* pl) {
+    if (!pl) return;
+    cudaSetDevice(pl->ctx->device);
+    if (pl->hstream) { cudaStreamSynchronize(pl->hstream); cudaStreamDestroy(pl->hstream); }
+    cudaFree(pl->tables); cudaFree(pl->h_ws); cudaFree(pl->h_pcm); cudaFree(pl->h_out); cudaFree(pl->h_mel); cudaFree(pl->h_lufs);
+    cudaFree(pl->h_clip); cudaFree(pl->h_noise);
+    delete pl;
+}
+
+extern "C" size_t maf_plan_workspace_bytes(const maf_plan* pl) { return pl ? (size_t)pl->ws_bytes : 0; }
+extern "C" int maf_plan_layout(const maf_plan* pl, int32_t item, maf_layout* out) {
+    if (!pl || !out || item < 0 || item >= pl->n_items) return fail(MAF_ERR_INVALID, "maf_plan_layout: bad argument");
+    *out = pl->layout[item];
+    return MAF_OK;
+}
+extern "C" int64_t maf_plan_total_pcm(const maf_plan* pl) { return pl ? pl->total_pcm : 0; }
+extern "C" int64_t maf_plan_total_out(const maf_plan* pl) { return pl ? pl->total_out : 0; }
+extern "C" int64_t maf_plan_total_mel(const maf_plan* pl) { return pl ? pl->total_mel : 0; }
+extern "C" int64_t maf_plan_launches(const maf_plan* pl) { return pl ? pl->launches : 0; }
+extern "C" int64_t maf_plan_den_offset(const maf_plan* pl, int32_t item) {
+    return (pl && item >= 0 && item < pl->n_items) ? pl->items[item].den_off : -1;
+}
+extern "C" int maf_plan_buffer(const maf_plan* pl, const char* name, int64_t* off, int64_t* size) {
+    if (!pl || !name || !off || !size) return fail(MAF_ERR_INVALID, "maf_plan_buffer: bad argument");
+    const WsBuf* b = nullptr;
+    if (!strcmp(name, "peak")) b = &pl->peak; else if (!strcmp(name, "peak_norm")) b = &pl->peak_norm;
+    else if (!strcmp(name, "mel_max")) b = &pl->mel_max; else if (!strcmp(name, "sub_energy")) b = &pl->sub;
+    else if (!strcmp(name, "den16")) b = &pl->den16; else if (!strcmp(name, "gates")) b = &pl->gates;
+    else if (!strcmp(name, "T2")) b = &pl->T2; else if (!strcmp(name, "seg")) b = &pl->seg;
+    if (!b) return fail(MAF_ERR_INVALID, std::string("maf_plan_buffer: unknown buffer ") + name);
+    *off = b->off; *size = b->bytes;
+    return MAF_OK;
+}
+
+extern "C" int maf_set_noise_clips(maf_plan* pl, const int64_t* offsets, const int32_t* lengths) {
+    if (!pl || !offsets || !lengths) return fail(MAF_ERR_INVALID, "maf_set_noise_clips: bad argument");
+    CU(cudaSetDevice(pl->ctx->device));
+    std::vector<Clip> cl(pl->n_items);
+    for (int i = 0; i < pl->n_items; ++i) {
+        if (lengths[i] <= 0 || offsets[i] < 0) return fail(MAF_ERR_INVALID, "maf_set_noise_clips: empty clip");
+        const int len = std::min<int>(lengths[i], CHUNK);
+        cl[i].start = offsets[i]; cl[i].len = len; cl[i].n_frames = len / HOP + 1;
+    }
+    CU(cudaMemcpy(pl->d_clips_fixed, cl.data(), sizeof(Clip) * pl->n_items, cudaMemcpyHostToDevice));
+    pl->have_noise_clips = true;
+    return MAF_OK;
+}
+
+// ---- helpers ----------------------------------------------------------------------------------------------------
+template <typename T> static T* ws_ptr(void* ws, const WsBuf& b) { return reinterpret_cast<T*>(static_cast<unsigned char*>(ws) + b.off); }
+
+__global__ void fill_int_kernel(int* p, int n, int v) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+__global__ void abs_max_kernel(const int16_t* __restrict__ x, const Item* __restrict__ items, int* __restrict__ peak) {
+    const Item it = items[blockIdx.y];
+    int pk = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < it.own_len; i += (long long)gridDim.x * blockDim.x) {
+        const int s = x[it.den_off + i];
+        pk = max(pk, s < 0 ? -s : s);
+    }
+    for (int o = 16; o > 0; o >>= 1) pk = max(pk, __shfl_xor_sync(0xffffffffu, pk, o));
+    if ((threadIdx.x & 31) == 0 && pk > 0) atomicMax(&peak[blockIdx.y], pk);
+}
+__global__ void gather_lufs_kernel(const Gate* __restrict__ g, int n, double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = g[i].lufs;
+}
+
+static const MelBank& pick_mel(const maf_plan* pl) { return pl->p.n_mels == 128 ? pl->ctx->mel128 : pl->ctx->mel80; }
+
+// S0 + thresholds + K1..K3.  `den_dst` receives the truncated int16 signal (workspace den16 layout, or the caller's
+// output layout when to_out), the per-item peak lands in the workspace.
+static int run_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pcm, void* ws, int16_t* den_dst, int to_out, float* out_f32,
+                       cudaStream_t st) {
+    const maf_params& p = pl->p;
+    const int n = pl->n_items;
+    Clip* clips = ws_ptr<Clip>(ws, pl->clips);
+    CU(cudaMemsetAsync(ws_ptr<int>(ws, pl->peak), 0, 4LL * n, st));
+    if (p.stationary) {
+        const int16_t* noise_src = pcm;
+        const Clip* use_clips = clips;
+        if (p.external_noise) {
+            if (!pl->have_noise_clips || !noise_pcm) return fail(MAF_ERR_INVALID, "external_noise set but no noise clips / noise pcm supplied");
+            noise_src = noise_pcm; use_clips = pl->d_clips_fixed;
+        } else if (p.auto_detect_noise) {
+            if (pl->sharded) return fail(MAF_ERR_INVALID, "sharded plans need external noise clips (run maf_frame_stats / maf_select_clip first)");
+            launch_frame_stats(pcm, pl->d_items, n, pl->max_sframes, pl->frame_len, pl->frame_hop, ws_ptr<float>(ws, pl->E), ws_ptr<int>(ws, pl->ZC), st);
+            const int fallback = (int)(p.sample_rate * (double)p.noise_sample_duration_s);
+            launch_select_clip(ws_ptr<float>(ws, pl->E), ws_ptr<int>(ws, pl->ZC), pl->d_foff, pl->d_fcount, pl->d_items, n, pl->frame_len,
+                               pl->frame_hop, p.sample_rate, fallback, clips, ws_ptr<int>(ws, pl->seg), st);
+            pl->launches += 2;
+        } else {
+            if (pl->sharded) return fail(MAF_ERR_INVALID, "sharded plans need external noise clips");
+            use_clips = pl->d_clips_fixed;
+            CU(cudaMemcpyAsync(ws_ptr<int>(ws, pl->seg), pl->seg_fixed.data(), 8LL * n, cudaMemcpyHostToDevice, st));
+        }
+        launch_noise_threshold(noise_src, use_clips, n, pl->n_slices, pl->ctx->c, ws_ptr<unsigned>(ws, pl->nmax),
+                               ws_ptr<double>(ws, pl->partial), ws_ptr<float>(ws, pl->T2), ws_ptr<float>(ws, pl->T2hi), 1.5, st);
+        pl->launches += 3;
+        CU(cudaMemsetAsync(ws_ptr<uint8_t>(ws, pl->rowflag), 0, pl->rowflag.bytes, st));
+    }
+    launch_stft(pcm, pl->d_items, pl->d_chunks, pl->n_chunks, pl->max_chunk_frames, pl->ctx->c, p.stationary, ws_ptr<float>(ws, pl->T2),
+                ws_ptr<float>(ws, pl->T2hi), ws_ptr<c32>(ws, pl->S), ws_ptr<uint32_t>(ws, pl->bits), ws_ptr<uint8_t>(ws, pl->rowflag), st);
+    pl->launches += 1;
+    if (!p.stationary) {
+        // noisereduce non-stationary defaults: time_constant_s = 2.0, thresh_n_mult = 2, sigmoid_slope = 10
+        const double t = 2.0 * p.sample_rate / HOP;
+        const double b = (sqrt(1.0 + 4.0 * t * t) - 1.0) / (2.0 * t * t);
+        launch_ns_mask(ws_ptr<c32>(ws, pl->S), pl->d_chunks, pl->n_chunks, b, 2.0f, 10.0f, ws_ptr<float>(ws, pl->M0), st);
+        pl->launches += 1;
+    }
+    launch_smooth_mask(ws_ptr<uint32_t>(ws, pl->bits), ws_ptr<uint8_t>(ws, pl->rowflag), ws_ptr<float>(ws, pl->M0), pl->d_chunks, pl->n_chunks,
+                       pl->max_chunk_frames, p.stationary, p.prop_decrease, pl->taps, ws_ptr<float>(ws, pl->M), st);
+    launch_istft(ws_ptr<c32>(ws, pl->S), ws_ptr<float>(ws, pl->M), pl->d_items, pl->d_chunks, pl->n_chunks, pl->ctx->c,
+                 den_dst, to_out, out_f32, ws_ptr<int>(ws, pl->peak), st);
+    pl->launches += 2;
+    CU(cudaGetLastError());
+    return MAF_OK;
+}
+
+static int run_loudness_stats(maf_plan* pl, const int16_t* src, const Item* items, int peak_normalize, void* ws, cudaStream_t st) {
+    if (pl->too_short) return fail(MAF_ERR_TOO_SHORT, "Audio must have length greater than the block size");
+    const int n = pl->n_items;
+    CU(cudaMemsetAsync(ws_ptr<int>(ws, pl->peak_norm), 0, 4LL * n, st));
+    launch_kweight_energy(src, items, n, pl->max_ktiles, pl->tile_len, pl->kw, peak_normalize, pl->target_peak, ws_ptr<int>(ws, pl->peak),
+                          ws_ptr<double>(ws, pl->sub), ws_ptr<int>(ws, pl->peak_norm), st);
+    pl->launches += 1;
+    CU(cudaGetLastError());
+    return MAF_OK;
+}
+
+static int run_gate(maf_plan* pl, const Item* items, void* ws, cudaStream_t st) {
+    launch_gate(ws_ptr<double>(ws, pl->sub), items, pl->n_items, pl->inv_block, (double)pl->p.target_lufs, ws_ptr<int>(ws, pl->peak_norm),
+                ws_ptr<Gate>(ws, pl->gates), st);
+    pl->launches += 1;
+    CU(cudaGetLastError());
+    return MAF_OK;
+}
+
+static int run_logmel(maf_plan* pl, const int16_t* src, const Item* items, int peak_normalize, const Gate* gates, void* ws, int16_t* out16,
+                      float* mel, bool finalize, cudaStream_t st) {
+    const int n = pl->n_items;
+    fill_int_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws_ptr<int>(ws, pl->mel_max), n, (int)0x80000001);
+    launch_logmel(src, items, n, pl->max_mel_tiles, pl->ctx->c, pick_mel(pl), pl->p.mel_padding, peak_normalize, pl->target_peak,
+                  ws_ptr<int>(ws, pl->peak), gates, out16, mel, ws_ptr<int>(ws, pl->mel_max), st);
+    pl->launches += 2;
+    if (finalize) {
+        launch_mel_finalize(mel, items, n, pl->p.n_mels, pl->max_mel_frames, ws_ptr<int>(ws, pl->mel_max), st);
+        pl->launches += 1;
+    }
+    CU(cudaGetLastError());
+    return MAF_OK;
+}
+
+extern "C" int maf_process(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pcm, void* ws, int16_t* out_pcm, float* mel,
+                           double* lufs, int32_t* clip, void* stream) {
+    if (!pl || !pcm || !ws || !out_pcm) return fail(MAF_ERR_INVALID, "maf_process: NULL argument");
+    if (pl->p.n_mels && !mel) return fail(MAF_ERR_INVALID, "maf_process: mel_dev is NULL but n_mels > 0");
+    if (pl->sharded) return fail(MAF_ERR_INVALID, "maf_process: sharded plans use the maf_sharded_* stages");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(pl->ctx->device));
+    int16_t* den16 = ws_ptr<int16_t>(ws, pl->den16);
+    int rc = run_denoise(pl, pcm, noise_pcm, ws, den16, 0, nullptr, st);
+    if (rc) return rc;
+    rc = run_loudness_stats(pl, den16, pl->d_items, pl->p.peak_normalize, ws, st);
+    if (rc) return rc;
+    rc = run_gate(pl, pl->d_items, ws, st);
+    if (rc) return rc;
+    const Gate* gates = ws_ptr<Gate>(ws, pl->gates);
+    if (pl->p.n_mels) {
+        rc = run_logmel(pl, den16, pl->d_items, pl->p.peak_normalize, gates, ws, out_pcm, mel, true, st);
+        if (rc) return rc;
+    } else {
+        launch_apply_gain(den16, pl->d_items, pl->n_items, pl->max_own, pl->p.peak_normalize, pl->target_peak, ws_ptr<int>(ws, pl->peak), gates, 1,
+                          out_pcm, st);
+        pl->launches += 1;
+    }
+    if (lufs) { gather_lufs_kernel<<<(pl->n_items + 255) / 256, 256, 0, st>>>(gates, pl->n_items, lufs); pl->launches += 1; }
+    if (clip && pl->p.stationary) CU(cudaMemcpyAsync(clip, ws_ptr<int>(ws, pl->seg), 8LL * pl->n_items, cudaMemcpyDeviceToDevice, st));
+    CU(cudaGetLastError());
+    return MAF_OK;
+}
+
+extern "C" int maf_process_host(maf_plan* pl, const int16_t* pcm_host, const int16_t* noise_host, int64_t noise_len, int16_t* out_host,
+                                float* mel_host, double* lufs_host, int32_t* clip_host) {
+    if (!pl || !pcm_host || !out_host) return fail(MAF_ERR_INVALID, "maf_process_host: NULL argument");
+    CU(cudaSetDevice(pl->ctx->device));
+    if (!pl->hstream) {
+        CU(cudaStreamCreateWithFlags(&pl->hstream, cudaStreamNonBlocking));
+        CU(cudaMalloc(&pl->h_ws, pl->ws_bytes));
+        CU(cudaMalloc((void**)&pl->h_pcm, 2 * std::max<long long>(8, pl->total_pcm)));
+        CU(cudaMalloc((void**)&pl->h_out, 2 * std::max<long long>(8, pl->total_out)));
+        CU(cudaMalloc((void**)&pl->h_mel, 4 * std::max<long long>(4, pl->total_mel)));
+        CU(cudaMalloc((void**)&pl->h_lufs, 8LL * pl->n_items));
+        CU(cudaMalloc((void**)&pl->h_clip, 8LL * pl->n_items));
+        CU(cudaMemsetAsync(pl->h_clip, 0, 8LL * pl->n_items, pl->hstream));
+    }
+    cudaStream_t st = pl->hstream;
+    if (noise_host && noise_len > 0) {
+        if (noise_len > pl->h_noise_cap) { cudaFree(pl->h_noise); pl->h_noise = nullptr; CU(cudaMalloc((void**)&pl->h_noise, 2 * noise_len)); pl->h_noise_cap = noise_len; }
+        CU(cudaMemcpyAsync(pl->h_noise, noise_host, 2 * noise_len, cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaMemcpyAsync(pl->h_pcm, pcm_host, 2 * pl->total_pcm, cudaMemcpyHostToDevice, st));
+    int rc = maf_process(pl, pl->h_pcm, (noise_host && noise_len > 0) ? pl->h_noise : nullptr, pl->h_ws, pl->h_out, pl->p.n_mels ? pl->h_mel : nullptr,
+                         pl->h_lufs, pl->h_clip, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_host, pl->h_out, 2 * pl->total_out, cudaMemcpyDeviceToHost, st));
+    if (mel_host && pl->p.n_mels) CU(cudaMemcpyAsync(mel_host, pl->h_mel, 4 * pl->total_mel, cudaMemcpyDeviceToHost, st));
+    if (lufs_host) CU(cudaMemcpyAsync(lufs_host, pl->h_lufs, 8LL * pl->n_items, cudaMemcpyDeviceToHost, st));
+    if (clip_host) CU(cudaMemcpyAsync(clip_host, pl->h_clip, 8LL * pl->n_items, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return MAF_OK;
+}
+
+// ---- stage entry points ---------------------------------------------------------------------------------------
+extern "C" int maf_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pcm, void* ws, int16_t* out_pcm, float* out_f32,
+                           int32_t* clip, void* stream) {
+    if (!pl || !pcm || !ws || !out_pcm) return fail(MAF_ERR_INVALID, "maf_denoise: NULL argument");
+    if (pl->sharded) return fail(MAF_ERR_INVALID, "maf_denoise: sharded plans use maf_sharded_denoise");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(pl->ctx->device));
+    int rc = run_denoise(pl, pcm, noise_pcm, ws, out_pcm, 1, out_f32, st);
+    if (rc) return rc;
+    if (clip && pl->p.stationary) CU(cudaMemcpyAsync(clip, ws_ptr<int>(ws, pl->seg), 8LL * pl->n_items, cudaMemcpyDeviceToDevice, st));
+    return MAF_OK;
+}
+
+extern "C" int maf_peak_normalize(maf_plan* pl, const int16_t* pcm, void* ws, int16_t* out_pcm, void* stream) {
+    if (!pl || !pcm || !ws || !out_pcm) return fail(MAF_ERR_INVALID, "maf_peak_normalize: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(pl->ctx->device));
+    CU(cudaMemsetAsync(ws_ptr<int>(ws, pl->peak), 0, 4LL * pl->n_items, st));
+    long long bx = std::max<long long>(1, std::min<long long>(1024, (pl->max_own + 4095) / 4096));
+    dim3 grid((unsigned)bx, pl->n_items);
+    abs_max_kernel<<<grid, 256, 0, st>>>(pcm, pl->d_items_io, ws_ptr<int>(ws, pl->peak));
+    launch_apply_gain(pcm, pl->d_items_io, pl->n_items, pl->max_own, 1, pl->target_peak, ws_ptr<int>(ws, pl->peak), nullptr, 0, out_pcm, st);
+    pl->launches += 2;
+    CU(cudaGetLastError());
+    return MAF_OK;
+}
+
+extern "C" int maf_loudness(maf_plan* pl, const int16_t* pcm, void* ws, int16_t* out_pcm, double* lufs, void* stream) {
+    if (!pl || !pcm || !ws || !out_pcm) return fail(MAF_ERR_INVALID, "maf_loudness: NULL argument");
+    if (pl->sharded) return fail(MAF_ERR_INVALID, "maf_loudness: sharded plans use maf_sharded_energy / maf_gate");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(pl->ctx->device));
+    int rc = run_loudness_stats(pl, pcm, pl->d_items_io, 0, ws, st);
+    if (rc) return rc;
+    rc = run_gate(pl, pl->d_items_io, ws, st);
+    if (rc) return rc;
+    const Gate* gates = ws_ptr<Gate>(ws, pl->gates);
+    launch_apply_gain(pcm, pl->d_items_io, pl->n_items, pl->max_own, 0, pl->target_peak, nullptr, gates, 1, out_pcm, st);
+    pl->launches += 1;
+    if (lufs) { gather_lufs_kernel<<<(pl->n_items + 255) / 256, 256, 0, st>>>(gates, pl->n_items, lufs); pl->launches += 1; }
+    CU(cudaGetLastError());
+    return MAF_OK;
+}
+
+extern "C" int maf_logmel(maf_plan* pl, const int16_t* pcm, void* ws, float* mel, void* stream) {
+    if (!pl || !pcm || !ws || !mel) return fail(MAF_ERR_INVALID, "maf_logmel: NULL argument");
+    if (!pl->p.n_mels) return fail(MAF_ERR_INVALID, "maf_logmel: plan was created with n_mels = 0");
+    if (pl->sharded) return fail(MAF_ERR_INVALID, "maf_logmel: sharded plans use maf_sharded_logmel");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(pl->ctx->device));
+    return run_logmel(pl, pcm, pl->d_items_io, 0, nullptr, ws, nullptr, mel, true, st);
+}
+
+// ---- time-sharded pieces ----------------------------------------------------------------------------------------
+extern "C" int maf_frame_stats(maf_plan* pl, const int16_t* pcm, float* energy, int32_t* zc, void* stream) {
+    if (!pl || !pcm || !energy || !zc) return fail(MAF_ERR_INVALID, "maf_frame_stats: NULL argument");
+    CU(cudaSetDevice(pl->ctx->device));
+    launch_frame_stats(pcm, pl->d_items, pl->n_items, pl->max_sframes, pl->frame_len, pl->frame_hop, energy, zc, (cudaStream_t)stream);
+    pl->launches += 1;
+    CU(cudaGetLastError());
+    return MAF_OK;
+}
+
+extern "C" int maf_select_clip(maf_ctx* ctx, const float* energy, const int32_t* zc, int64_t n_frames, int64_t n_global, int32_t sr,
+                               float dur, int32_t* seg, void* stream) {
+    if (!ctx || !energy || !zc || !seg) return fail(MAF_ERR_INVALID, "maf_select_clip: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    struct { Item it; long long foff; int fcount; int pad; Clip clip; } h{};
+    h.it.n_global = n_global; h.it.own_len = n_global; h.it.buf_len = n_global;
+    h.foff = 0; h.fcount = (int)n_frames;
+    unsigned char* d = (unsigned char*)ctx->scratch;
+    CU(cudaMemcpyAsync(d, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    const int frame_len = (int)(sr * 0.025), hop = (int)(sr * 0.010);
+    launch_select_clip(energy, zc, (const long long*)(d + offsetof(decltype(h), foff)), (const int*)(d + offsetof(decltype(h), fcount)),
+                       (const Item*)d, 1, frame_len, hop, sr, (int)(sr * (double)dur), (Clip*)(d + offsetof(decltype(h), clip)), seg, st);
+    CU(cudaGetLastError());
+    return MAF_OK;
+}
+
+extern "C" int maf_sharded_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pcm, void* ws, void* stream) {
+    if (!pl || !pcm || !ws) return fail(MAF_ERR_INVALID, "maf_sharded_denoise: NULL argument");
+    CU(cudaSetDevice(pl->ctx->device));
+    return run_denoise(pl, pcm, noise_pcm, ws, ws_ptr<int16_t>(ws, pl->den16), 0, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int maf_sharded_energy(maf_plan* pl, void* ws, void* stream) {
+    if (!pl || !ws) return fail(MAF_ERR_INVALID, "maf_sharded_energy: NULL argument");
+    CU(cudaSetDevice(pl->ctx->device));
+    return run_loudness_stats(pl, ws_ptr<int16_t>(ws, pl->den16), pl->d_items, pl->p.peak_normalize, ws, (cudaStream_t)stream);
+}
+
+extern "C" int maf_gate(maf_ctx* ctx, const double* sub_energy, int64_t n_tiles, int64_t n_blocks, int32_t sr, float target_lufs,
+                        const int32_t* peak_norm, void* gate, void* stream) {
+    if (!ctx || !sub_energy || !peak_norm || !gate) return fail(MAF_ERR_INVALID, "maf_gate: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Item it{};
+    it.ktile_first = 0; it.n_ktiles = (int)n_tiles; it.n_blocks = (int)n_blocks;
+    unsigned char* d = (unsigned char*)ctx->scratch + 512;
+    CU(cudaMemcpyAsync(d, &it, sizeof(it), cudaMemcpyHostToDevice, st));
+    launch_gate(sub_energy, (const Item*)d, 1, 1.0 / (0.4 * (double)sr), (double)target_lufs, peak_norm, (Gate*)gate, st);
+    CU(cudaGetLastError());
+    return MAF_OK;
+}
+
+extern "C" int maf_sharded_logmel(maf_plan* pl, void* ws, const void* gate, int16_t* out_pcm, float* mel, void* stream) {
+    if (!pl || !ws || !gate || !mel) return fail(MAF_ERR_INVALID, "maf_sharded_logmel: NULL argument");
+    if (pl->n_items != 1) return fail(MAF_ERR_INVALID, "maf_sharded_logmel: one shard per plan");
+    CU(cudaSetDevice(pl->ctx->device));
+    return run_logmel(pl, ws_ptr<int16_t>(ws, pl->den16), pl->d_items, pl->p.peak_normalize, (const Gate*)gate, ws, out_pcm, mel, false,
+                      (cudaStream_t)stream);
+}
+
+extern "C" int maf_mel_finalize(maf_plan* pl, void* ws, float* mel, void* stream) {
+    if (!pl || !ws || !mel) return fail(MAF_ERR_INVALID, "maf_mel_finalize: NULL argument");
+    CU(cudaSetDevice(pl->ctx->device));
+    launch_mel_finalize(mel, pl->d_items, pl->n_items, pl->p.n_mels, pl->max_mel_frames, ws_ptr<int>(ws, pl->mel_max), (cudaStream_t)stream);
+    pl->launches += 1;
+    CU(cudaGetLastError());
+    return MAF_OK;
+}

@@ -1,0 +1,182 @@
+// FFT cores shared by the STFT-1024 (denoise) and STFT-400 (Whisper) kernels.
+//
+// Every routine is a per-thread step function: the kernels call the steps with a __syncthreads() between them,
+// tests/host_fft_check.cpp calls them in a loop over "thread ids" on the CPU to verify the index math against a
+// direct DFT without a GPU.  FP32 throughout (FP32 STFT/iSTFT gives 136 dB vs float64).
+//
+//   fft512_*  : 512-point complex FFT as 8 x 8 x 8 (three radix-8 register butterflies, two shared-memory
+//               exchanges), 64 threads per transform, 8 points per thread.
+//   rfft1024  : 1024-point real FFT = 512-point complex FFT of (even + i odd) + split post-pass; and its inverse.
+//   fft200_*  : 200-point complex FFT as 8 x 25 (radix-8, then 5 x 5 in registers) for the 400-point real FFT
+//               Whisper needs (400 = 2^4 5^2: radix-2/4 alone cannot produce it).
+#pragma once
+
+#if defined(__CUDACC__)
+#define MAF_HD __host__ __device__ __forceinline__
+#else
+#define MAF_HD inline
+#endif
+
+namespace maf {
+
+struct c32 { float x, y; };
+
+MAF_HD c32 mk(float x, float y) { c32 r; r.x = x; r.y = y; return r; }
+MAF_HD c32 cadd(c32 a, c32 b) { return mk(a.x + b.x, a.y + b.y); }
+MAF_HD c32 csub(c32 a, c32 b) { return mk(a.x - b.x, a.y - b.y); }
+MAF_HD c32 cmul(c32 a, c32 b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+MAF_HD c32 cconj(c32 a) { return mk(a.x, -a.y); }
+MAF_HD c32 mul_mi(c32 a) { return mk(a.y, -a.x); }      // a * (-i)
+MAF_HD c32 mul_pi(c32 a) { return mk(-a.y, a.x); }      // a * (+i)
+
+// 4-point forward DFT, natural order in and out.
+MAF_HD void fft4(c32& c0, c32& c1, c32& c2, c32& c3) {
+    c32 t0 = cadd(c0, c2), t1 = csub(c0, c2), t2 = cadd(c1, c3), t3 = mul_mi(csub(c1, c3));
+    c0 = cadd(t0, t2); c2 = csub(t0, t2); c1 = cadd(t1, t3); c3 = csub(t1, t3);
+}
+
+// 8-point forward DFT (kernel e^{-2 pi i nk/8}), natural order in and out.
+MAF_HD void fft8(c32 (&v)[8]) {
+    const float h = 0.70710678118654752440f;
+    c32 a0 = cadd(v[0], v[4]), a1 = cadd(v[1], v[5]), a2 = cadd(v[2], v[6]), a3 = cadd(v[3], v[7]);
+    c32 b0 = csub(v[0], v[4]), b1 = csub(v[1], v[5]), b2 = csub(v[2], v[6]), b3 = csub(v[3], v[7]);
+    b1 = mk((b1.x + b1.y) * h, (b1.y - b1.x) * h);          // * W8^1
+    b2 = mul_mi(b2);                                        // * W8^2
+    b3 = mk((b3.y - b3.x) * h, -(b3.x + b3.y) * h);         // * W8^3
+    fft4(a0, a1, a2, a3);
+    fft4(b0, b1, b2, b3);
+    v[0] = a0; v[2] = a1; v[4] = a2; v[6] = a3;
+    v[1] = b0; v[3] = b1; v[5] = b2; v[7] = b3;
+}
+
+// 5-point forward DFT, natural order in and out.
+MAF_HD void fft5(c32& v0, c32& v1, c32& v2, c32& v3, c32& v4) {
+    const float c1 = 0.30901699437494742410f;   // cos(2 pi/5)
+    const float c2 = -0.80901699437494742410f;  // cos(4 pi/5)
+    const float s1 = 0.95105651629515357212f;   // sin(2 pi/5)
+    const float s2 = 0.58778525229247312917f;   // sin(4 pi/5)
+    c32 p14 = cadd(v1, v4), m14 = csub(v1, v4), p23 = cadd(v2, v3), m23 = csub(v2, v3);
+    c32 r0 = mk(v0.x + p14.x + p23.x, v0.y + p14.y + p23.y);
+    c32 ra = mk(v0.x + c1 * p14.x + c2 * p23.x, v0.y + c1 * p14.y + c2 * p23.y);
+    c32 rb = mk(v0.x + c2 * p14.x + c1 * p23.x, v0.y + c2 * p14.y + c1 * p23.y);
+    // -i * (s1 m14 + s2 m23) and -i * (s2 m14 - s1 m23)
+    c32 ia = mk(s1 * m14.y + s2 * m23.y, -(s1 * m14.x + s2 * m23.x));
+    c32 ib = mk(s2 * m14.y - s1 * m23.y, -(s2 * m14.x - s1 * m23.x));
+    v0 = r0; v1 = cadd(ra, ia); v4 = csub(ra, ia); v2 = cadd(rb, ib); v3 = csub(rb, ib);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// 512-point complex FFT, 64 threads, thread t holds 8 points.  Shared scratch: FFT512_SMEM c32 per transform.
+//   in : v[m] = x[t + 64 m]
+//   out: v[d] = X[u + 64 d] with u = fft512_out_base(t)
+// tw512[e] = e^{-2 pi i e / 512}, e = 0..511.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int FFT512_SMEM = 8 * 72;
+
+MAF_HD int fft512_out_base(int t) { return (t >> 3) + 8 * (t & 7); }
+
+MAF_HD void fft512_step1(c32 (&v)[8], c32* sm, const c32* tw512, int t) {
+    fft8(v);
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        c32 w = tw512[t * p];
+        sm[p * 72 + t] = (p == 0) ? v[0] : cmul(v[p], w);
+    }
+}
+// (barrier)
+MAF_HD void fft512_step2_load(c32 (&v)[8], const c32* sm, int t) {
+    const int p = t >> 3, a = t & 7;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) v[b] = sm[p * 72 + a + 8 * b];
+}
+// (barrier)
+MAF_HD void fft512_step2_store(c32 (&v)[8], c32* sm, const c32* tw512, int t) {
+    const int p = t >> 3, a = t & 7;
+    fft8(v);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        c32 w = tw512[8 * a * c];
+        sm[p * 72 + 9 * a + c] = (c == 0) ? v[0] : cmul(v[c], w);
+    }
+}
+// (barrier)
+MAF_HD void fft512_step3(c32 (&v)[8], const c32* sm, int t) {
+    const int p = t >> 3, c = t & 7;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) v[a] = sm[p * 72 + 9 * a + c];
+    fft8(v);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Real 1024-point FFT split pass.  Z = FFT512(x[2n] + i x[2n+1]); for one pair index k in 1..255 returns
+// X[k] and X[512-k].  tw1024k = e^{-2 pi i k / 1024}.
+// ------------------------------------------------------------------------------------------------------------
+MAF_HD void rfft_split_pair(c32 zk, c32 znk, c32 tw1024k, c32& xk, c32& xnk) {
+    // E = (Z[k] + conj Z[512-k]) / 2 ; O = -i (Z[k] - conj Z[512-k]) / 2 ; X[k] = E + W^k O ; X[512-k] = conj(E - W^k O)
+    c32 e = mk(0.5f * (zk.x + znk.x), 0.5f * (zk.y - znk.y));
+    c32 d = mk(0.5f * (zk.x - znk.x), 0.5f * (zk.y + znk.y));
+    c32 o = mul_mi(d);
+    c32 wo = cmul(tw1024k, o);
+    xk = cadd(e, wo);
+    xnk = cconj(csub(e, wo));
+}
+
+// Inverse: from Hermitian X[k], X[512-k] (k in 1..255) build 2*conj(Z[k]) and 2*conj(Z[512-k]) so that a FORWARD
+// FFT512 of the result F gives x[2n] = Re F[n] / 2, x[2n+1] = -Im F[n] / 2 (unnormalised inverse; the 1/2 and the
+// synthesis window are folded into the kernel's window table).
+MAF_HD void irfft_merge_pair(c32 xk, c32 xnk, c32 tw1024k, c32& zck, c32& zcnk) {
+    // 2E = X[k] + conj X[512-k] ; 2O = (X[k] - conj X[512-k]) * conj(W^k) ; Z[k] = E + iO ; Z[512-k] = conj(E) + i conj(O)
+    c32 e2 = mk(xk.x + xnk.x, xk.y - xnk.y);
+    c32 d2 = mk(xk.x - xnk.x, xk.y + xnk.y);
+    c32 o2 = cmul(d2, cconj(tw1024k));
+    c32 zk = cadd(e2, mul_pi(o2));
+    c32 znk = cadd(cconj(e2), mul_pi(cconj(o2)));
+    zck = cconj(zk);
+    zcnk = cconj(znk);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// 200-point complex FFT as 8 x 25.  n = j + 25 m (j < 25, m < 8), k = p + 8 q (p < 8, q < 25):
+//   X[p + 8q] = sum_j W25^{jq} [ W200^{jp} sum_m x[j + 25m] W8^{mp} ]
+// step A: work item (j): 8-point FFT over m, twiddle W200^{jp}, store sm[p * 25 + j]        (25 items / transform)
+// step B: work item (p): 25-point DFT over j (5 x 5 in registers) -> X[p + 8q], q = 0..24   ( 8 items / transform)
+// tw200[e] = e^{-2 pi i e / 200}, e = 0..199.   Shared scratch: 200 c32 per transform.
+// ------------------------------------------------------------------------------------------------------------
+MAF_HD void fft200_stepA(c32 (&v)[8], c32* sm, const c32* tw200, int j) {
+    fft8(v);
+#pragma unroll
+    for (int p = 0; p < 8; ++p) sm[p * 25 + j] = (p == 0) ? v[0] : cmul(v[p], tw200[j * p]);
+}
+
+// 25-point DFT of sm[p*25 + j], j = 0..24, result X[p + 8 q] written to out[q] (q = 0..24).
+// j = j0 + 5 j1, q = q1 + 5 q0:  W25^{jq} = W25^{j0 q1} W5^{j0 q0} W5^{j1 q1}
+MAF_HD void fft200_stepB(const c32* sm, const c32* tw200, int p, c32 (&out)[25]) {
+    c32 y[25];
+#pragma unroll
+    for (int j0 = 0; j0 < 5; ++j0) {
+        c32 a0 = sm[p * 25 + j0], a1 = sm[p * 25 + j0 + 5], a2 = sm[p * 25 + j0 + 10],
+            a3 = sm[p * 25 + j0 + 15], a4 = sm[p * 25 + j0 + 20];
+        fft5(a0, a1, a2, a3, a4);                 // over j1 -> q1
+        // twiddle W25^{j0 q1} = W200^{8 j0 q1}
+        y[j0 * 5 + 0] = a0;
+        y[j0 * 5 + 1] = (j0 == 0) ? a1 : cmul(a1, tw200[8 * j0 * 1]);
+        y[j0 * 5 + 2] = (j0 == 0) ? a2 : cmul(a2, tw200[8 * j0 * 2]);
+        y[j0 * 5 + 3] = (j0 == 0) ? a3 : cmul(a3, tw200[8 * j0 * 3]);
+        y[j0 * 5 + 4] = (j0 == 0) ? a4 : cmul(a4, tw200[8 * j0 * 4]);
+    }
+#pragma unroll
+    for (int q1 = 0; q1 < 5; ++q1) {
+        c32 b0 = y[0 * 5 + q1], b1 = y[1 * 5 + q1], b2 = y[2 * 5 + q1], b3 = y[3 * 5 + q1], b4 = y[4 * 5 + q1];
+        fft5(b0, b1, b2, b3, b4);                 // over j0 -> q0
+        out[q1 + 0] = b0; out[q1 + 5] = b1; out[q1 + 10] = b2; out[q1 + 15] = b3; out[q1 + 20] = b4;
+    }
+}
+
+// Real 400-point split: Z = FFT200(x[2n] + i x[2n+1]); X[k], k = 0..200, from Z[k], Z[200-k]; tw400k = e^{-2 pi i k/400}.
+MAF_HD c32 rfft400_bin(c32 zk, c32 znk, c32 tw400k) {
+    c32 e = mk(0.5f * (zk.x + znk.x), 0.5f * (zk.y - znk.y));
+    c32 d = mk(0.5f * (zk.x - znk.x), 0.5f * (zk.y + znk.y));
+    return cadd(e, cmul(tw400k, mul_mi(d)));
+}
+
+}  // namespace maf

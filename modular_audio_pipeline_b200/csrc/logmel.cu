@@ -1,0 +1,188 @@
+// S8-S9 -- Whisper log-mel front-end (reference call site: audio_pipeline/transcriber.py:229-238 ->
+// whisper.audio.log_mel_spectrogram(audio, n_mels, padding); restated in oracle/reference_path.py).
+//
+//   logmel_kernel        K5: loudness gain / limiter / int16 truncation fused into the load (the final PCM is written
+//                        on the way), reflect-centred STFT 400 / hop 160 with a periodic Hann window as a 200-point
+//                        complex FFT (8 x 25: radix-8 then 5 x 5 in registers) + real split, power spectrum,
+//                        sparse Slaney mel projection, log10(max(., 1e-10)); per-recording running maximum.
+//                        The spectrum never leaves shared memory.
+//   mel_finalize_kernel  max(L, gmax - 8), (L + 4) / 4 in place once the recording-wide maximum is known.
+#include "maf_common.cuh"
+
+namespace maf {
+
+__device__ __forceinline__ int gain_sample_m(int s, const Gate& gt) {
+    if (!gt.applied) return s;
+    float y = __fmul_rn(gt.gain, (float)s * (1.0f / 32768.0f));
+    if (gt.lim) y = __fdiv_rn(y, gt.limp);
+    float v = __fmul_rn(y, 32768.0f);
+    v = fminf(fmaxf(v, -32768.0f), 32767.0f);
+    return (int)v;
+}
+
+constexpr int MEL_SPAN = (MEL_TILE - 1) * W_HOP + W_NFFT;            // 5360 samples per tile
+constexpr int Z_PITCH = 200;
+constexpr int P_PITCH = 201;
+constexpr size_t LOGMEL_SMEM = sizeof(float) * MEL_SPAN + sizeof(c32) * MEL_TILE * Z_PITCH + sizeof(float) * MEL_TILE * P_PITCH +
+                               sizeof(float) * W_NFFT + sizeof(c32) * 200 + sizeof(c32) * 208;
+
+__global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__ den16, const Item* __restrict__ items, Consts cs,
+                                                     MelBank mel, int padding, int peak_normalize, double target_peak,
+                                                     const int* __restrict__ peak, const Gate* __restrict__ gates,
+                                                     int16_t* __restrict__ out16, float* __restrict__ mel_out,
+                                                     int* __restrict__ mel_max) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* span = reinterpret_cast<float*>(smem_raw);
+    c32* zb = reinterpret_cast<c32*>(span + MEL_SPAN);
+    float* pw = reinterpret_cast<float*>(zb + MEL_TILE * Z_PITCH);
+    float* win = pw + MEL_TILE * P_PITCH;
+    c32* tw200 = reinterpret_cast<c32*>(win + W_NFFT);
+    c32* tw400 = tw200 + 200;
+
+    const int item = blockIdx.y;
+    const Item it = items[item];
+    const int lf0 = blockIdx.x * MEL_TILE;                       // first frame of the tile, item-relative
+    if (lf0 >= it.mel_frames) return;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < W_NFFT; i += 256) win[i] = cs.win400[i];
+    for (int i = tid; i < 200; i += 256) tw200[i] = cs.tw200[i];
+    for (int i = tid; i < 201; i += 256) tw400[i] = cs.tw400[i];
+
+    const int pkin = peak_normalize ? peak[item] : 0;
+    const bool pn = peak_normalize && pkin > 0;
+    const double factor = pn ? peak_factor(pkin, target_peak) : 1.0;
+    Gate gt; gt.applied = 0;
+    if (gates) gt = gates[item];
+    const int16_t* x = den16 + it.den_off;
+    const long long np_global = it.n_global + padding;            // length of the zero-padded recording
+
+    // Stage the tile's samples: global index i = 160 f - 200 + e, reflected at the true ends of the zero-padded
+    // recording.  The tile also writes the final PCM of the 32 hops it is centred on (the last tile up to the item's
+    // end: with padding 0 the tail N mod 160 plus the last hop still lies inside its span).
+    {
+        const long long i0 = ((long long)it.mel_f0 + lf0) * W_HOP - W_NFFT / 2;
+        const bool last_tile = lf0 + MEL_TILE >= it.mel_frames;
+        const long long own_lo = i0 + W_NFFT / 2;
+        const long long own_hi = last_tile ? it.g0 + it.own_len : own_lo + (long long)MEL_TILE * W_HOP;
+        for (int e = tid; e < MEL_SPAN; e += 256) {
+            const long long i = i0 + e;
+            long long r = i;
+            if (r < 0) r = -r;
+            if (r >= np_global) r = 2 * (np_global - 1) - r;
+            float a = 0.f;
+            if (r >= 0 && r < it.n_global) {
+                const long long l = r - it.g0;                    // item-relative index into the denoised samples
+                if (l >= -(long long)it.lo_avail && l < it.own_len + it.hi_avail) {
+                    int s = x[l];
+                    if (pn) s = peak_norm_sample(s, factor);
+                    const int q = gain_sample_m(s, gt);
+                    a = (float)q * (1.0f / 32768.0f);
+                    if (out16 && r == i && i >= own_lo && i < own_hi && l >= 0 && l < it.own_len) out16[it.out_off + l] = (int16_t)q;
+                }
+            }
+            span[e] = a;
+        }
+    }
+    __syncthreads();
+
+    // stage A: (frame, j) -> 8-point FFT over m of z[j + 25 m], twiddle, store
+    for (int w = tid; w < MEL_TILE * 25; w += 256) {
+        const int lf = w / 25, j = w - lf * 25;
+        c32 v[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int n = j + 25 * m;
+            const float* s = span + lf * W_HOP + 2 * n;
+            v[m] = mk(s[0] * win[2 * n], s[1] * win[2 * n + 1]);
+        }
+        fft200_stepA(v, zb + lf * Z_PITCH, tw200, j);
+    }
+    __syncthreads();
+    // stage B: (frame, p) -> 25-point DFT in registers; exactly one round, so the in-place write is safe after a barrier
+    {
+        const int lf = tid >> 3, p = tid & 7;
+        c32 o[25];
+        fft200_stepB(zb + lf * Z_PITCH, tw200, p, o);
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 25; ++q) zb[lf * Z_PITCH + p + 8 * q] = o[q];
+    }
+    __syncthreads();
+    // real split + power
+    for (int w = tid; w < MEL_TILE * W_NBIN; w += 256) {
+        const int lf = w / W_NBIN, k = w - lf * W_NBIN;
+        const c32* z = zb + lf * Z_PITCH;
+        const c32 zk = z[k == 200 ? 0 : k], znk = z[k == 0 ? 0 : 200 - k];
+        const c32 X = rfft400_bin(zk, znk, tw400[k]);
+        pw[lf * P_PITCH + k] = X.x * X.x + X.y * X.y;
+    }
+    __syncthreads();
+    // mel projection: warp-uniform mel row, lane = frame (coalesced 128 B row segments of the [n_mels, frames] output)
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        const int lf = lane;
+        const bool valid = lf0 + lf < it.mel_frames;
+        float bmax = -INFINITY;
+        for (int m = warp; m < mel.n_mels; m += 8) {
+            const int st = mel.start[m], cnt = mel.count[m];
+            const float* wts = mel.w + mel.woff[m];
+            float acc = 0.f;
+            for (int i = 0; i < cnt; ++i) acc += wts[i] * pw[lf * P_PITCH + st + i];
+            const float lv = log10f(fmaxf(acc, 1e-10f));
+            if (valid) {
+                mel_out[it.mel_off + (long long)m * it.mel_frames + lf0 + lf] = lv;
+                bmax = fmaxf(bmax, lv);
+            }
+        }
+        bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, 16));
+        bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, 8));
+        bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, 4));
+        bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, 2));
+        bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, 1));
+        if (lane == 0 && bmax > -INFINITY) atomicMax(&mel_max[item], float_to_ordered(bmax));
+    }
+}
+
+void launch_logmel(const int16_t* den16, const Item* items, int n_items, int max_tiles, const Consts& c,
+                   const MelBank& mel, int padding, int peak_normalize, double target_peak, const int* peak,
+                   const Gate* gates, int16_t* out16, float* mel_out, int* mel_max, cudaStream_t st) {
+    if (n_items <= 0) return;
+    cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOGMEL_SMEM);
+    if (max_tiles < 1) max_tiles = 1;
+    for (int y0 = 0; y0 < n_items; y0 += 32768) {
+        const int ny = n_items - y0 < 32768 ? n_items - y0 : 32768;
+        dim3 grid(max_tiles, ny);
+        logmel_kernel<<<grid, 256, LOGMEL_SMEM, st>>>(den16, items + y0, c, mel, padding, peak_normalize, target_peak,
+                                                      peak ? peak + y0 : nullptr, gates ? gates + y0 : nullptr, out16,
+                                                      mel_out, mel_max + y0);
+    }
+}
+
+__global__ void __launch_bounds__(256) mel_finalize_kernel(float* __restrict__ mel_out, const Item* __restrict__ items, int n_mels,
+                                                           const int* __restrict__ mel_max) {
+    const int item = blockIdx.y;
+    const Item it = items[item];
+    const long long total = (long long)n_mels * it.mel_frames;
+    const float floor_v = ordered_to_float(mel_max[item]) - 8.0f;
+    float* p = mel_out + it.mel_off;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const float v = fmaxf(p[i], floor_v);
+        p[i] = __fdiv_rn(__fadd_rn(v, 4.0f), 4.0f);
+    }
+}
+
+void launch_mel_finalize(float* mel_out, const Item* items, int n_items, int n_mels, int max_frames,
+                         const int* mel_max, cudaStream_t st) {
+    if (n_items <= 0 || max_frames <= 0) return;
+    long long bx = ((long long)n_mels * max_frames + 256 * 4 - 1) / (256 * 4);
+    if (bx > 8192) bx = 8192;
+    if (bx < 1) bx = 1;
+    for (int y0 = 0; y0 < n_items; y0 += 32768) {
+        const int ny = n_items - y0 < 32768 ? n_items - y0 : 32768;
+        dim3 grid((unsigned)bx, ny);
+        mel_finalize_kernel<<<grid, 256, 0, st>>>(mel_out, items + y0, n_mels, mel_max + y0);
+    }
+}
+
+}  // namespace maf

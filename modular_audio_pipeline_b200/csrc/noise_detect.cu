@@ -1,0 +1,263 @@
+// S0 -- noise-clip auto-detection on the device (reference: audio_pipeline/preprocessor.py:92-147, :179-197).
+//
+// Kernel frame_stats : one thread per 25 ms / 10 ms frame.  Energy is sqrt(mean(frame**2)) evaluated in float32
+//                      with numpy's pairwise summation order (8 strided accumulators per <=128-element leaf,
+//                      halving splits rounded down to multiples of 8), so it is bit-identical to the reference's
+//                      np.mean on float32 and the percentile RANKS cannot differ.  ZCR is kept as an integer count.
+// Kernel select_clip : one CTA per recording.  20th percentile of energy by 4-pass radix select on the float bits,
+//                      median ZCR from a histogram, numpy 'linear' interpolation in float64, the
+//                      (E < eT) & (ZCR > 0.5 zT) mask, and the longest run of >= 100 ms that is closed by a
+//                      non-noise frame (an open run at the end is dropped, like the reference's loop).
+#include "maf_common.cuh"
+
+namespace maf {
+
+// ---- numpy pairwise_sum (loops_utils.h.src) over x[i]^2, float32, no FMA contraction ------------------------
+__device__ float sq_at(const int16_t* p, int i) {
+    float v = (float)p[i];
+    return __fmul_rn(v, v);
+}
+
+__device__ float pairwise_leaf(const int16_t* p, int n) {
+    if (n < 8) {
+        float res = 0.f;
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, sq_at(p, i));
+        return res;
+    }
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = sq_at(p, j);
+    int i = 8;
+    const int lim = n - (n % 8);
+    for (; i < lim; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], sq_at(p, i + j));
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __fadd_rn(res, sq_at(p, i));
+    return res;
+}
+
+// iterative form of the recursion: explicit stack of (offset, n) with post-order combination
+__device__ float pairwise_sumsq(const int16_t* p, int n) {
+    if (n <= 128) return pairwise_leaf(p, n);
+    // depth <= 12 for any realistic frame length
+    int off_stack[16], n_stack[16], state[16];
+    float val[16];
+    int sp = 0;
+    off_stack[0] = 0; n_stack[0] = n; state[0] = 0;
+    float ret = 0.f;
+    while (sp >= 0) {
+        int o = off_stack[sp], m = n_stack[sp];
+        if (m <= 128) { ret = pairwise_leaf(p + o, m); --sp; continue; }
+        int n2 = m / 2; n2 -= n2 % 8;
+        if (state[sp] == 0) {            // descend left
+            state[sp] = 1;
+            ++sp; off_stack[sp] = o; n_stack[sp] = n2; state[sp] = 0;
+        } else if (state[sp] == 1) {     // left done -> descend right
+            val[sp] = ret; state[sp] = 2;
+            ++sp; off_stack[sp] = o + n2; n_stack[sp] = m - n2; state[sp] = 0;
+        } else {                         // both done
+            ret = __fadd_rn(val[sp], ret); --sp;
+        }
+    }
+    return ret;
+}
+
+__global__ void __launch_bounds__(128) frame_stats_kernel(const int16_t* __restrict__ pcm, const Item* __restrict__ items,
+                                                          int frame_len, int hop, float* __restrict__ energies,
+                                                          int* __restrict__ zc) {
+    const Item it = items[blockIdx.y];
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= it.n_sframes) return;
+    const int16_t* p = pcm + it.pcm_off + it.origin + (long long)f * hop;
+    float s = pairwise_sumsq(p, frame_len);
+    float mean = __fdiv_rn(s, (float)frame_len);
+    energies[it.sframe_off + f] = __fsqrt_rn(mean);
+    int c = 0;
+    int prev = p[0] < 0;
+    for (int i = 1; i < frame_len; ++i) { int cur = p[i] < 0; c += (cur != prev); prev = cur; }
+    zc[it.sframe_off + f] = c;
+}
+
+void launch_frame_stats(const int16_t* pcm, const Item* items, int n_items, int max_frames, int frame_len, int hop,
+                        float* energies, int* zc, cudaStream_t st) {
+    if (max_frames <= 0 || n_items <= 0) return;
+    dim3 grid((max_frames + 127) / 128, n_items);
+    frame_stats_kernel<<<grid, 128, 0, st>>>(pcm, items, frame_len, hop, energies, zc);
+}
+
+// ---- selection ------------------------------------------------------------------------------------------------
+constexpr int SEL_THREADS = 1024;
+
+// numpy _lerp(a, b, t) in float64 without FMA contraction
+__device__ double np_lerp(double a, double b, double t) {
+    double d = __dsub_rn(b, a);
+    if (t >= 0.5) return __dsub_rn(b, __dmul_rn(d, __dsub_rn(1.0, t)));
+    return __dadd_rn(a, __dmul_rn(d, t));
+}
+
+// k-th smallest (0-based) of non-negative floats by radix select on their bit patterns; also returns via *next the
+// (k+1)-th smallest.  All threads of the CTA call this; hist is 256 ints of shared memory, scratch 4 ints.
+__device__ void radix_select2(const float* __restrict__ v, int n, int k, unsigned* hist, unsigned* scratch, float& vk,
+                              float& vk1) {
+    unsigned prefix = 0, mask = 0;
+    int kk = k;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        {   // neighbouring frames mostly share a digit: aggregate runs locally before touching shared memory
+            int cur = -1; unsigned run = 0;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                unsigned u = __float_as_uint(v[i]);
+                if ((u & mask) != prefix) continue;
+                int d = (u >> shift) & 255;
+                if (d == cur) { ++run; continue; }
+                if (run) atomicAdd(&hist[cur], run);
+                cur = d; run = 1;
+            }
+            if (run) atomicAdd(&hist[cur], run);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned acc = 0; int d = 0;
+            for (; d < 256; ++d) { if (acc + hist[d] > (unsigned)kk) break; acc += hist[d]; }
+            scratch[0] = d; scratch[1] = acc;
+        }
+        __syncthreads();
+        prefix |= scratch[0] << shift; mask |= 255u << shift; kk -= (int)scratch[1];
+        __syncthreads();
+    }
+    vk = __uint_as_float(prefix);
+    // count of elements <= vk and the smallest element > vk
+    if (threadIdx.x == 0) { scratch[2] = 0; scratch[3] = 0x7f800000u; }
+    __syncthreads();
+    unsigned cnt = 0, mn = 0x7f800000u;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        unsigned u = __float_as_uint(v[i]);
+        if (u <= prefix) ++cnt; else mn = min(mn, u);
+    }
+    atomicAdd(&scratch[2], cnt); atomicMin(&scratch[3], mn);
+    __syncthreads();
+    vk1 = (scratch[2] > (unsigned)(k + 1)) ? vk : __uint_as_float(scratch[3]);
+    __syncthreads();
+}
+
+struct RunSummary { int all, lead, trail, best_len, best_start; };
+
+__global__ void __launch_bounds__(SEL_THREADS) select_clip_kernel(const float* __restrict__ energies, const int* __restrict__ zc,
+                                                                   const long long* __restrict__ foff, const int* __restrict__ fcount,
+                                                                   const Item* __restrict__ items, int frame_len, int hop, int sr,
+                                                                   int fallback_len, Clip* __restrict__ clips, int* __restrict__ seg_out) {
+    __shared__ unsigned hist[2048];
+    __shared__ unsigned scratch[4];
+    __shared__ RunSummary sums[SEL_THREADS];
+    __shared__ double thr[2];
+    const int item = blockIdx.x;
+    const Item it = items[item];
+    const int F = fcount[item];
+    const float* E = energies + foff[item];
+    const int* Z = zc + foff[item];
+    int found = 0, best_s = 0, best_e = 0;
+    if (F > 0) {
+        // --- energy 20th percentile
+        {
+            double vi = __dmul_rn((double)(F - 1), 0.2);        // (n - 1) * (20 / 100)
+            double lo = floor(vi);
+            int k = (int)lo;
+            float a, b;
+            radix_select2(E, F, k, hist, scratch, a, b);
+            if (k + 1 > F - 1) b = a;
+            if (threadIdx.x == 0) thr[0] = np_lerp((double)a, (double)b, __dsub_rn(vi, lo));
+        }
+        // --- ZCR median from a histogram of the integer counts (count < frame_len <= 2047)
+        {
+            for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < F; i += blockDim.x) atomicAdd(&hist[min(Z[i], 2047)], 1u);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double vi = __dmul_rn((double)(F - 1), 0.5);
+                double lo = floor(vi);
+                int k = (int)lo, k1 = min(k + 1, F - 1);
+                int ca = -1, cb = -1; unsigned acc = 0;
+                for (int d = 0; d < 2048; ++d) {
+                    acc += hist[d];
+                    if (ca < 0 && acc > (unsigned)k) ca = d;
+                    if (cb < 0 && acc > (unsigned)k1) { cb = d; break; }
+                }
+                double a = __ddiv_rn((double)ca, (double)frame_len), b = __ddiv_rn((double)cb, (double)frame_len);
+                thr[1] = __dmul_rn(np_lerp(a, b, __dsub_rn(vi, lo)), 0.5);
+            }
+        }
+        __syncthreads();
+        const double eT = thr[0], zT = thr[1];
+        // --- run detection: each thread summarises a contiguous segment, thread 0 stitches them in order
+        const int per = (F + SEL_THREADS - 1) / SEL_THREADS;
+        const int s0 = threadIdx.x * per, s1 = min(F, s0 + per);
+        RunSummary rs; rs.all = 1; rs.lead = 0; rs.trail = 0; rs.best_len = 0; rs.best_start = 0;
+        {
+            int run_start = -1; bool seen_false = false;
+            for (int i = s0; i < s1; ++i) {
+                bool nz = ((double)E[i] < eT) && (__ddiv_rn((double)Z[i], (double)frame_len) > zT);
+                if (nz) {
+                    if (run_start < 0) run_start = i;
+                } else {
+                    if (run_start >= 0) {
+                        if (!seen_false && run_start == s0) rs.lead = i - s0;
+                        else if (i - run_start > rs.best_len) { rs.best_len = i - run_start; rs.best_start = run_start; }
+                        run_start = -1;
+                    }
+                    seen_false = true; rs.all = 0;
+                }
+            }
+            if (s1 <= s0) { rs.all = 1; rs.lead = 0; rs.trail = 0; }
+            else if (rs.all) { rs.lead = s1 - s0; rs.trail = s1 - s0; }
+            else rs.trail = (run_start >= 0) ? s1 - run_start : 0;
+        }
+        sums[threadIdx.x] = rs;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int open_start = -1, bl = 0, bs = 0;
+            for (int t = 0; t < SEL_THREADS; ++t) {
+                const int a0 = t * per, a1 = min(F, a0 + per);
+                if (a1 <= a0) break;
+                const RunSummary r = sums[t];
+                if (r.all) { if (open_start < 0) open_start = a0; continue; }
+                // run that reaches this segment's first False
+                if (open_start >= 0 || r.lead > 0) {
+                    int st = open_start >= 0 ? open_start : a0;
+                    int en = a0 + r.lead;
+                    if (en - st > bl) { bl = en - st; bs = st; }
+                }
+                if (r.best_len > bl) { bl = r.best_len; bs = r.best_start; }
+                open_start = r.trail > 0 ? a1 - r.trail : -1;
+            }
+            // (i - start) * hop / sr >= 0.1 ; longest first-maximum run.  Length ordering equals frame-count ordering.
+            if (bl > 0 && __ddiv_rn((double)((long long)bl * hop), (double)sr) >= 0.1) { found = 1; best_s = bs; best_e = bs + bl; }
+        }
+    }
+    if (threadIdx.x == 0) {
+        // sample range in GLOBAL coordinates of the recording; map to the item's local buffer
+        long long gs, ge;
+        if (found) { gs = (long long)best_s * hop; ge = (long long)best_e * hop; }
+        else { gs = 0; ge = min((long long)fallback_len, it.n_global); }
+        Clip c;
+        c.start = it.pcm_off + gs - it.g0 + it.origin;
+        long long len = ge - gs; if (len > CHUNK) len = CHUNK;
+        c.len = (int)len; c.n_frames = (int)(len / HOP) + 1;
+        clips[item] = c;
+        if (seg_out) { seg_out[2 * item] = (int)gs; seg_out[2 * item + 1] = (int)ge; }
+    }
+}
+
+void launch_select_clip(const float* energies, const int* zc, const long long* foff, const int* fcount,
+                        const Item* items, int n_items, int frame_len, int hop, int sr, int fallback_len,
+                        Clip* clips, int* seg_out, cudaStream_t st) {
+    if (n_items <= 0) return;
+    select_clip_kernel<<<n_items, SEL_THREADS, 0, st>>>(energies, zc, foff, fcount, items, frame_len, hop, sr,
+                                                       fallback_len, clips, seg_out);
+}
+
+}  // namespace maf

@@ -1,0 +1,250 @@
+"""Device-resident front-end: batch plans over libmaf_b200.so with torch tensors as the memory hand-off.
+
+This is the in-memory "fast path beyond the Protocol" of SURVEY.md section 8(b): ``FrontEnd.plan(...)`` fixes the
+geometry of a batch (lengths, mode, mel size), ``Plan.process(pcm)`` runs denoise -> peak normalise -> loudness
+normalise -> log-mel entirely on the GPU and returns device tensors (the log-mel is what Whisper's encoder eats).
+PyTorch is used for device memory, streams and the tensor hand-off only; all arithmetic is in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _capi
+from ._capi import ItemDesc, Layout, MafError, Params, check
+
+CHUNK = 600000
+PAD = 30000
+KW_HALO = 2048
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(device) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("modular_audio_pipeline_b200 needs a CUDA device (B200); there is no CPU path")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("modular_audio_pipeline_b200 runs on CUDA devices only")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+@dataclass
+class FrontEndResult:
+    pcm: List[torch.Tensor]            # final int16 PCM per item (views into one device buffer)
+    log_mel: List[torch.Tensor]        # float32 [n_mels, frames] per item (views); empty when n_mels == 0
+    lufs: torch.Tensor                 # float64 [n_items], loudness measured before the gain
+    noise_clip: Optional[torch.Tensor]  # int32 [n_items, 2] sample range of the noise clip (stationary mode)
+
+
+class FrontEnd:
+    """One per process and GPU: owns the constant tables (windows, twiddles, mel banks) on the device."""
+
+    def __init__(self, device=None):
+        self.device = _require_cuda(device)
+        self._lib = _capi.lib()
+        h = C.c_void_p()
+        check(self._lib.maf_create(self.device.index, C.byref(h)))
+        self._h = h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.maf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def plan(self, lengths: Sequence[int], sample_rate: int = 16000, stationary: bool = True,
+             prop_decrease: float = 0.8, auto_detect_noise: bool = True, noise_sample_duration_s: float = 0.5,
+             external_noise: bool = False, peak_normalize: bool = True, target_lufs: float = -16.0,
+             n_mels: int = 80, mel_padding: int = 0, shards: Optional[Sequence[ItemDesc]] = None) -> "Plan":
+        params = Params(sample_rate, int(stationary), prop_decrease, int(auto_detect_noise), noise_sample_duration_s,
+                        int(external_noise), int(peak_normalize), target_lufs, n_mels, mel_padding)
+        if shards is None:
+            descs = (ItemDesc * len(lengths))(*[ItemDesc(int(n), 0, int(n), 0, int(n), 0, 0) for n in lengths])
+        else:
+            descs = (ItemDesc * len(shards))(*shards)
+        return Plan(self, params, descs)
+
+
+class Plan:
+    """Geometry + workspace of one batch.  Reusable: call process() as often as you like with new PCM."""
+
+    def __init__(self, fe: FrontEnd, params: Params, descs):
+        self.fe = fe
+        self.params = params
+        self.n_items = len(descs)
+        self._lib = fe._lib
+        h = C.c_void_p()
+        check(self._lib.maf_plan_create(fe._h, C.byref(params), descs, self.n_items, C.byref(h)))
+        self._h = h
+        self.descs = descs
+        self.layout: List[Layout] = []
+        for i in range(self.n_items):
+            lay = Layout()
+            check(self._lib.maf_plan_layout(h, i, C.byref(lay)))
+            self.layout.append(lay)
+        self.total_pcm = int(self._lib.maf_plan_total_pcm(h))
+        self.total_out = int(self._lib.maf_plan_total_out(h))
+        self.total_mel = int(self._lib.maf_plan_total_mel(h))
+        self.workspace_bytes = int(self._lib.maf_plan_workspace_bytes(h))
+        self._ws: Optional[torch.Tensor] = None
+
+    # ---- memory ------------------------------------------------------------------------------------------------
+    @property
+    def device(self) -> torch.device:
+        return self.fe.device
+
+    @property
+    def workspace(self) -> torch.Tensor:
+        if self._ws is None:
+            self._ws = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.maf_plan_destroy(self._h)
+            self._h = None
+        self._ws = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self._lib.maf_plan_launches(self._h))
+
+    def buffer(self, name: str, dtype: torch.dtype) -> torch.Tensor:
+        """View of a named workspace buffer (for the collectives of the time-sharded mode)."""
+        off, size = C.c_int64(), C.c_int64()
+        check(self._lib.maf_plan_buffer(self._h, name.encode(), C.byref(off), C.byref(size)))
+        return self.workspace[off.value: off.value + size.value].view(dtype)
+
+    def den_offset(self, item: int = 0) -> int:
+        return int(self._lib.maf_plan_den_offset(self._h, item))
+
+    def pack(self, items: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Lay int16 recordings out in the plan's input layout (device tensor unless ``out`` is given)."""
+        if out is None:
+            out = torch.zeros(max(self.total_pcm, 8), dtype=torch.int16, device=self.device)
+        for lay, d, x in zip(self.layout, self.descs, items):
+            if x.dtype != torch.int16 or x.numel() != d.buf_len:
+                raise ValueError("pack: every item must be int16 with the planned length")
+            out[lay.pcm_off: lay.pcm_off + d.buf_len].copy_(x, non_blocking=True)
+        return out
+
+    def split_out(self, buf: torch.Tensor) -> List[torch.Tensor]:
+        return [buf[lay.out_off: lay.out_off + d.own_len] for lay, d in zip(self.layout, self.descs)]
+
+    def split_mel(self, buf: torch.Tensor) -> List[torch.Tensor]:
+        nm = self.params.n_mels
+        return [buf[lay.mel_off: lay.mel_off + nm * lay.mel_frames].view(nm, lay.mel_frames) for lay in self.layout]
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def set_noise_clips(self, offsets: Sequence[int], lengths: Sequence[int]) -> None:
+        n = self.n_items
+        check(self._lib.maf_set_noise_clips(self._h, (C.c_int64 * n)(*offsets), (C.c_int32 * n)(*lengths)))
+
+    # ---- fused hot path ----------------------------------------------------------------------------------------
+    def process(self, pcm: torch.Tensor, noise_pcm: Optional[torch.Tensor] = None,
+                out_pcm: Optional[torch.Tensor] = None, mel: Optional[torch.Tensor] = None) -> FrontEndResult:
+        """denoise -> peak normalise -> loudness normalise -> log-mel on device-resident int16 PCM (plan layout)."""
+        self._check_in(pcm)
+        dev = self.device
+        if out_pcm is None:
+            out_pcm = torch.empty(max(self.total_out, 8), dtype=torch.int16, device=dev)
+        nm = self.params.n_mels
+        if nm and mel is None:
+            mel = torch.empty(max(self.total_mel, 4), dtype=torch.float32, device=dev)
+        lufs = torch.empty(self.n_items, dtype=torch.float64, device=dev)
+        clip = torch.zeros(self.n_items, 2, dtype=torch.int32, device=dev) if self.params.stationary else None
+        with torch.cuda.device(dev):
+            check(self._lib.maf_process(self._h, _ptr(pcm), _ptr(noise_pcm), _ptr(self.workspace), _ptr(out_pcm),
+                                        _ptr(mel) if nm else None, _ptr(lufs), _ptr(clip), self._stream()))
+        return FrontEndResult(self.split_out(out_pcm), self.split_mel(mel) if nm else [], lufs, clip)
+
+    def process_host(self, pcm: torch.Tensor, out_pcm: torch.Tensor, mel: Optional[torch.Tensor],
+                     lufs: torch.Tensor, clip: Optional[torch.Tensor] = None,
+                     noise_pcm: Optional[torch.Tensor] = None) -> None:
+        """Same call on HOST tensors (pinned for full PCIe speed); returns when the results are in host memory."""
+        for t in (pcm, out_pcm, mel, lufs, clip, noise_pcm):
+            if t is not None and t.device.type != "cpu":
+                raise ValueError("process_host takes CPU tensors")
+        with torch.cuda.device(self.device):
+            check(self._lib.maf_process_host(self._h, _ptr(pcm), _ptr(noise_pcm),
+                                             0 if noise_pcm is None else noise_pcm.numel(), _ptr(out_pcm), _ptr(mel),
+                                             _ptr(lufs), _ptr(clip)))
+
+    # ---- single stages (what the Protocol methods call) --------------------------------------------------------------
+    def _check_in(self, pcm: torch.Tensor) -> None:
+        if pcm.dtype != torch.int16 or pcm.device != self.device or pcm.numel() < self.total_pcm or not pcm.is_contiguous():
+            raise ValueError("expected a contiguous int16 tensor in the plan's layout on the plan's device")
+
+    def denoise(self, pcm: torch.Tensor, noise_pcm: Optional[torch.Tensor] = None, want_float: bool = False):
+        self._check_in(pcm)
+        dev = self.device
+        out = torch.empty(max(self.total_out, 8), dtype=torch.int16, device=dev)
+        outf = torch.empty(max(self.total_out, 8), dtype=torch.float32, device=dev) if want_float else None
+        clip = torch.zeros(self.n_items, 2, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(self._lib.maf_denoise(self._h, _ptr(pcm), _ptr(noise_pcm), _ptr(self.workspace), _ptr(out), _ptr(outf),
+                                        _ptr(clip), self._stream()))
+        return self.split_out(out), (self.split_out(outf) if want_float else None), clip
+
+    def peak_normalize(self, pcm: torch.Tensor) -> List[torch.Tensor]:
+        self._check_in(pcm)
+        out = torch.empty(max(self.total_out, 8), dtype=torch.int16, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.maf_peak_normalize(self._h, _ptr(pcm), _ptr(self.workspace), _ptr(out), self._stream()))
+        return self.split_out(out)
+
+    def loudness(self, pcm: torch.Tensor):
+        self._check_in(pcm)
+        out = torch.empty(max(self.total_out, 8), dtype=torch.int16, device=self.device)
+        lufs = torch.empty(self.n_items, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.maf_loudness(self._h, _ptr(pcm), _ptr(self.workspace), _ptr(out), _ptr(lufs), self._stream()))
+        return self.split_out(out), lufs
+
+    def frame_stats(self, pcm: torch.Tensor):
+        """S0 per-frame statistics of every item: (float32 energies, int32 zero-crossing counts), concatenated."""
+        self._check_in(pcm)
+        hop = int(self.params.sample_rate * 0.010)
+        flen = int(self.params.sample_rate * 0.025)
+        total = 0
+        for d in self.descs:
+            fg = (d.n_global - flen) // hop + 1 if d.n_global >= flen else 0
+            first = -(-d.g0 // hop)
+            last = min(fg, -(-(d.g0 + d.own_len) // hop))
+            total += max(0, last - first)
+        e = torch.empty(max(total, 1), dtype=torch.float32, device=self.device)
+        z = torch.empty(max(total, 1), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.maf_frame_stats(self._h, _ptr(pcm), _ptr(e), _ptr(z), self._stream()))
+        return e[:total], z[:total]
+
+    def log_mel(self, pcm: torch.Tensor) -> List[torch.Tensor]:
+        self._check_in(pcm)
+        mel = torch.empty(max(self.total_mel, 4), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.maf_logmel(self._h, _ptr(pcm), _ptr(self.workspace), _ptr(mel), self._stream()))
+        return self.split_mel(mel)
+
+
+__all__ = ["FrontEnd", "Plan", "FrontEndResult", "MafError", "ItemDesc"]

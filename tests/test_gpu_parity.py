@@ -1,0 +1,202 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical stage inputs.
+
+Tolerances are BASELINE.json's: log-mel max-abs <= 1e-4, integrated loudness within 0.01 LU, denoised waveform
+SNR >= 80 dB vs the oracle's float output (and its int16 form <= 1 LSB on <= 0.1 % of samples); integer stages
+(noise-clip indices, peak normalise) bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from modular_audio_pipeline_b200.synth import speech_noise
+from oracle import reference_path as O
+
+pytestmark = pytest.mark.gpu
+SR = 16000
+
+
+def snr_db(ref, x):
+    ref = np.asarray(ref, dtype=np.float64)
+    err = np.asarray(x, dtype=np.float64) - ref
+    return 10 * np.log10(np.sum(ref ** 2) / max(np.sum(err ** 2), 1e-300))
+
+
+def gen(seconds, seed, **kw):
+    return speech_noise(seconds, seed, **kw)
+
+
+# ---- S0 ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seconds,seed", [(30, 3), (60, 0), (97.3, 5)])
+def test_frame_stats_bit_exact(frontend, seconds, seed):
+    pcm = gen(seconds, seed)
+    plan = frontend.plan([pcm.numel()], n_mels=0)
+    e, z = plan.frame_stats(plan.pack([pcm]))
+    eo, zo = O.frame_stats(pcm.numpy().astype(np.float32), SR)
+    assert np.array_equal(e.cpu().numpy().astype(np.float64), eo)
+    assert np.array_equal(z.cpu().numpy() / 400.0, zo)
+
+
+@pytest.mark.parametrize("seconds,seed", [(30, 3), (60, 0), (97.3, 5), (12, 9)])
+def test_noise_clip_indices(frontend, seconds, seed):
+    pcm = gen(seconds, seed)
+    plan = frontend.plan([pcm.numel()], n_mels=0)
+    _, _, clip = plan.denoise(plan.pack([pcm]))
+    want = O.choose_noise_clip(pcm.numpy().astype(np.float32), SR)
+    assert tuple(clip.cpu().numpy()[0]) == want
+
+
+def test_noise_clip_fallback_when_nothing_detected(frontend):
+    # a pure tone has no low-energy frames with high ZCR runs -> reference falls back to the first 0.5 s (:189-192)
+    t = np.arange(5 * SR) / SR
+    pcm = torch.from_numpy((8000 * np.sin(2 * np.pi * 440 * t)).astype(np.int16))
+    plan = frontend.plan([pcm.numel()], n_mels=0)
+    _, _, clip = plan.denoise(plan.pack([pcm]))
+    want = O.choose_noise_clip(pcm.numpy().astype(np.float32), SR)
+    assert tuple(clip.cpu().numpy()[0]) == want
+
+
+# ---- S1-S4 --------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seconds,seed", [(20, 1), (37.5, 2), (60, 0), (100.2, 4)])
+@pytest.mark.parametrize("stationary", [True, False])
+def test_denoise_parity(frontend, seconds, seed, stationary):
+    pcm = gen(seconds, seed, meeting=not stationary)
+    plan = frontend.plan([pcm.numel()], stationary=stationary, n_mels=0)
+    out16, outf, clip = plan.denoise(plan.pack([pcm]), want_float=True)
+    red, den16, _ = O.denoise_int16(pcm.numpy(), SR, stationary=stationary)
+    got = outf[0].cpu().numpy()
+    s = snr_db(red, got)
+    assert s >= 80.0, f"SNR {s:.1f} dB"
+    g16 = out16[0].cpu().numpy().astype(np.int32)
+    diff = np.abs(g16 - den16.astype(np.int32))
+    assert diff.max() <= 1
+    assert np.mean(diff != 0) <= 1e-3
+
+
+def test_denoise_fixed_clip_and_external_noise(frontend):
+    pcm = gen(25, 7)
+    x = pcm.numpy()
+    # auto_detect off -> first 0.5 s (preprocessor.py:193-197)
+    plan = frontend.plan([pcm.numel()], auto_detect_noise=False, n_mels=0)
+    _, outf, clip = plan.denoise(plan.pack([pcm]), want_float=True)
+    red, _, rng = O.denoise_int16(x, SR, auto_detect=False)
+    assert tuple(clip.cpu().numpy()[0]) == rng == (0, 8000)
+    assert snr_db(red, outf[0].cpu().numpy()) >= 80.0
+    # explicit noise sample (noise_sample_path, :174-178)
+    noise = gen(1.3, 99, sigma=0.02)
+    plan2 = frontend.plan([pcm.numel()], external_noise=True, n_mels=0)
+    plan2.set_noise_clips([0], [noise.numel()])
+    _, outf2, _ = plan2.denoise(plan2.pack([pcm]), noise_pcm=noise.cuda(), want_float=True)
+    red2 = O.reduce_noise(x.astype(np.float32), SR, noise.numpy().astype(np.float32), 0.8, True)
+    assert snr_db(red2, outf2[0].cpu().numpy()) >= 80.0
+
+
+def test_denoise_top_db_row_clamp(frontend):
+    # a bin whose chunk maximum is > 80 dB above the noise threshold opens the whole row (amp_to_db top_db clamp)
+    rng = np.random.default_rng(0)
+    n = 20 * SR
+    t = np.arange(n) / SR
+    x = rng.normal(0, 1.2, n)
+    x[5 * SR: 6 * SR] += 30000 * np.sin(2 * np.pi * 1000 * t[5 * SR: 6 * SR])
+    pcm = torch.from_numpy(np.clip(np.round(x), -32768, 32767).astype(np.int16))
+    plan = frontend.plan([n], auto_detect_noise=False, n_mels=0)
+    _, outf, _ = plan.denoise(plan.pack([pcm]), want_float=True)
+    red, _, _ = O.denoise_int16(pcm.numpy(), SR, auto_detect=False)
+    assert snr_db(red, outf[0].cpu().numpy()) >= 80.0
+
+
+# ---- S5 -----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", [0, 1])
+def test_peak_normalize_bit_exact(frontend, seed):
+    pcm = gen(10, seed)
+    plan = frontend.plan([pcm.numel()], n_mels=0)
+    out = plan.peak_normalize(plan.pack([pcm]))[0].cpu().numpy()
+    assert np.array_equal(out, O.peak_normalize(pcm.numpy()))
+    silent = torch.zeros(8000, dtype=torch.int16)
+    plan = frontend.plan([8000], n_mels=0)
+    assert np.array_equal(plan.peak_normalize(plan.pack([silent]))[0].cpu().numpy(), silent.numpy())
+
+
+# ---- S6-S7 ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seconds,seed,scale", [(30, 0, 1.0), (60.05, 1, 0.2), (10, 2, 4.0), (0.45, 3, 1.0)])
+def test_loudness_parity(frontend, seconds, seed, scale):
+    pcm = gen(seconds, seed)
+    pcm = torch.clamp((pcm.float() * scale).round(), -32768, 32767).to(torch.int16)
+    plan = frontend.plan([pcm.numel()], n_mels=0)
+    out, lufs = plan.loudness(plan.pack([pcm]))
+    want16, want_lufs, applied = O.normalize_loudness(pcm.numpy(), SR)
+    assert abs(lufs.item() - want_lufs) <= 0.01
+    assert abs(lufs.item() - want_lufs) <= 1e-4           # what FP64 recurrences actually deliver
+    d = np.abs(out[0].cpu().numpy().astype(np.int32) - want16.astype(np.int32))
+    assert d.max() <= 1 and np.mean(d != 0) <= 1e-3
+
+
+def test_loudness_silence_passthrough_and_too_short(frontend):
+    from modular_audio_pipeline_b200 import MafError
+    silent = torch.zeros(3 * SR, dtype=torch.int16)
+    plan = frontend.plan([silent.numel()], n_mels=0)
+    out, lufs = plan.loudness(plan.pack([silent]))
+    assert not np.isfinite(lufs.item())                    # -inf, reference returns the input unchanged (:267-269)
+    assert np.array_equal(out[0].cpu().numpy(), silent.numpy())
+    short = gen(0.3, 0)
+    plan = frontend.plan([short.numel()], n_mels=0)
+    with pytest.raises(MafError):                          # pyloudnorm: "Audio must have length greater than the block size"
+        plan.loudness(plan.pack([short]))
+
+
+# ---- S8-S9 ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_mels", [80, 128])
+@pytest.mark.parametrize("seconds,padding", [(30, 0), (11.37, 160), (60, 480000), (1.0, 0)])
+def test_logmel_parity(frontend, n_mels, seconds, padding):
+    pcm = gen(seconds, 11)
+    plan = frontend.plan([pcm.numel()], n_mels=n_mels, mel_padding=padding)
+    mel = plan.log_mel(plan.pack([pcm]))[0].cpu().numpy()
+    want = O.log_mel_spectrogram(pcm.numpy().astype(np.float32) / 32768.0, n_mels, padding)
+    assert mel.shape == want.shape
+    assert np.abs(mel - want).max() <= 1e-4
+
+
+# ---- fused path -------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("stationary,n_mels,padding", [(True, 80, 480000), (False, 128, 0)])
+def test_fused_front_end(frontend, stationary, n_mels, padding):
+    pcm = gen(60, 0, meeting=not stationary)
+    plan = frontend.plan([pcm.numel()], stationary=stationary, n_mels=n_mels, mel_padding=padding)
+    res = plan.process(plan.pack([pcm]))
+    ref = O.front_end(pcm.numpy(), SR, stationary, n_mels, padding)
+    assert abs(res.lufs.item() - ref["lufs"]) <= 0.01
+    got16 = res.pcm[0].cpu().numpy()
+    d = np.abs(got16.astype(np.int32) - ref["loud_i16"].astype(np.int32))
+    assert d.max() <= 2 and np.mean(d != 0) <= 2e-3
+    # the log-mel must match the oracle evaluated on the SAME (GPU-produced) samples to 1e-4
+    want = O.log_mel_spectrogram(got16.astype(np.float32) / 32768.0, n_mels, padding)
+    assert np.abs(res.log_mel[0].cpu().numpy() - want).max() <= 1e-4
+    if stationary:
+        assert tuple(res.noise_clip.cpu().numpy()[0]) == ref["noise_clip"]
+
+
+def test_batch_equals_single(frontend):
+    """Ragged batch: every item must come out bit-identical to running it alone (no cross-item leakage)."""
+    clips = [gen(s, 20 + i) for i, s in enumerate([5.0, 30.0, 41.7, 8.25])]
+    plan = frontend.plan([c.numel() for c in clips], n_mels=80)
+    res = plan.process(plan.pack(clips))
+    torch.cuda.synchronize()
+    for i, c in enumerate(clips):
+        p1 = frontend.plan([c.numel()], n_mels=80)
+        r1 = p1.process(p1.pack([c]))
+        assert torch.equal(res.pcm[i], r1.pcm[0])
+        assert torch.equal(res.log_mel[i], r1.log_mel[0])
+        assert res.lufs[i].item() == r1.lufs[0].item()
+
+
+def test_process_host_matches_device(frontend):
+    pcm = gen(20, 4)
+    plan = frontend.plan([pcm.numel()], n_mels=80)
+    res = plan.process(plan.pack([pcm]))
+    hin = torch.zeros(plan.total_pcm, dtype=torch.int16).pin_memory()
+    hin[:pcm.numel()] = pcm
+    hout = torch.empty(plan.total_out, dtype=torch.int16).pin_memory()
+    hmel = torch.empty(plan.total_mel, dtype=torch.float32).pin_memory()
+    hl = torch.empty(1, dtype=torch.float64).pin_memory()
+    plan.process_host(hin, hout, hmel, hl)
+    assert torch.equal(plan.split_out(hout)[0], res.pcm[0].cpu())
+    assert torch.equal(plan.split_mel(hmel)[0], res.log_mel[0].cpu())
+    assert hl.item() == res.lufs.item()
