@@ -79,6 +79,12 @@ int64_t maf_plan_total_out(const maf_plan* plan);   /* int16 samples the output 
 int64_t maf_plan_total_mel(const maf_plan* plan);   /* floats the mel array must hold           */
 int64_t maf_plan_launches(const maf_plan* plan);    /* kernels launched by this library through the plan so far */
 
+/* Per-stage device timing for bench.py's roofline: after maf_plan_profile(plan, S) every maf_process call records CUDA
+ * events between its stages into a ring of S sets; maf_plan_stage_ms reads stage 1..9 (noise+S0, stft, ns_mask,
+ * smooth_mask, istft, kweight, gate, logmel, mel_finalize) of ring slot `step` once the stream is synchronised. */
+int maf_plan_profile(maf_plan* plan, int32_t max_steps);
+int maf_plan_stage_ms(maf_plan* plan, int32_t step, int32_t stage, float* ms);
+
 /* Explicit noise clips (reduce_stationary_noise(input_wav, noise_sample_path), preprocessor.py:174-178):
  * clip i is noise_pcm_dev[offsets[i] .. offsets[i] + lengths[i]).  Host arrays, copied synchronously. */
 int maf_set_noise_clips(maf_plan* plan, const int64_t* offsets, const int32_t* lengths);

@@ -50,6 +50,8 @@ SYMBOLS = {
     "maf_plan_total_out": (C.c_int64, [_P]),
     "maf_plan_total_mel": (C.c_int64, [_P]),
     "maf_plan_launches": (C.c_int64, [_P]),
+    "maf_plan_profile": (C.c_int, [_P, C.c_int32]),
+    "maf_plan_stage_ms": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
     "maf_set_noise_clips": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "maf_process": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "maf_process_host": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P]),

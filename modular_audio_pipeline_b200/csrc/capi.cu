@@ -145,6 +145,8 @@ struct maf_plan {
     WsBuf S, M, M0, bits, rowflag, T2, T2hi, nmax, partial, E, ZC, clips, seg, den16, peak, peak_norm, mel_max, sub, gates;
     long long ws_bytes = 0;
     long long launches = 0;
+    // optional per-stage CUDA-event timing (maf_plan_profile): ring of event sets, one per maf_process call
+    int prof_steps = 0; long long prof_calls = 0; std::vector<cudaEvent_t> prof_ev;   // [(step, boundary)]
     // host-path staging (maf_process_host)
     cudaStream_t hstream = nullptr;
     void* h_ws = nullptr; int16_t* h_pcm = nullptr; int16_t* h_out = nullptr; float* h_mel = nullptr; double* h_lufs = nullptr;
@@ -358,6 +360,7 @@ extern "C" void maf_plan_destroy(maf_plan* pl) {
     if (!pl) return;
     cudaSetDevice(pl->ctx->device);
     if (pl->hstream) { cudaStreamSynchronize(pl->hstream); cudaStreamDestroy(pl->hstream); }
+    for (cudaEvent_t e : pl->prof_ev) cudaEventDestroy(e);
     cudaFree(pl->tables); cudaFree(pl->h_ws); cudaFree(pl->h_pcm); cudaFree(pl->h_out); cudaFree(pl->h_mel); cudaFree(pl->h_lufs);
     cudaFree(pl->h_clip); cudaFree(pl->h_noise);
     delete pl;
@@ -422,6 +425,34 @@ __global__ void gather_lufs_kernel(const Gate* __restrict__ g, int n, double* __
 
 static const MelBank& pick_mel(const maf_plan* pl) { return pl->p.n_mels == 128 ? pl->ctx->mel128 : pl->ctx->mel80; }
 
+
+// ---- per-stage timing ---------------------------------------------------------------------------------------------
+enum { ST_BEGIN = 0, ST_NOISE, ST_STFT, ST_NSMASK, ST_SMOOTH, ST_ISTFT, ST_KWEIGHT, ST_GATE, ST_LOGMEL, ST_MELFIN, ST_COUNT };
+static inline void mark(maf_plan* pl, int boundary, cudaStream_t st) {
+    if (!pl->prof_steps) return;
+    const int step = (int)(pl->prof_calls % pl->prof_steps);
+    cudaEventRecord(pl->prof_ev[(size_t)step * ST_COUNT + boundary], st);
+}
+
+extern "C" int maf_plan_profile(maf_plan* pl, int32_t max_steps) {
+    if (!pl || max_steps < 0) return fail(MAF_ERR_INVALID, "maf_plan_profile: bad argument");
+    CU(cudaSetDevice(pl->ctx->device));
+    for (cudaEvent_t e : pl->prof_ev) cudaEventDestroy(e);
+    pl->prof_ev.clear(); pl->prof_steps = 0; pl->prof_calls = 0;
+    for (int i = 0; i < max_steps * ST_COUNT; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); pl->prof_ev.push_back(e); }
+    pl->prof_steps = max_steps;
+    return MAF_OK;
+}
+
+// elapsed ms of stage `stage` (1..9: noise, stft, ns_mask, smooth, istft, kweight, gate, logmel, mel_finalize) in the
+// `step`-th most recent profiled maf_process call window (caller must have synchronised the stream)
+extern "C" int maf_plan_stage_ms(maf_plan* pl, int32_t step, int32_t stage, float* ms) {
+    if (!pl || !ms || !pl->prof_steps || step < 0 || step >= pl->prof_steps || stage < 1 || stage >= ST_COUNT)
+        return fail(MAF_ERR_INVALID, "maf_plan_stage_ms: bad argument");
+    CU(cudaEventElapsedTime(ms, pl->prof_ev[(size_t)step * ST_COUNT + stage - 1], pl->prof_ev[(size_t)step * ST_COUNT + stage]));
+    return MAF_OK;
+}
+
 // S0 + thresholds + K1..K3.  `den_dst` receives the truncated int16 signal (workspace den16 layout, or the caller's
 // output layout when to_out), the per-item peak lands in the workspace.
 static int run_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pcm, void* ws, int16_t* den_dst, int to_out, float* out_f32,
@@ -429,6 +460,7 @@ static int run_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pc
     const maf_params& p = pl->p;
     const int n = pl->n_items;
     Clip* clips = ws_ptr<Clip>(ws, pl->clips);
+    mark(pl, ST_BEGIN, st);
     CU(cudaMemsetAsync(ws_ptr<int>(ws, pl->peak), 0, 4LL * n, st));
     if (p.stationary) {
         const int16_t* noise_src = pcm;
@@ -453,9 +485,11 @@ static int run_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pc
         pl->launches += 3;
         CU(cudaMemsetAsync(ws_ptr<uint8_t>(ws, pl->rowflag), 0, pl->rowflag.bytes, st));
     }
+    mark(pl, ST_NOISE, st);
     launch_stft(pcm, pl->d_items, pl->d_chunks, pl->n_chunks, pl->max_chunk_frames, pl->ctx->c, p.stationary, ws_ptr<float>(ws, pl->T2),
                 ws_ptr<float>(ws, pl->T2hi), ws_ptr<c32>(ws, pl->S), ws_ptr<uint32_t>(ws, pl->bits), ws_ptr<uint8_t>(ws, pl->rowflag), st);
     pl->launches += 1;
+    mark(pl, ST_STFT, st);
     if (!p.stationary) {
         // noisereduce non-stationary defaults: time_constant_s = 2.0, thresh_n_mult = 2, sigmoid_slope = 10
         const double t = 2.0 * p.sample_rate / HOP;
@@ -463,11 +497,14 @@ static int run_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pc
         launch_ns_mask(ws_ptr<c32>(ws, pl->S), pl->d_chunks, pl->n_chunks, b, 2.0f, 10.0f, ws_ptr<float>(ws, pl->M0), st);
         pl->launches += 1;
     }
+    mark(pl, ST_NSMASK, st);
     launch_smooth_mask(ws_ptr<uint32_t>(ws, pl->bits), ws_ptr<uint8_t>(ws, pl->rowflag), ws_ptr<float>(ws, pl->M0), pl->d_chunks, pl->n_chunks,
                        pl->max_chunk_frames, p.stationary, p.prop_decrease, pl->taps, ws_ptr<float>(ws, pl->M), st);
+    mark(pl, ST_SMOOTH, st);
     launch_istft(ws_ptr<c32>(ws, pl->S), ws_ptr<float>(ws, pl->M), pl->d_items, pl->d_chunks, pl->n_chunks, pl->ctx->c,
                  den_dst, to_out, out_f32, ws_ptr<int>(ws, pl->peak), st);
     pl->launches += 2;
+    mark(pl, ST_ISTFT, st);
     CU(cudaGetLastError());
     return MAF_OK;
 }
@@ -479,6 +516,7 @@ static int run_loudness_stats(maf_plan* pl, const int16_t* src, const Item* item
     launch_kweight_energy(src, items, n, pl->max_ktiles, pl->tile_len, pl->kw, peak_normalize, pl->target_peak, ws_ptr<int>(ws, pl->peak),
                           ws_ptr<double>(ws, pl->sub), ws_ptr<int>(ws, pl->peak_norm), st);
     pl->launches += 1;
+    mark(pl, ST_KWEIGHT, st);
     CU(cudaGetLastError());
     return MAF_OK;
 }
@@ -487,6 +525,7 @@ static int run_gate(maf_plan* pl, const Item* items, void* ws, cudaStream_t st) 
     launch_gate(ws_ptr<double>(ws, pl->sub), items, pl->n_items, pl->inv_block, (double)pl->p.target_lufs, ws_ptr<int>(ws, pl->peak_norm),
                 ws_ptr<Gate>(ws, pl->gates), st);
     pl->launches += 1;
+    mark(pl, ST_GATE, st);
     CU(cudaGetLastError());
     return MAF_OK;
 }
@@ -498,10 +537,12 @@ static int run_logmel(maf_plan* pl, const int16_t* src, const Item* items, int p
     launch_logmel(src, items, n, pl->max_mel_tiles, pl->ctx->c, pick_mel(pl), pl->p.mel_padding, peak_normalize, pl->target_peak,
                   ws_ptr<int>(ws, pl->peak), gates, out16, mel, ws_ptr<int>(ws, pl->mel_max), st);
     pl->launches += 2;
+    mark(pl, ST_LOGMEL, st);
     if (finalize) {
         launch_mel_finalize(mel, items, n, pl->p.n_mels, pl->max_mel_frames, ws_ptr<int>(ws, pl->mel_max), st);
         pl->launches += 1;
     }
+    mark(pl, ST_MELFIN, st);
     CU(cudaGetLastError());
     return MAF_OK;
 }
@@ -532,6 +573,7 @@ extern "C" int maf_process(maf_plan* pl, const int16_t* pcm, const int16_t* nois
     if (lufs) { gather_lufs_kernel<<<(pl->n_items + 255) / 256, 256, 0, st>>>(gates, pl->n_items, lufs); pl->launches += 1; }
     if (clip && pl->p.stationary) CU(cudaMemcpyAsync(clip, ws_ptr<int>(ws, pl->seg), 8LL * pl->n_items, cudaMemcpyDeviceToDevice, st));
     CU(cudaGetLastError());
+    if (pl->prof_steps) pl->prof_calls += 1;
     return MAF_OK;
 }
 

@@ -128,6 +128,20 @@ class Plan:
     def launches(self) -> int:
         return int(self._lib.maf_plan_launches(self._h))
 
+    STAGES = ("noise", "stft", "ns_mask", "smooth_mask", "istft", "kweight", "gate", "logmel", "mel_finalize")
+
+    def profile(self, max_steps: int) -> None:
+        """Record CUDA events between the stages of the next process() calls (ring of ``max_steps`` sets)."""
+        check(self._lib.maf_plan_profile(self._h, max_steps))
+
+    def stage_ms(self, step: int) -> dict:
+        out = {}
+        ms = C.c_float()
+        for i, name in enumerate(self.STAGES, start=1):
+            check(self._lib.maf_plan_stage_ms(self._h, step, i, C.byref(ms)))
+            out[name] = ms.value
+        return out
+
     def buffer(self, name: str, dtype: torch.dtype) -> torch.Tensor:
         """View of a named workspace buffer (for the collectives of the time-sharded mode)."""
         off, size = C.c_int64(), C.c_int64()

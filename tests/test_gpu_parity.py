@@ -158,19 +158,58 @@ def test_logmel_parity(frontend, n_mels, seconds, padding):
 # ---- fused path -------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("stationary,n_mels,padding", [(True, 80, 480000), (False, 128, 0)])
 def test_fused_front_end(frontend, stationary, n_mels, padding):
+    """The fused entry must equal the stage entry points chained on the GPU bit for bit (each stage is parity-tested
+    against the oracle above), and stay close to the oracle's own chain."""
     pcm = gen(60, 0, meeting=not stationary)
-    plan = frontend.plan([pcm.numel()], stationary=stationary, n_mels=n_mels, mel_padding=padding)
+    n = pcm.numel()
+    plan = frontend.plan([n], stationary=stationary, n_mels=n_mels, mel_padding=padding)
     res = plan.process(plan.pack([pcm]))
+    den16, _, clip = plan.denoise(plan.pack([pcm]))
+    norm16 = plan.peak_normalize(plan.pack([den16[0]]))
+    loud16, lufs = plan.loudness(plan.pack([norm16[0]]))
+    mel = plan.log_mel(plan.pack([loud16[0]]))
+    assert torch.equal(res.pcm[0], loud16[0])
+    assert torch.equal(res.log_mel[0], mel[0])
+    assert res.lufs.item() == lufs.item()
+    # chained oracle: one flipped LSB after the denoise is amplified by the peak-normalise factor (~10x here), so the
+    # end-to-end comparison is bounded by that amplification, not by 1 LSB (SURVEY.md section 7, "Hard parts")
     ref = O.front_end(pcm.numpy(), SR, stationary, n_mels, padding)
     assert abs(res.lufs.item() - ref["lufs"]) <= 0.01
+    amp = 32768.0 / max(1, np.abs(ref["denoised_i16"].astype(np.int32)).max())
     got16 = res.pcm[0].cpu().numpy()
     d = np.abs(got16.astype(np.int32) - ref["loud_i16"].astype(np.int32))
-    assert d.max() <= 2 and np.mean(d != 0) <= 2e-3
-    # the log-mel must match the oracle evaluated on the SAME (GPU-produced) samples to 1e-4
+    assert d.max() <= 2 * amp + 2 and np.mean(d != 0) <= 2e-3
     want = O.log_mel_spectrogram(got16.astype(np.float32) / 32768.0, n_mels, padding)
     assert np.abs(res.log_mel[0].cpu().numpy() - want).max() <= 1e-4
     if stationary:
         assert tuple(res.noise_clip.cpu().numpy()[0]) == ref["noise_clip"]
+
+
+@pytest.mark.parametrize("name", ["clip_a", "clip_b"])
+def test_golden_fixtures(frontend, name):
+    """Committed golden vectors (tests/golden/make_golden.py): oracle outputs plus the independent HF log-mel."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    pcm = torch.from_numpy(g["pcm"])
+    stationary, n_mels = bool(g["stationary"]), int(g["n_mels"])
+    plan = frontend.plan([pcm.numel()], stationary=stationary, n_mels=n_mels)
+    den16, denf, clip = plan.denoise(plan.pack([pcm]), want_float=True)
+    assert snr_db(g["denoised_f32"], denf[0].cpu().numpy()) >= 80.0
+    if stationary:
+        assert tuple(clip.cpu().numpy()[0]) == tuple(g["noise_clip"])
+    norm = plan.peak_normalize(plan.pack([torch.from_numpy(g["denoised_i16"])]))[0].cpu().numpy()
+    assert np.array_equal(norm, g["norm_i16"])
+    loud, lufs = plan.loudness(plan.pack([torch.from_numpy(g["norm_i16"])]))
+    assert abs(lufs.item() - float(g["lufs"])) <= 0.01
+    d = np.abs(loud[0].cpu().numpy().astype(np.int32) - g["loud_i16"].astype(np.int32))
+    assert d.max() <= 1 and np.mean(d != 0) <= 1e-3
+    mel = plan.log_mel(plan.pack([torch.from_numpy(g["loud_i16"])]))[0].cpu().numpy()
+    assert np.abs(mel - g["log_mel"]).max() <= 1e-4
+    # independent implementation: transformers.WhisperFeatureExtractor pads to 30 s before the STFT
+    n = pcm.numel()
+    plan30 = frontend.plan([n], n_mels=n_mels, mel_padding=480000 - n)
+    mel30 = plan30.log_mel(plan30.pack([torch.from_numpy(g["loud_i16"])]))[0].cpu().numpy()
+    assert np.abs(mel30 - g["hf_log_mel"]).max() <= 1e-4
 
 
 def test_batch_equals_single(frontend):

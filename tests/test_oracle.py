@@ -1,0 +1,116 @@
+"""CPU tests of the oracle (oracle/reference_path.py): golden fixtures, independent cross-checks, reference semantics."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from modular_audio_pipeline_b200.synth import speech_noise
+from oracle import reference_path as O
+
+SR = 16000
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name", ["clip_a", "clip_b"])
+def test_oracle_reproduces_golden(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    r = O.front_end(g["pcm"], SR, bool(g["stationary"]), int(g["n_mels"]), 0)
+    assert np.array_equal(r["denoised_i16"], g["denoised_i16"])
+    assert np.array_equal(r["norm_i16"], g["norm_i16"])
+    assert np.array_equal(r["loud_i16"], g["loud_i16"])
+    assert abs(r["lufs"] - float(g["lufs"])) < 1e-9
+    assert np.abs(r["log_mel"] - g["log_mel"]).max() < 1e-6
+    assert tuple(r["noise_clip"]) == tuple(g["noise_clip"])
+
+
+@pytest.mark.parametrize("name", ["clip_a", "clip_b"])
+def test_golden_independent_implementations(name):
+    """The fixtures also hold outputs of implementations that share no code with the oracle."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    assert np.abs(g["hf_log_mel"] - g["oracle_log_mel_30s"]).max() <= 1e-6          # transformers.WhisperFeatureExtractor
+    assert abs(float(g["ta_lufs"]) - float(g["quiet_lufs"])) <= 1e-3                 # torchaudio.functional.loudness
+
+
+def test_frame_stats_vectorised_equals_reference_loop():
+    pcm = speech_noise(20, 3).numpy().astype(np.float32)
+    e1, z1 = O.frame_stats_loop(pcm, SR)
+    e2, z2 = O.frame_stats(pcm, SR)
+    assert np.array_equal(e1, e2) and np.array_equal(z1, z2)
+
+
+def test_detect_noise_segments_matches_literal_loop():
+    pcm = speech_noise(30, 5).numpy().astype(np.float32)
+    # literal transcription of preprocessor.py:128-145
+    e, z = O.frame_stats_loop(pcm, SR)
+    nf = (e < np.percentile(e, 20)) & (z > np.percentile(z, 50) * 0.5)
+    segs, in_noise, start = [], False, 0
+    for i, v in enumerate(nf):
+        if v and not in_noise:
+            start, in_noise = i, True
+        elif not v and in_noise:
+            if (i - start) * 160 / SR >= 0.1:
+                segs.append((start * 160, i * 160))
+            in_noise = False
+    assert segs == O.detect_noise_segments(pcm, SR)
+    assert len(segs) > 0
+
+
+def test_mel_filters_match_transformers():
+    from transformers.audio_utils import mel_filter_bank
+    for n_mels in (80, 128):
+        hf = mel_filter_bank(201, n_mels, 0.0, 8000.0, 16000, norm="slaney", mel_scale="slaney").T
+        assert np.abs(O.mel_filters(n_mels) - hf.astype(np.float32)).max() < 1e-6
+
+
+def test_log_mel_matches_whisper_feature_extractor():
+    from transformers import WhisperFeatureExtractor
+    x = speech_noise(30, 2).numpy().astype(np.float32) / 32768.0
+    for n_mels in (80, 128):
+        hf = WhisperFeatureExtractor(feature_size=n_mels)(x, sampling_rate=SR, return_tensors="np")["input_features"][0]
+        assert np.abs(O.log_mel_spectrogram(x, n_mels, 0) - hf).max() <= 1e-6
+
+
+def test_peak_normalize_matches_audioop():
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        audioop = pytest.importorskip("audioop")
+    pcm = speech_noise(3, 1).numpy()
+    peak = audioop.max(pcm.tobytes(), 2)
+    want = np.frombuffer(audioop.mul(pcm.tobytes(), 2, O.peak_normalize_factor(peak)), dtype=np.int16)
+    assert np.array_equal(O.peak_normalize(pcm), want)
+    assert audioop.max(np.array([-32768], dtype=np.int16).tobytes(), 2) == 32768
+
+
+def test_loudness_matches_torchaudio_on_quiet_signal():
+    import torchaudio
+    x = speech_noise(20, 4).numpy().astype(np.float32) / 32768.0 * np.float32(0.5)
+    ta = torchaudio.functional.loudness(torch.from_numpy(x)[None], SR).item()
+    assert abs(O.integrated_loudness(x, SR) - ta) <= 1e-3
+
+
+def test_k_weighting_coefficients_at_16k():
+    (b1, a1), (b2, a2) = O.k_weighting_coeffs(16000)
+    assert np.allclose(b1, [1.444233908713844, -1.839542987741787, 0.685432300820589], atol=1e-12)
+    assert np.allclose(a1, [1.0, -1.1071392365035588, 0.3972624582962044], atol=1e-12)
+    assert np.allclose(b2, [0.9852425301500196, -1.9704850603000392, 0.9852425301500196], atol=1e-12)
+    assert np.allclose(a2, [1.0, -1.9703753578723906, 0.9705947627276879], atol=1e-12)
+
+
+def test_chunk_geometry():
+    assert O.chunk_table(960000) == [(0, 600000, 660000), (600000, 360000, 660000)]
+    assert O.chunk_table(480000) == [(0, 480000, 540000)]
+    assert O._stft(np.zeros(660000)).shape == (513, 2579)
+    assert O._stft(np.zeros(540000)).shape == (513, 2110)
+    vf, vt = O.smoothing_taps(16000)
+    assert len(vf) == 33 and len(vt) == 7 and abs(np.outer(vf, vt).sum() - 68.0) < 1e-9
+
+
+def test_loudness_glue_semantics():
+    silent = np.zeros(SR, dtype=np.int16)
+    out, lufs, applied = O.normalize_loudness(silent, SR)
+    assert not applied and not np.isfinite(lufs) and np.array_equal(out, silent)
+    with pytest.raises(ValueError):
+        O.integrated_loudness(np.zeros(100, dtype=np.float32), SR)
+    assert list(O.to_int16_trunc(np.array([1.7, -1.7, 40000.0], dtype=np.float32))) == [1, -1, -25536]
