@@ -68,12 +68,17 @@ MAF_HD void fft5(c32& v0, c32& v1, c32& v2, c32& v3, c32& v4) {
 // ------------------------------------------------------------------------------------------------------------
 // 512-point complex FFT, 64 threads, thread t holds 8 points.  Shared scratch: FFT512_SMEM c32 per transform.
 //   in : v[m] = x[t + 64 m]
-//   out: v[d] = X[u + 64 d] with u = fft512_out_base(t)
+//   out: v[d] = X[t + 64 d]  (fft512_out_base(t) == t)
 // tw512[e] = e^{-2 pi i e / 512}, e = 0..511.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int FFT512_SMEM = 8 * 72;
 
-MAF_HD int fft512_out_base(int t) { return (t >> 3) + 8 * (t & 7); }
+MAF_HD int fft512_out_base(int t) { return t; }
+
+// Exchange-2 layout.  Element (p, a, c) lives at ((p + 2a + 8c) & 15) + 16 a + 128 (c >> 1): a bijection onto 0..511
+// whose low 4 bits (the 8-byte bank within a half-warp) are distinct both for the step-2 writers
+// (half-warp = 2 p's x 8 a's, fixed c) and for the step-3 readers (half-warp = 8 p's x 2 c's, fixed a).
+MAF_HD int fft512_x2(int p, int a, int c) { return ((p + 2 * a + 8 * c) & 15) + 16 * a + 128 * (c >> 1); }
 
 MAF_HD void fft512_step1(c32 (&v)[8], c32* sm, const c32* tw512, int t) {
     fft8(v);
@@ -96,14 +101,15 @@ MAF_HD void fft512_step2_store(c32 (&v)[8], c32* sm, const c32* tw512, int t) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         c32 w = tw512[8 * a * c];
-        sm[p * 72 + 9 * a + c] = (c == 0) ? v[0] : cmul(v[c], w);
+        sm[fft512_x2(p, a, c)] = (c == 0) ? v[0] : cmul(v[c], w);
     }
 }
 // (barrier)
+// step 3: thread t handles (p = t & 7, c = t >> 3); its outputs are X[t + 64 d], d = 0..7 (natural order)
 MAF_HD void fft512_step3(c32 (&v)[8], const c32* sm, int t) {
-    const int p = t >> 3, c = t & 7;
+    const int p = t & 7, c = t >> 3;
 #pragma unroll
-    for (int a = 0; a < 8; ++a) v[a] = sm[p * 72 + 9 * a + c];
+    for (int a = 0; a < 8; ++a) v[a] = sm[fft512_x2(p, a, c)];
     fft8(v);
 }
 

@@ -49,13 +49,16 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     for (int i = tid; i < 200; i += 256) tw200[i] = cs.tw200[i];
     for (int i = tid; i < 201; i += 256) tw400[i] = cs.tw400[i];
 
+    __shared__ double s_factor;
     const int pkin = peak_normalize ? peak[item] : 0;
     const bool pn = peak_normalize && pkin > 0;
-    const double factor = pn ? peak_factor(pkin, target_peak) : 1.0;
+    if (tid == 0) s_factor = pn ? peak_factor(pkin, target_peak) : 1.0;     // pow / log10 in float64: once per CTA
     Gate gt; gt.applied = 0;
     if (gates) gt = gates[item];
     const int16_t* x = den16 + it.den_off;
     const long long np_global = it.n_global + padding;            // length of the zero-padded recording
+    __syncthreads();
+    const double factor = s_factor;
 
     // Stage the tile's samples: global index i = 160 f - 200 + e, reflected at the true ends of the zero-padded
     // recording.  The tile also writes the final PCM of the 32 hops it is centred on (the last tile up to the item's
@@ -65,23 +68,53 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
         const bool last_tile = lf0 + MEL_TILE >= it.mel_frames;
         const long long own_lo = i0 + W_NFFT / 2;
         const long long own_hi = last_tile ? it.g0 + it.own_len : own_lo + (long long)MEL_TILE * W_HOP;
-        for (int e = tid; e < MEL_SPAN; e += 256) {
-            const long long i = i0 + e;
-            long long r = i;
-            if (r < 0) r = -r;
-            if (r >= np_global) r = 2 * (np_global - 1) - r;
-            float a = 0.f;
-            if (r >= 0 && r < it.n_global) {
-                const long long l = r - it.g0;                    // item-relative index into the denoised samples
-                if (l >= -(long long)it.lo_avail && l < it.own_len + it.hi_avail) {
-                    int s = x[l];
-                    if (pn) s = peak_norm_sample(s, factor);
-                    const int q = gain_sample_m(s, gt);
-                    a = (float)q * (1.0f / 32768.0f);
-                    if (out16 && r == i && i >= own_lo && i < own_hi && l >= 0 && l < it.own_len) out16[it.out_off + l] = (int16_t)q;
+        const long long l0 = i0 - it.g0;                            // item-relative index of span[0]
+        const bool interior = i0 >= 0 && i0 + MEL_SPAN <= it.n_global && l0 >= -(long long)it.lo_avail &&
+                              l0 + MEL_SPAN <= it.own_len + it.hi_avail && ((it.den_off + l0) & 7) == 0 && !last_tile &&
+                              (!out16 || (((it.out_off + l0) & 7) == 0 && l0 + W_NFFT / 2 >= 0 && l0 + W_NFFT / 2 + MEL_TILE * W_HOP <= it.own_len));
+        if (interior) {
+            // fast path: no reflection, no padding, 16-byte loads and stores (i0, own_lo and the hop are multiples of 8)
+            for (int gq = tid; gq < MEL_SPAN / 8; gq += 256) {
+                const uint4 v = *reinterpret_cast<const uint4*>(x + l0 + 8 * gq);
+                int sv[8];
+                sv[0] = (short)(v.x & 0xffff); sv[1] = (short)(v.x >> 16); sv[2] = (short)(v.y & 0xffff); sv[3] = (short)(v.y >> 16);
+                sv[4] = (short)(v.z & 0xffff); sv[5] = (short)(v.z >> 16); sv[6] = (short)(v.w & 0xffff); sv[7] = (short)(v.w >> 16);
+                float a[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if (pn) sv[e] = peak_norm_sample(sv[e], factor);
+                    sv[e] = gain_sample_m(sv[e], gt);
+                    a[e] = (float)sv[e] * (1.0f / 32768.0f);
+                }
+                *reinterpret_cast<float4*>(span + 8 * gq) = make_float4(a[0], a[1], a[2], a[3]);
+                *reinterpret_cast<float4*>(span + 8 * gq + 4) = make_float4(a[4], a[5], a[6], a[7]);
+                const int e0 = 8 * gq;
+                if (out16 && e0 >= W_NFFT / 2 && e0 < W_NFFT / 2 + MEL_TILE * W_HOP) {
+                    uint4 o;
+                    o.x = (uint32_t)(sv[0] & 0xffff) | ((uint32_t)sv[1] << 16); o.y = (uint32_t)(sv[2] & 0xffff) | ((uint32_t)sv[3] << 16);
+                    o.z = (uint32_t)(sv[4] & 0xffff) | ((uint32_t)sv[5] << 16); o.w = (uint32_t)(sv[6] & 0xffff) | ((uint32_t)sv[7] << 16);
+                    *reinterpret_cast<uint4*>(out16 + it.out_off + l0 + e0) = o;
                 }
             }
-            span[e] = a;
+        } else {
+            for (int e = tid; e < MEL_SPAN; e += 256) {
+                const long long i = i0 + e;
+                long long r = i;
+                if (r < 0) r = -r;
+                if (r >= np_global) r = 2 * (np_global - 1) - r;
+                float a = 0.f;
+                if (r >= 0 && r < it.n_global) {
+                    const long long l = r - it.g0;                    // item-relative index into the denoised samples
+                    if (l >= -(long long)it.lo_avail && l < it.own_len + it.hi_avail) {
+                        int sv = x[l];
+                        if (pn) sv = peak_norm_sample(sv, factor);
+                        const int q = gain_sample_m(sv, gt);
+                        a = (float)q * (1.0f / 32768.0f);
+                        if (out16 && r == i && i >= own_lo && i < own_hi && l >= 0 && l < it.own_len) out16[it.out_off + l] = (int16_t)q;
+                    }
+                }
+                span[e] = a;
+            }
         }
     }
     __syncthreads();
@@ -109,13 +142,17 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
         for (int q = 0; q < 25; ++q) zb[lf * Z_PITCH + p + 8 * q] = o[q];
     }
     __syncthreads();
-    // real split + power
-    for (int w = tid; w < MEL_TILE * W_NBIN; w += 256) {
-        const int lf = w / W_NBIN, k = w - lf * W_NBIN;
-        const c32* z = zb + lf * Z_PITCH;
-        const c32 zk = z[k == 200 ? 0 : k], znk = z[k == 0 ? 0 : 200 - k];
-        const c32 X = rfft400_bin(zk, znk, tw400[k]);
-        pw[lf * P_PITCH + k] = X.x * X.x + X.y * X.y;
+    // real split + power: warp w takes frames w, w + 8, ...; lanes stride over the 201 bins
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int lf = warp; lf < MEL_TILE; lf += 8) {
+            const c32* z = zb + lf * Z_PITCH;
+            for (int k = lane; k < W_NBIN; k += 32) {
+                const c32 zk = z[k == 200 ? 0 : k], znk = z[k == 0 ? 0 : 200 - k];
+                const c32 X = rfft400_bin(zk, znk, tw400[k]);
+                pw[lf * P_PITCH + k] = X.x * X.x + X.y * X.y;
+            }
+        }
     }
     __syncthreads();
     // mel projection: warp-uniform mel row, lane = frame (coalesced 128 B row segments of the [n_mels, frames] output)

@@ -32,27 +32,50 @@ __global__ void __launch_bounds__(128) kweight_energy_kernel(const int16_t* __re
         if (begin < -(long long)it.lo_avail) begin = -(long long)it.lo_avail;
         long long end = start + tile_len;
         if (end > it.own_len) end = it.own_len;
-        // direct form II transposed, like scipy.signal.lfilter
+        // direct form II transposed, like scipy.signal.lfilter.  Samples are fetched and converted eight at a time so
+        // that only the four dependent DFMAs per sample sit on the recurrence's critical path.
         double z10 = 0.0, z11 = 0.0, z20 = 0.0, z21 = 0.0;
         double acc = 0.0;
-        for (long long i = begin; i < end; ++i) {
-            int s = x[i];
-            if (pn) s = peak_norm_sample(s, factor);
-            const float xin = (float)s * (1.0f / 32768.0f);
+        auto step = [&](float xin, int s, bool own) {
             const double xd = (double)xin;
             const double y1 = kw.b1[0] * xd + z10;
-            z10 = kw.b1[1] * xd - kw.a1[1] * y1 + z11;
+            z10 = (kw.b1[1] * xd + z11) - kw.a1[1] * y1;
             z11 = kw.b1[2] * xd - kw.a1[2] * y1;
-            const float d1 = (float)y1;
-            const double x2 = (double)d1;
+            const double x2 = (double)(float)y1;
             const double y2 = kw.b2[0] * x2 + z20;
-            z20 = kw.b2[1] * x2 - kw.a2[1] * y2 + z21;
+            z20 = (kw.b2[1] * x2 + z21) - kw.a2[1] * y2;
             z21 = kw.b2[2] * x2 - kw.a2[2] * y2;
             const float d = (float)y2;
-            if (i >= start) {
+            if (own) {
                 acc += (double)__fmul_rn(d, d);
                 pk = max(pk, s < 0 ? -s : s);
             }
+        };
+        long long i = begin;
+        const bool aligned = ((it.den_off + begin) & 7) == 0;
+        for (; i + 8 <= end; i += 8) {
+            int sv[8];
+            if (aligned) {
+                const uint4 v = *reinterpret_cast<const uint4*>(x + i);
+                sv[0] = (short)(v.x & 0xffff); sv[1] = (short)(v.x >> 16); sv[2] = (short)(v.y & 0xffff); sv[3] = (short)(v.y >> 16);
+                sv[4] = (short)(v.z & 0xffff); sv[5] = (short)(v.z >> 16); sv[6] = (short)(v.w & 0xffff); sv[7] = (short)(v.w >> 16);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) sv[e] = x[i + e];
+            }
+            float xin[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (pn) sv[e] = peak_norm_sample(sv[e], factor);
+                xin[e] = (float)sv[e] * (1.0f / 32768.0f);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) step(xin[e], sv[e], i + e >= start);
+        }
+        for (; i < end; ++i) {
+            int sv = x[i];
+            if (pn) sv = peak_norm_sample(sv, factor);
+            step((float)sv * (1.0f / 32768.0f), sv, i >= start);
         }
         sub_energy[it.ktile_first + tile] = acc;
     }
@@ -77,12 +100,14 @@ void launch_kweight_energy(const int16_t* den16, const Item* items, int n_items,
 }
 
 // ---- gating -----------------------------------------------------------------------------------------------------
+constexpr int GATE_THREADS = 1024;
+
 __device__ double block_sum(double v, double* sh) {
-    // deterministic tree reduction over 256 threads
+    // deterministic tree reduction over the CTA
     const int tid = threadIdx.x;
     sh[tid] = v;
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
+    for (int s = GATE_THREADS / 2; s > 0; s >>= 1) {
         if (tid < s) sh[tid] += sh[tid + s];
         __syncthreads();
     }
@@ -91,37 +116,36 @@ __device__ double block_sum(double v, double* sh) {
     return r;
 }
 
-__global__ void __launch_bounds__(256) gate_kernel(const double* __restrict__ sub_energy, const Item* __restrict__ items,
-                                                   double inv_block, double target_lufs, const int* __restrict__ peak_norm,
-                                                   Gate* __restrict__ gates) {
-    __shared__ double sh[256];
+// The two gates are evaluated on the block energies themselves: l_j >= -70 <=> z_j >= 10^((-70 + 0.691)/10) and
+// l_j > Gamma_r <=> z_j > mean(z_abs_gated) / 10 (BS.1770-4 eq. 5-7; pyloudnorm compares the equivalent dB values).
+__global__ void __launch_bounds__(GATE_THREADS) gate_kernel(const double* __restrict__ sub_energy, const Item* __restrict__ items,
+                                                            double inv_block, double target_lufs, const int* __restrict__ peak_norm,
+                                                            Gate* __restrict__ gates) {
+    __shared__ double sh[GATE_THREADS];
     const int item = blockIdx.x;
     const Item it = items[item];
     const double* sb = sub_energy + it.ktile_first;
     const int nb = it.n_blocks;
-    // pass 1: absolute gate
+    const double zabs = pow(10.0, (-70.0 + 0.691) / 10.0);
     double s = 0.0, c = 0.0;
-    for (int j = threadIdx.x; j < nb; j += 256) {
+    for (int j = threadIdx.x; j < nb; j += GATE_THREADS) {
         double e = sb[j];
         if (j + 1 < it.n_ktiles) e += sb[j + 1];
         if (j + 2 < it.n_ktiles) e += sb[j + 2];
         if (j + 3 < it.n_ktiles) e += sb[j + 3];
         const double z = inv_block * e;
-        const double l = -0.691 + 10.0 * log10(z);
-        if (l >= -70.0) { s += z; c += 1.0; }
+        if (z >= zabs) { s += z; c += 1.0; }
     }
     s = block_sum(s, sh); c = block_sum(c, sh);
-    const double gamma_r = -0.691 + 10.0 * log10(s / c) - 10.0;       // NaN when no block passes, like np.mean([])
-    // pass 2: relative and absolute gates
+    const double zrel = c > 0.0 ? (s / c) * 0.1 : NAN;                 // NaN threshold: nothing passes, like np.mean([])
     double s2 = 0.0, c2 = 0.0;
-    for (int j = threadIdx.x; j < nb; j += 256) {
+    for (int j = threadIdx.x; j < nb; j += GATE_THREADS) {
         double e = sb[j];
         if (j + 1 < it.n_ktiles) e += sb[j + 1];
         if (j + 2 < it.n_ktiles) e += sb[j + 2];
         if (j + 3 < it.n_ktiles) e += sb[j + 3];
         const double z = inv_block * e;
-        const double l = -0.691 + 10.0 * log10(z);
-        if (l > gamma_r && l > -70.0) { s2 += z; c2 += 1.0; }
+        if (z > zrel && z > zabs) { s2 += z; c2 += 1.0; }
     }
     s2 = block_sum(s2, sh); c2 = block_sum(c2, sh);
     if (threadIdx.x == 0) {
@@ -144,7 +168,7 @@ __global__ void __launch_bounds__(256) gate_kernel(const double* __restrict__ su
 void launch_gate(const double* sub_energy, const Item* items, int n_items, double inv_block, double target_lufs,
                  const int* peak_norm, Gate* gates, cudaStream_t st) {
     if (n_items <= 0) return;
-    gate_kernel<<<n_items, 256, 0, st>>>(sub_energy, items, inv_block, target_lufs, peak_norm, gates);
+    gate_kernel<<<n_items, GATE_THREADS, 0, st>>>(sub_energy, items, inv_block, target_lufs, peak_norm, gates);
 }
 
 // ---- standalone gain application ------------------------------------------------------------------------------------

@@ -15,15 +15,18 @@
 
 namespace maf {
 
-// 512-point FFT for the 64-thread group `t` of a 256-thread CTA; all 256 threads must call it (barriers inside).
+// 512-point FFT for one 64-thread group of a 256-thread CTA (group-local barriers inside).
 // in: v[m] = x[t + 64 m]; out: v[d] = X[fft512_out_base(t) + 64 d].  `sm` is this group's FFT512_SMEM scratch.
-__device__ __forceinline__ void group_fft512(c32 (&v)[8], c32* sm, const c32* tw512, int t) {
+// Barrier among the 64 threads (2 warps) of FFT group g only: named barriers 1..4, barrier 0 stays __syncthreads().
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory"); }
+
+__device__ __forceinline__ void group_fft512(c32 (&v)[8], c32* sm, const c32* tw512, int t, int g) {
     fft512_step1(v, sm, tw512, t);
-    __syncthreads();
+    group_bar(g);
     fft512_step2_load(v, sm, t);
-    __syncthreads();
+    group_bar(g);
     fft512_step2_store(v, sm, tw512, t);
-    __syncthreads();
+    group_bar(g);
     fft512_step3(v, sm, t);
 }
 
@@ -83,6 +86,9 @@ __global__ void __launch_bounds__(256) stft1024_kernel(const int16_t* __restrict
     const float* t2hi = STATIONARY ? T2hi + (long long)ch.item * T_PITCH : nullptr;
     uint8_t* rf = STATIONARY ? rowflag + (long long)blockIdx.y * M_PITCH : nullptr;
 
+    // the four 64-thread groups run decoupled from here on: span / tables are read-only, fsm / flags are per group
+    const short2* span2 = reinterpret_cast<const short2*>(span);
+    const float2* win2 = reinterpret_cast<const float2*>(win);
     for (int r = 0; r < STFT_TILE / 4; ++r) {
         const int lf = r * 4 + g;
         const int f = f0 + lf;
@@ -91,17 +97,15 @@ __global__ void __launch_bounds__(256) stft1024_kernel(const int16_t* __restrict
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
             const int n = t + 64 * m;
-            const int i = lf * HOP + 2 * n;
-            v[m] = mk((float)span[i] * win[2 * n], (float)span[i + 1] * win[2 * n + 1]);
+            const short2 sv = span2[lf * (HOP / 2) + n];
+            const float2 w = win2[n];
+            v[m] = mk((float)sv.x * w.x, (float)sv.y * w.y);
         }
-        group_fft512(v, fsm[g], tw512, t);
-        __syncthreads();
-        {
-            const int u = fft512_out_base(t);
+        group_fft512(v, fsm[g], tw512, t, g);
+        group_bar(g);
 #pragma unroll
-            for (int d = 0; d < 8; ++d) fsm[g][u + 64 * d] = v[d];
-        }
-        __syncthreads();
+        for (int d = 0; d < 8; ++d) fsm[g][t + 64 * d] = v[d];
+        group_bar(g);
         if (active) {
             c32* row = S + (ch.row0 + f) * S_PITCH;
             const c32* z = fsm[g];
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(256) stft1024_kernel(const int16_t* __restrict
             }
         }
         if (STATIONARY) {
-            __syncthreads();
+            group_bar(g);
             if (active && t < 17) {
                 const uint32_t* fw = reinterpret_cast<const uint32_t*>(&flags[g][32 * t]);
                 uint32_t word = 0;
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(256) stft1024_kernel(const int16_t* __restrict
                 bits[(ch.row0 + f) * B_PITCH + t] = word;
             }
         }
-        __syncthreads();
+        group_bar(g);
     }
 }
 
@@ -232,14 +236,11 @@ __global__ void __launch_bounds__(256) noise_pass_kernel(const int16_t* __restri
             }
             v[m] = mk(a * win[2 * n], b * win[2 * n + 1]);
         }
-        group_fft512(v, fsm[g], tw512, t);
-        __syncthreads();
-        {
-            const int u = fft512_out_base(t);
+        group_fft512(v, fsm[g], tw512, t, g);
+        group_bar(g);
 #pragma unroll
-            for (int d = 0; d < 8; ++d) fsm[g][u + 64 * d] = v[d];
-        }
-        __syncthreads();
+        for (int d = 0; d < 8; ++d) fsm[g][t + 64 * d] = v[d];
+        group_bar(g);
         if (active) {
             const c32* z = fsm[g];
 #pragma unroll
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(256) noise_pass_kernel(const int16_t* __restri
                 }
             }
         }
-        __syncthreads();
+        group_bar(g);
     }
     // publish
     if (PASS == 1) {
@@ -339,55 +340,119 @@ void launch_noise_threshold(const int16_t* pcm, const Clip* clips, int n_items, 
 // Deviation (documented in DESIGN.md): where Sm == 0 (an all-zero frequency row) noisereduce yields NaN; here the
 // relative excess is taken as 0 so the mask is sigmoid(-20) and the output is silence instead of NaN.
 // ============================================================================================================
-__device__ __forceinline__ float bin_abs(const c32* row, int k) {
-    if (k == 0) return fabsf(row[0].x);
-    if (k == 512) return fabsf(row[0].y);
-    const c32 x = row[k];
-    return sqrtf(x.x * x.x + x.y * x.y);
-}
+constexpr int NS_BINS = 32;          // bins per CTA: one 256-byte segment of every S row
+constexpr int NS_TT = 64;            // frames per streamed tile
+constexpr int NS_THREADS = 128;
+constexpr int NS_PITCH = NS_BINS + 1;
 
-__global__ void __launch_bounds__(128) ns_mask_kernel(const c32* __restrict__ S, const Chunk* __restrict__ chunks, double b,
-                                                      float thresh_mult, float slope, float* __restrict__ M0) {
+// A CTA owns (chunk, 32 bins) -- plus bin 512, which shares slot 0 with bin 0, for group 0 -- and streams the chunk's
+// frames through shared memory in tiles of 64: all threads load the tile with 16-byte coalesced accesses (the next tile
+// is prefetched into registers while the current one is processed), lanes 0..32 run the serial one-pole recurrence over
+// the tile from shared memory, all threads write the tile back.  Forward pass writes yf into M0, the backward pass
+// re-reads S and yf in reverse and overwrites M0 with the sigmoid mask.
+__global__ void __launch_bounds__(NS_THREADS, 6) ns_mask_kernel(const c32* __restrict__ S, const Chunk* __restrict__ chunks, double b,
+                                                             float thresh_mult, float slope, float* __restrict__ M0) {
+    __shared__ float A[NS_TT][NS_PITCH];
+    __shared__ float Y[NS_TT][NS_PITCH];
     const Chunk ch = chunks[blockIdx.y];
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= NBIN) return;
+    const int gi = blockIdx.x;
     const int F = ch.n_frames;
-    const c32* s = S + ch.row0 * S_PITCH;
-    float* m = M0 + ch.row0 * M_PITCH + k;
+    const int tid = threadIdx.x;
+    const bool has_nyq = gi == 0;
+    const int nser = has_nyq ? NS_BINS + 1 : NS_BINS;
+    const float4* s4 = reinterpret_cast<const float4*>(S + ch.row0 * S_PITCH + gi * NS_BINS);   // row pitch = 256 float4
+    float* m0 = M0 + ch.row0 * M_PITCH + gi * NS_BINS;
     const double a = 1.0 - b;
-    // forward pass, steady-state start (lfilter_zi): y[-1] = x[0]
-    double y = (double)bin_abs(s, k);
-    constexpr int U = 8;
-    int f = 0;
-    for (; f + U <= F; f += U) {
-        float x[U];
+    const int n_tiles = (F + NS_TT - 1) / NS_TT;
+
+    float4 ps[8];                                   // prefetched S tile: element idx = tid + 128 i -> row idx/16, float4 idx%16
+    auto load_s = [&](int f0) {
 #pragma unroll
-        for (int j = 0; j < U; ++j) x[j] = bin_abs(s + (long long)(f + j) * S_PITCH, k);
-#pragma unroll
-        for (int j = 0; j < U; ++j) { y = b * (double)x[j] + a * y; m[(long long)(f + j) * M_PITCH] = (float)y; }
-    }
-    for (; f < F; ++f) { y = b * (double)bin_abs(s + (long long)f * S_PITCH, k) + a * y; m[(long long)f * M_PITCH] = (float)y; }
-    // backward pass over the forward output, again started in steady state
-    double z = (double)m[(long long)(F - 1) * M_PITCH];
-    f = F - 1;
-    for (; f - U + 1 >= 0; f -= U) {
-        float x[U], yf[U];
-#pragma unroll
-        for (int j = 0; j < U; ++j) { x[j] = bin_abs(s + (long long)(f - j) * S_PITCH, k); yf[j] = m[(long long)(f - j) * M_PITCH]; }
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-            z = b * (double)yf[j] + a * z;
-            const float sm = (float)z;
-            const float r = sm > 0.f ? (x[j] - sm) / sm : 0.f;
-            m[(long long)(f - j) * M_PITCH] = 1.0f / (1.0f + expf(-(r - thresh_mult) * slope));
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + NS_THREADS * i, r = idx >> 4, c = idx & 15;
+            ps[i] = (f0 + r < F) ? __ldg(s4 + (long long)(f0 + r) * (S_PITCH / 2) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    };
+    auto put_abs = [&]() {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + NS_THREADS * i, r = idx >> 4, c = idx & 15;
+            if (has_nyq && c == 0) { A[r][0] = fabsf(ps[i].x); A[r][NS_BINS] = fabsf(ps[i].y); }
+            else A[r][2 * c] = sqrtf(ps[i].x * ps[i].x + ps[i].y * ps[i].y);
+            A[r][2 * c + 1] = sqrtf(ps[i].z * ps[i].z + ps[i].w * ps[i].w);
+        }
+    };
+
+    // ---------------- forward pass (steady-state start: y[-1] = x[0]) ----------------
+    double y = 0.0;
+    load_s(0);
+    for (int tI = 0; tI < n_tiles; ++tI) {
+        const int f0 = tI * NS_TT;
+        const int rows = min(NS_TT, F - f0);
+        put_abs();
+        __syncthreads();
+        if (tI + 1 < n_tiles) load_s(f0 + NS_TT);
+        if (tid < nser) {
+            if (tI == 0) y = (double)A[0][tid];
+            for (int r = 0; r < rows; ++r) { y = b * (double)A[r][tid] + a * y; Y[r][tid] = (float)y; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int idx = tid + NS_THREADS * i, r = idx >> 5, c = idx & 31;
+            if (r < rows) m0[(long long)(f0 + r) * M_PITCH + c] = Y[r][c];
+        }
+        if (has_nyq && tid < rows) M0[(ch.row0 + f0 + tid) * M_PITCH + 512] = Y[tid][NS_BINS];
+        // the next iteration's put_abs only touches A, and Y is rewritten after the next barrier: no extra barrier needed
     }
-    for (; f >= 0; --f) {
-        const float x = bin_abs(s + (long long)f * S_PITCH, k);
-        z = b * (double)m[(long long)f * M_PITCH] + a * z;
-        const float sm = (float)z;
-        const float r = sm > 0.f ? (x - sm) / sm : 0.f;
-        m[(long long)f * M_PITCH] = 1.0f / (1.0f + expf(-(r - thresh_mult) * slope));
+    // ---------------- backward pass over yf, again started in steady state ----------------
+    double z = (double)(float)y;                    // yf[F - 1] as stored
+    float4 py[4];
+    auto load_y = [&](int f0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + NS_THREADS * i, r = idx >> 3, c = idx & 7;
+            py[i] = (f0 + r < F) ? *reinterpret_cast<const float4*>(m0 + (long long)(f0 + r) * M_PITCH + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    __syncthreads();
+    load_s((n_tiles - 1) * NS_TT);
+    load_y((n_tiles - 1) * NS_TT);
+    float ynyq = (has_nyq && tid < NS_TT && (n_tiles - 1) * NS_TT + tid < F) ? M0[(ch.row0 + (n_tiles - 1) * NS_TT + tid) * M_PITCH + 512] : 0.f;
+    for (int tI = n_tiles - 1; tI >= 0; --tI) {
+        const int f0 = tI * NS_TT;
+        const int rows = min(NS_TT, F - f0);
+        put_abs();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + NS_THREADS * i, r = idx >> 3, c = idx & 7;
+            Y[r][4 * c] = py[i].x; Y[r][4 * c + 1] = py[i].y; Y[r][4 * c + 2] = py[i].z; Y[r][4 * c + 3] = py[i].w;
+        }
+        if (has_nyq && tid < NS_TT) Y[tid][NS_BINS] = ynyq;
+        __syncthreads();
+        if (tI > 0) {
+            load_s(f0 - NS_TT); load_y(f0 - NS_TT);
+            if (has_nyq && tid < NS_TT) ynyq = M0[(ch.row0 + f0 - NS_TT + tid) * M_PITCH + 512];
+        }
+        if (tid < nser) {
+            for (int r = rows - 1; r >= 0; --r) { z = b * (double)Y[r][tid] + a * z; Y[r][tid] = (float)z; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int idx = tid + NS_THREADS * i, r = idx >> 5, c = idx & 31;
+            if (r < rows) {
+                const float sm = Y[r][c], x = A[r][c];
+                const float rr = sm > 0.f ? (x - sm) / sm : 0.f;
+                m0[(long long)(f0 + r) * M_PITCH + c] = 1.0f / (1.0f + expf(-(rr - thresh_mult) * slope));
+            }
+        }
+        if (has_nyq && tid < rows) {
+            const float sm = Y[tid][NS_BINS], x = A[tid][NS_BINS];
+            const float rr = sm > 0.f ? (x - sm) / sm : 0.f;
+            M0[(ch.row0 + f0 + tid) * M_PITCH + 512] = 1.0f / (1.0f + expf(-(rr - thresh_mult) * slope));
+        }
+        __syncthreads();
     }
 }
 
@@ -396,8 +461,8 @@ void launch_ns_mask(const c32* S, const Chunk* chunks, int n_chunks, double b, f
     if (n_chunks <= 0) return;
     for (int y0 = 0; y0 < n_chunks; y0 += 32768) {
         const int ny = n_chunks - y0 < 32768 ? n_chunks - y0 : 32768;
-        dim3 grid((NBIN + 127) / 128, ny);
-        ns_mask_kernel<<<grid, 128, 0, st>>>(S, chunks + y0, b, thresh_mult, slope, M0);
+        dim3 grid(S_PITCH / NS_BINS, ny);
+        ns_mask_kernel<<<grid, NS_THREADS, 0, st>>>(S, chunks + y0, b, thresh_mult, slope, M0);
     }
 }
 
@@ -452,6 +517,31 @@ __global__ void __launch_bounds__(256) smooth_mask_kernel(const uint32_t* __rest
 #pragma unroll
             for (int b = 0; b < 32; ++b) if (b < nb) rows[lf][MAX_NF + 32 * wi + b] = acc[b];
         }
+    } else if (nt == 3) {
+        // one work item = 4 consecutive bins x 8 output frames: 14 float4 row loads feed 8 outputs (sliding window)
+        for (int w = tid; w < 2 * 129; w += 256) {
+            const int q = w >> 1, h = w & 1;
+            const int fa = f0 + 8 * h;                       // first output frame of this item
+            const float* src = M0 + ch.row0 * M_PITCH + 4 * q;
+            float4 x[14];
+#pragma unroll
+            for (int j = 0; j < 14; ++j) {
+                const int ff = fa - 3 + j;
+                x[j] = (ff >= 0 && ff < ch.n_frames) ? *reinterpret_cast<const float4*>(src + (long long)ff * M_PITCH) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const float t0 = taps.vt[0], t1 = taps.vt[1], t2 = taps.vt[2], t3 = taps.vt[3];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                if (fa + o >= ch.n_frames) break;
+                float4 r;
+                r.x = t0 * (x[o].x + x[o + 6].x) + t1 * (x[o + 1].x + x[o + 5].x) + t2 * (x[o + 2].x + x[o + 4].x) + t3 * x[o + 3].x;
+                r.y = t0 * (x[o].y + x[o + 6].y) + t1 * (x[o + 1].y + x[o + 5].y) + t2 * (x[o + 2].y + x[o + 4].y) + t3 * x[o + 3].y;
+                r.z = t0 * (x[o].z + x[o + 6].z) + t1 * (x[o + 1].z + x[o + 5].z) + t2 * (x[o + 2].z + x[o + 4].z) + t3 * x[o + 3].z;
+                r.w = t0 * (x[o].w + x[o + 6].w) + t1 * (x[o + 1].w + x[o + 5].w) + t2 * (x[o + 2].w + x[o + 4].w) + t3 * x[o + 3].w;
+                if (q == 128) { r.y = 0.f; r.z = 0.f; r.w = 0.f; }           // bins 513..515 are row padding
+                *reinterpret_cast<float4*>(&rows[8 * h + o][MAX_NF + 4 * q]) = r;
+            }
+        }
     } else {
         for (int e = tid; e < MASK_TILE * NBIN; e += 256) {
             const int lf = e / NBIN, k = e - lf * NBIN;
@@ -478,18 +568,28 @@ __global__ void __launch_bounds__(256) smooth_mask_kernel(const uint32_t* __rest
         for (int o = 0; o < 8; ++o) out[o] = 0.f;
         const float* src = &rows[lf][MAX_NF + k0];
         if (nf == 16) {
+            // triangle(33) = box(17) * box(17) / 289: two running sums restarted per work item (<= 23 updates each)
             float in[40];
 #pragma unroll
             for (int i = 0; i < 10; ++i) {
                 const float4 q = *reinterpret_cast<const float4*>(src - 16 + 4 * i);
                 in[4 * i] = q.x; in[4 * i + 1] = q.y; in[4 * i + 2] = q.z; in[4 * i + 3] = q.w;
             }
+            float b1[24];                                   // b1[i] = sum in[i .. i + 16]  (centre k0 - 8 + i)
+            float acc = 0.f;
 #pragma unroll
-            for (int tp = 0; tp < 33; ++tp) {
-                const float wt = taps.vf[tp];
+            for (int i = 0; i < 17; ++i) acc += in[i];
+            b1[0] = acc;
 #pragma unroll
-                for (int o = 0; o < 8; ++o) out[o] += wt * in[o + tp];
-            }
+            for (int i = 1; i < 24; ++i) { acc += in[i + 16] - in[i - 1]; b1[i] = acc; }
+            float a2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 17; ++i) a2 += b1[i];
+            out[0] = a2;
+#pragma unroll
+            for (int o = 1; o < 8; ++o) { a2 += b1[o + 16] - b1[o - 1]; out[o] = a2; }
+#pragma unroll
+            for (int o = 0; o < 8; ++o) out[o] *= (1.0f / 289.0f);
         } else {
             for (int tp = 0; tp <= 2 * nf; ++tp) {
                 const float wt = taps.vf[tp];
@@ -584,25 +684,26 @@ __global__ void __launch_bounds__(256) istft_kernel(const c32* __restrict__ S, c
                 }
             }
         }
-        __syncthreads();
+        group_bar(g);
         c32 v[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m) v[m] = active ? z[t + 64 * m] : mk(0.f, 0.f);
-        __syncthreads();
-        group_fft512(v, z, tw512, t);
+        group_bar(g);
+        group_fft512(v, z, tw512, t, g);
         if (active) {
-            const int u = fft512_out_base(t);
             float2* o2 = reinterpret_cast<float2*>(ola + lf * HOP);
+            const float2* w2 = reinterpret_cast<const float2*>(winv);
 #pragma unroll
             for (int d = 0; d < 8; ++d) {
-                const int n = u + 64 * d;
+                const int n = t + 64 * d;
                 float2 acc = o2[n];
-                acc.x += v[d].x * winv[2 * n];
-                acc.y += -v[d].y * winv[2 * n + 1];
+                const float2 w = w2[n];
+                acc.x += v[d].x * w.x;
+                acc.y += -v[d].y * w.y;
                 o2[n] = acc;
             }
         }
-        __syncthreads();
+        __syncthreads();            // the overlap-add buffer is shared by all four groups: one CTA-wide barrier per round
     }
     // emit: segment g covers padded-chunk samples [256 g, 256 g + 256) = ola[768 + 256 (g - g0) ...]
     int pk = 0;
