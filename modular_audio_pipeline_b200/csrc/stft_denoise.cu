@@ -340,18 +340,18 @@ void launch_noise_threshold(const int16_t* pcm, const Clip* clips, int n_items, 
 // Deviation (documented in DESIGN.md): where Sm == 0 (an all-zero frequency row) noisereduce yields NaN; here the
 // relative excess is taken as 0 so the mask is sigmoid(-20) and the output is silence instead of NaN.
 // ============================================================================================================
-constexpr int NS_BINS = 32;          // bins per CTA: one 256-byte segment of every S row
-constexpr int NS_TT = 64;            // frames per streamed tile
+constexpr int NS_BINS = 64;          // bins per CTA: one 512-byte segment of every S row, 256 bytes of every M0 row
+constexpr int NS_TT = 32;            // frames per streamed tile
 constexpr int NS_THREADS = 128;
 constexpr int NS_PITCH = NS_BINS + 1;
 
-// A CTA owns (chunk, 32 bins) -- plus bin 512, which shares slot 0 with bin 0, for group 0 -- and streams the chunk's
-// frames through shared memory in tiles of 64: all threads load the tile with 16-byte coalesced accesses (the next tile
-// is prefetched into registers while the current one is processed), lanes 0..32 run the serial one-pole recurrence over
+// A CTA owns (chunk, 64 bins) -- plus bin 512, which shares slot 0 with bin 0, for group 0 -- and streams the chunk's
+// frames through shared memory in tiles of 32: all threads load the tile with 16-byte coalesced accesses (the next tile
+// is prefetched into registers while the current one is processed), lanes 0..64 run the serial one-pole recurrence over
 // the tile from shared memory, all threads write the tile back.  Forward pass writes yf into M0, the backward pass
-// re-reads S and yf in reverse and overwrites M0 with the sigmoid mask.
+// re-reads S and yf in reverse and overwrites M0 with the sigmoid mask.  8 groups x chunks CTAs, all resident at once.
 __global__ void __launch_bounds__(NS_THREADS, 6) ns_mask_kernel(const c32* __restrict__ S, const Chunk* __restrict__ chunks, double b,
-                                                             float thresh_mult, float slope, float* __restrict__ M0) {
+                                                                float thresh_mult, float slope, float* __restrict__ M0) {
     __shared__ float A[NS_TT][NS_PITCH];
     __shared__ float Y[NS_TT][NS_PITCH];
     const Chunk ch = chunks[blockIdx.y];
@@ -365,18 +365,18 @@ __global__ void __launch_bounds__(NS_THREADS, 6) ns_mask_kernel(const c32* __res
     const double a = 1.0 - b;
     const int n_tiles = (F + NS_TT - 1) / NS_TT;
 
-    float4 ps[8];                                   // prefetched S tile: element idx = tid + 128 i -> row idx/16, float4 idx%16
+    float4 ps[8];                                   // prefetched S tile: element idx = tid + 128 i -> row idx/32, float4 idx%32
     auto load_s = [&](int f0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int idx = tid + NS_THREADS * i, r = idx >> 4, c = idx & 15;
+            const int idx = tid + NS_THREADS * i, r = idx >> 5, c = idx & 31;
             ps[i] = (f0 + r < F) ? __ldg(s4 + (long long)(f0 + r) * (S_PITCH / 2) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
     auto put_abs = [&]() {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int idx = tid + NS_THREADS * i, r = idx >> 4, c = idx & 15;
+            const int idx = tid + NS_THREADS * i, r = idx >> 5, c = idx & 31;
             if (has_nyq && c == 0) { A[r][0] = fabsf(ps[i].x); A[r][NS_BINS] = fabsf(ps[i].y); }
             else A[r][2 * c] = sqrtf(ps[i].x * ps[i].x + ps[i].y * ps[i].y);
             A[r][2 * c + 1] = sqrtf(ps[i].z * ps[i].z + ps[i].w * ps[i].w);
@@ -394,12 +394,13 @@ __global__ void __launch_bounds__(NS_THREADS, 6) ns_mask_kernel(const c32* __res
         if (tI + 1 < n_tiles) load_s(f0 + NS_TT);
         if (tid < nser) {
             if (tI == 0) y = (double)A[0][tid];
+#pragma unroll 8
             for (int r = 0; r < rows; ++r) { y = b * (double)A[r][tid] + a * y; Y[r][tid] = (float)y; }
         }
         __syncthreads();
-#pragma unroll
+#pragma unroll 4
         for (int i = 0; i < 16; ++i) {
-            const int idx = tid + NS_THREADS * i, r = idx >> 5, c = idx & 31;
+            const int idx = tid + NS_THREADS * i, r = idx >> 6, c = idx & 63;
             if (r < rows) m0[(long long)(f0 + r) * M_PITCH + c] = Y[r][c];
         }
         if (has_nyq && tid < rows) M0[(ch.row0 + f0 + tid) * M_PITCH + 512] = Y[tid][NS_BINS];
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(NS_THREADS, 6) ns_mask_kernel(const c32* __res
     auto load_y = [&](int f0) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int idx = tid + NS_THREADS * i, r = idx >> 3, c = idx & 7;
+            const int idx = tid + NS_THREADS * i, r = idx >> 4, c = idx & 15;
             py[i] = (f0 + r < F) ? *reinterpret_cast<const float4*>(m0 + (long long)(f0 + r) * M_PITCH + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(NS_THREADS, 6) ns_mask_kernel(const c32* __res
         put_abs();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int idx = tid + NS_THREADS * i, r = idx >> 3, c = idx & 7;
+            const int idx = tid + NS_THREADS * i, r = idx >> 4, c = idx & 15;
             Y[r][4 * c] = py[i].x; Y[r][4 * c + 1] = py[i].y; Y[r][4 * c + 2] = py[i].z; Y[r][4 * c + 3] = py[i].w;
         }
         if (has_nyq && tid < NS_TT) Y[tid][NS_BINS] = ynyq;
@@ -435,22 +436,23 @@ __global__ void __launch_bounds__(NS_THREADS, 6) ns_mask_kernel(const c32* __res
             if (has_nyq && tid < NS_TT) ynyq = M0[(ch.row0 + f0 - NS_TT + tid) * M_PITCH + 512];
         }
         if (tid < nser) {
+#pragma unroll 8
             for (int r = rows - 1; r >= 0; --r) { z = b * (double)Y[r][tid] + a * z; Y[r][tid] = (float)z; }
         }
         __syncthreads();
-#pragma unroll
+#pragma unroll 4
         for (int i = 0; i < 16; ++i) {
-            const int idx = tid + NS_THREADS * i, r = idx >> 5, c = idx & 31;
+            const int idx = tid + NS_THREADS * i, r = idx >> 6, c = idx & 63;
             if (r < rows) {
                 const float sm = Y[r][c], x = A[r][c];
                 const float rr = sm > 0.f ? (x - sm) / sm : 0.f;
-                m0[(long long)(f0 + r) * M_PITCH + c] = 1.0f / (1.0f + expf(-(rr - thresh_mult) * slope));
+                m0[(long long)(f0 + r) * M_PITCH + c] = 1.0f / (1.0f + __expf(-(rr - thresh_mult) * slope));
             }
         }
         if (has_nyq && tid < rows) {
             const float sm = Y[tid][NS_BINS], x = A[tid][NS_BINS];
             const float rr = sm > 0.f ? (x - sm) / sm : 0.f;
-            M0[(ch.row0 + f0 + tid) * M_PITCH + 512] = 1.0f / (1.0f + expf(-(rr - thresh_mult) * slope));
+            M0[(ch.row0 + f0 + tid) * M_PITCH + 512] = 1.0f / (1.0f + __expf(-(rr - thresh_mult) * slope));
         }
         __syncthreads();
     }

@@ -1,0 +1,247 @@
+"""GpuAudioPreprocessor -- drop-in for ``audio_pipeline.preprocessor.AudioPreprocessor`` (reference
+``audio_pipeline/preprocessor.py:35-405``) behind ``PreprocessorProtocol`` (``protocols.py:68-90``).
+
+Same constructor, same method names, argument meaning, output file names and error behaviour as the reference
+class, so ``AudioPipeline(config, preprocessor=GpuAudioPreprocessor.from_config(config))`` runs unchanged.
+Every numerical stage is a CUDA kernel of libmaf_b200.so; this file only does WAV I/O and path bookkeeping.
+
+Beyond the Protocol ("fast path"): results of a stage stay resident on the GPU keyed by the
+output path, so the next Protocol call on that path skips the disk read and the PCIe upload; ``process()`` is the
+fused in-memory entry (denoise -> peak normalise -> loudness -> log-mel in one call).
+"""
+from __future__ import annotations
+
+import contextlib
+import logging
+import os
+import wave
+from pathlib import Path
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .frontend import FrontEnd, MafError
+
+logger = logging.getLogger(__name__)
+
+try:  # use the reference's own types when its package is importable, so isinstance / except clauses line up
+    from audio_pipeline.exceptions import AudioProcessingError  # type: ignore
+    from audio_pipeline.protocols import TimestampMapping  # type: ignore
+except Exception:  # pragma: no cover - the reference package needs pydub / noisereduce at import time
+    from ._compat import AudioProcessingError, TimestampMapping
+
+from ._compat import NoiseReductionConfig
+
+__all__ = ["GpuAudioPreprocessor"]
+
+
+class GpuAudioPreprocessor:
+    """Noise reduction, peak / loudness normalisation and silence removal on a B200."""
+
+    def __init__(self, sample_rate: int, temp_dir: str, noise_config=None, device=None, stationary: bool = True):
+        self.sample_rate = sample_rate
+        self.temp_dir = temp_dir
+        self.noise_config = noise_config or NoiseReductionConfig()
+        self.stationary = stationary
+        self._device = device
+        self._fe: Optional[FrontEnd] = None
+        self._resident: Dict[str, Tuple[torch.Tensor, int, float]] = {}   # path -> (int16 device tensor, sr, mtime)
+        os.makedirs(temp_dir, exist_ok=True)
+
+    @classmethod
+    def from_config(cls, config, **kw) -> "GpuAudioPreprocessor":
+        """preprocessor.py:62-69."""
+        return cls(sample_rate=config.audio.sample_rate, temp_dir=config.temp_dir, noise_config=config.noise_reduction, **kw)
+
+    # ---- plumbing ---------------------------------------------------------------------------------------------------
+    @property
+    def frontend(self) -> FrontEnd:
+        if self._fe is None:
+            self._fe = FrontEnd(self._device)
+        return self._fe
+
+    def read_wave(self, path: str) -> Tuple[bytes, int]:
+        """preprocessor.py:71-79 (channel count and sample width are ignored there too)."""
+        try:
+            with contextlib.closing(wave.open(path, "rb")) as wf:
+                sr = wf.getframerate()
+                pcm = wf.readframes(wf.getnframes())
+            return pcm, sr
+        except Exception as e:
+            raise AudioProcessingError(f"Failed to read WAV file: {path}", details=str(e))
+
+    def write_wave(self, path: str, audio: bytes, sample_rate: int) -> None:
+        """preprocessor.py:81-90: always mono, 16-bit."""
+        try:
+            with wave.open(path, "wb") as wf:
+                wf.setnchannels(1)
+                wf.setsampwidth(2)
+                wf.setframerate(sample_rate)
+                wf.writeframes(audio)
+        except Exception as e:
+            raise AudioProcessingError(f"Failed to write WAV file: {path}", details=str(e))
+
+    def _read_wav_info(self, path: str):
+        with contextlib.closing(wave.open(path, "rb")) as wf:
+            return wf.getnchannels(), wf.getsampwidth(), wf.getframerate(), wf.readframes(wf.getnframes())
+
+    def _upload(self, path: str) -> Tuple[torch.Tensor, int]:
+        """int16 samples of `path` on the device (resident copy of an earlier stage's output when still valid)."""
+        hit = self._resident.get(path)
+        if hit is not None:
+            try:
+                if os.path.getmtime(path) == hit[2]:
+                    return hit[0], hit[1]
+            except OSError:
+                pass
+            self._resident.pop(path, None)       # temp_dir may have been wiped (media_handler.py:98-102)
+        pcm, sr = self.read_wave(path)
+        x = torch.frombuffer(bytearray(pcm), dtype=torch.int16)
+        return x.to(self.frontend.device, non_blocking=True), sr
+
+    def _store(self, path: str, dev: torch.Tensor, sr: int) -> None:
+        self.write_wave(path, dev.cpu().numpy().tobytes(), sr)
+        self._resident.clear()                   # keep exactly one stage output resident
+        self._resident[path] = (dev, sr, os.path.getmtime(path))
+
+    # ---- noise-clip detection (preprocessor.py:92-147) ---------------------------------------------------------------
+    def _detect_noise_segments(self, audio: np.ndarray, sr: int) -> List[Tuple[int, int]]:
+        """All (start, end) noise segments.  Frame energies / zero crossings come from the S0 kernel; the percentile
+        thresholds and the run decoding of :125-145 are repeated here on the (small) per-frame arrays."""
+        x = torch.from_numpy(np.asarray(audio).astype(np.int16)).to(self.frontend.device)
+        plan = self.frontend.plan([x.numel()], sample_rate=sr, n_mels=0)
+        e, z = plan.frame_stats(plan.pack([x]))
+        energies = e.cpu().numpy().astype(np.float64)
+        frame_length, hop_length = int(sr * 0.025), int(sr * 0.010)
+        zcrs = z.cpu().numpy() / frame_length
+        if len(energies) == 0:
+            return []
+        noise = (energies < np.percentile(energies, 20)) & (zcrs > np.percentile(zcrs, 50) * 0.5)
+        segs, in_noise, start = [], False, 0
+        for i, is_noise in enumerate(noise):
+            if is_noise and not in_noise:
+                start, in_noise = i, True
+            elif not is_noise and in_noise:
+                if (i - start) * hop_length / sr >= 0.1:
+                    segs.append((start * hop_length, i * hop_length))
+                in_noise = False
+        return segs
+
+    # ---- Protocol methods -----------------------------------------------------------------------------------------
+    def reduce_stationary_noise(self, input_wav: str, noise_sample_path: Optional[str] = None) -> str:
+        """preprocessor.py:149-214: spectral-gating denoise with an auto-detected, explicit or leading noise clip."""
+        if not self.noise_config.enabled:
+            logger.info("Noise reduction disabled, skipping")
+            return input_wav
+        x, sr = self._upload(input_wav)
+        try:
+            fe = self.frontend
+            if noise_sample_path:
+                noise, _ = self._upload(noise_sample_path)
+                plan = fe.plan([x.numel()], sample_rate=sr, stationary=self.stationary, external_noise=True, n_mels=0)
+                plan.set_noise_clips([0], [noise.numel()])
+                out, _, _ = plan.denoise(plan.pack([x]), noise_pcm=noise.contiguous())
+            else:
+                plan = fe.plan([x.numel()], sample_rate=sr, stationary=self.stationary,
+                               auto_detect_noise=bool(self.noise_config.auto_detect_noise),
+                               noise_sample_duration_s=float(self.noise_config.noise_sample_duration_s), n_mels=0)
+                out, _, clip = plan.denoise(plan.pack([x]))
+                if self.stationary:
+                    c = clip.cpu().numpy()[0]
+                    logger.info(f"Noise profile: {c[0] / sr:.2f}s - {c[1] / sr:.2f}s")
+            den = out[0].clone()
+            plan.close()
+        except (MafError, RuntimeError, ValueError) as e:
+            raise AudioProcessingError("Noise reduction failed", details=str(e))
+        out_path = os.path.join(self.temp_dir, f"{Path(input_wav).stem}_denoised.wav")
+        self._store(out_path, den, sr)
+        logger.info(f"Noise reduced: {out_path}")
+        return out_path
+
+    def normalize_audio(self, input_wav: str) -> str:
+        """preprocessor.py:216-242: pydub peak normalise (-0.1 dBFS), then mono / 16-bit at the target rate.
+
+        16-bit input at the target rate is the pipeline's contract (media_handler.py:219-223); multi-channel input is
+        downmixed with audioop.tomono semantics after the normalise, like pydub's call order.  Other sample rates or
+        widths are outside this path's scope and raise AudioProcessingError."""
+        try:
+            hit = self._resident.get(input_wav)
+            if hit is not None and os.path.exists(input_wav) and os.path.getmtime(input_wav) == hit[2]:
+                x, sr, ch = hit[0], hit[1], 1
+            else:
+                ch, width, sr, raw = self._read_wav_info(input_wav)
+                if width != 2:
+                    raise ValueError(f"unsupported sample width {width} (16-bit PCM expected)")
+                x = torch.frombuffer(bytearray(raw), dtype=torch.int16).to(self.frontend.device)
+            if sr != self.sample_rate:
+                raise ValueError(f"sample rate {sr} != target {self.sample_rate}: resampling is not part of this path")
+            plan = self.frontend.plan([x.numel()], sample_rate=sr, n_mels=0)
+            y = plan.peak_normalize(plan.pack([x]))[0].clone()
+            plan.close()
+            if ch > 1:   # audioop.tomono(0.5, 0.5): floor of the mean, per frame
+                y = torch.floor(y.view(-1, ch).to(torch.float64).mean(dim=1)).to(torch.int16)
+        except Exception as e:
+            raise AudioProcessingError("Audio normalization failed", details=str(e))
+        out_path = os.path.join(self.temp_dir, f"{Path(input_wav).stem}_norm.wav")
+        self._store(out_path, y, self.sample_rate)
+        logger.info(f"Audio normalized: {out_path}")
+        return out_path
+
+    def normalize_loudness(self, input_wav: str, target_lufs: float = -16.0) -> str:
+        """preprocessor.py:244-288: BS.1770 integrated loudness -> gain to target -> peak limiter -> int16."""
+        try:
+            x, sr = self._upload(input_wav)
+            plan = self.frontend.plan([x.numel()], sample_rate=self.sample_rate, target_lufs=target_lufs, n_mels=0)
+            out, lufs = plan.loudness(plan.pack([x]))
+            loudness = float(lufs.item())
+            y = out[0].clone()
+            plan.close()
+            if not np.isfinite(loudness) or loudness < -70:
+                logger.warning("Audio is too quiet for LUFS normalization, skipping")
+                return input_wav
+        except Exception as e:
+            raise AudioProcessingError("Loudness normalization failed", details=str(e))
+        out_path = os.path.join(self.temp_dir, f"{Path(input_wav).stem}_loudnorm.wav")
+        self._store(out_path, y, self.sample_rate)
+        logger.info(f"Loudness normalized to {target_lufs} LUFS: {out_path}")
+        return out_path
+
+    def remove_silence(self, input_wav: str, min_silence_len: int = 250, silence_offset_db: float = 40.0,
+                       silence_margin: int = 100, preserve_timestamps: bool = True):
+        """preprocessor.py:290-375.  See silence.py."""
+        from .silence import remove_silence
+        try:
+            x, sr = self._upload(input_wav)
+            res = remove_silence(self.frontend, x, sr, min_silence_len, silence_offset_db, silence_margin, preserve_timestamps,
+                                 TimestampMapping)
+        except Exception as e:
+            raise AudioProcessingError("Silence removal failed", details=str(e))
+        if res is None:
+            logger.warning("No non-silent segments found, returning original")
+            return input_wav, []
+        cleaned, mappings = res
+        out_path = os.path.join(self.temp_dir, f"{Path(input_wav).stem}_nosilence.wav")
+        self._store(out_path, cleaned, sr)
+        return out_path, mappings
+
+    def detect_silence_segments(self, input_wav: str, min_silence_len: int = 500, silence_offset_db: float = 40.0):
+        """preprocessor.py:377-405."""
+        from .silence import detect_silence_ms
+        x, sr = self._upload(input_wav)
+        return [(s / 1000.0, e / 1000.0) for s, e in detect_silence_ms(self.frontend, x, sr, min_silence_len, silence_offset_db)]
+
+    # ---- fused in-memory entry ------------------------------------------------------------------------------------------
+    def process(self, pcm: torch.Tensor, n_mels: int = 80, mel_padding: int = 0, target_lufs: float = -16.0):
+        """denoise -> peak normalise -> loudness normalise -> log-mel on one int16 recording already in memory.
+
+        Returns (int16 device tensor, LUFS before the gain, float32 [n_mels, frames] device tensor)."""
+        x = pcm.to(self.frontend.device)
+        plan = self.frontend.plan([x.numel()], sample_rate=self.sample_rate, stationary=self.stationary,
+                                  auto_detect_noise=bool(self.noise_config.auto_detect_noise),
+                                  noise_sample_duration_s=float(self.noise_config.noise_sample_duration_s),
+                                  target_lufs=target_lufs, n_mels=n_mels, mel_padding=mel_padding)
+        res = plan.process(plan.pack([x]))
+        out = res.pcm[0].clone(), float(res.lufs.item()), (res.log_mel[0].clone() if n_mels else None)
+        plan.close()
+        return out
