@@ -139,6 +139,15 @@ int maf_mel_finalize(maf_plan* plan, void* workspace_dev, float* mel_dev, void* 
 int maf_plan_buffer(const maf_plan* plan, const char* name, int64_t* offset_bytes, int64_t* size_bytes);
 int64_t maf_plan_den_offset(const maf_plan* plan, int32_t item);   /* int16 index of own sample 0 inside "den16" */
 
+/* ---- silence detection for AudioPreprocessor.remove_silence / detect_silence_segments (preprocessor.py:290-405 ->
+ * pydub.silence.detect_silence over audioop.rms).  maf_ms_energy: exact integer sum of squares per millisecond
+ * bucket [int(i r), int((i+1) r)), r = rate / 1000, and of the whole recording (seg.rms -> seg.dBFS).
+ * maf_silence_flags: flags[i] = (audioop.rms of the window_ms buckets starting at i) <= thresh, i < n_starts. */
+int maf_ms_energy(maf_ctx* ctx, const int16_t* pcm_dev, int64_t n, int32_t sample_rate, int64_t n_ms, uint64_t* bucket_dev,
+                  uint64_t* total_dev, void* stream);
+int maf_silence_flags(maf_ctx* ctx, const uint64_t* bucket_dev, int64_t n, int32_t sample_rate, int64_t n_starts, int32_t window_ms,
+                      double thresh, uint8_t* flags_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,8 @@ SYMBOLS = {
     "maf_mel_finalize": (C.c_int, [_P, _P, _P, _P]),
     "maf_plan_buffer": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "maf_plan_den_offset": (C.c_int64, [_P, C.c_int32]),
+    "maf_ms_energy": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int64, _P, _P, _P]),
+    "maf_silence_flags": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_double, _P, _P]),
 }
 
 _lib = None

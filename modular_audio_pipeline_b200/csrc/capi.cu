@@ -730,3 +730,22 @@ extern "C" int maf_mel_finalize(maf_plan* pl, void* ws, float* mel, void* stream
     CU(cudaGetLastError());
     return MAF_OK;
 }
+
+// ---- silence detection (next-row: remove_silence / detect_silence_segments) -------------------------------------------
+extern "C" int maf_ms_energy(maf_ctx* ctx, const int16_t* pcm, int64_t n, int32_t sr, int64_t n_ms, uint64_t* bucket, uint64_t* total,
+                             void* stream) {
+    if (!ctx || !pcm || !bucket || !total || n <= 0 || n_ms < 0) return fail(MAF_ERR_INVALID, "maf_ms_energy: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    launch_ms_energy(pcm, n, sr, n_ms, (unsigned long long*)bucket, (unsigned long long*)total, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return MAF_OK;
+}
+
+extern "C" int maf_silence_flags(maf_ctx* ctx, const uint64_t* bucket, int64_t n, int32_t sr, int64_t n_starts, int32_t window_ms,
+                                 double thresh, uint8_t* flags, void* stream) {
+    if (!ctx || !bucket || !flags || window_ms <= 0) return fail(MAF_ERR_INVALID, "maf_silence_flags: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    launch_silence_flags((const unsigned long long*)bucket, n, sr, n_starts, window_ms, thresh, flags, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return MAF_OK;
+}

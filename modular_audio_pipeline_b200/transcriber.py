@@ -1,0 +1,123 @@
+"""Transcriber-input side of the seam: Whisper's log-mel front-end on the GPU (reference call sites
+``audio_pipeline/transcriber.py:229-238`` -> ``whisper.transcribe`` -> ``whisper.audio.log_mel_spectrogram`` and
+``:421-427`` -> faster-whisper's ``FeatureExtractor``), handed to the model as a device tensor.
+
+* ``GpuLogMelFrontEnd.log_mel_spectrogram(audio, n_mels=80, padding=0, device=None)`` has the signature of
+  ``whisper.audio.log_mel_spectrogram`` and returns a ``torch.float32`` CUDA tensor ``[n_mels, frames]``.
+* ``GpuLogMelFrontEnd.feature_extractor(waveform, padding=160, chunk_length=None)`` has the call signature of
+  faster-whisper's ``FeatureExtractor.__call__`` and returns ``np.ndarray [n_mels, frames]``.
+* ``GpuFrontEndTranscriber`` wraps a reference transcriber (``WhisperTranscriber`` / ``FasterWhisperTranscriber``,
+  ``TranscriberProtocol``: ``transcribe`` / ``is_loaded`` / ``load_model``) and installs the GPU front-end into the
+  loaded model.  The ASR encoder / decoder are not part of this path.
+"""
+from __future__ import annotations
+
+import sys
+import wave
+from typing import Any, Dict, Optional, Union
+
+import numpy as np
+import torch
+
+from .frontend import FrontEnd
+
+__all__ = ["GpuLogMelFrontEnd", "GpuFrontEndTranscriber"]
+
+N_SAMPLES = 480000      # whisper.audio.N_SAMPLES: 30 s at 16 kHz
+N_FRAMES = 3000
+
+
+class GpuLogMelFrontEnd:
+    def __init__(self, device=None):
+        self._device = device
+        self._fe: Optional[FrontEnd] = None
+
+    @property
+    def frontend(self) -> FrontEnd:
+        if self._fe is None:
+            self._fe = FrontEnd(self._device)
+        return self._fe
+
+    def _to_int16(self, audio: Union[str, np.ndarray, torch.Tensor]) -> torch.Tensor:
+        """whisper.load_audio decodes to s16le and divides by 32768; the kernels take the int16 samples directly.
+        Float input must therefore be int16-representable (it is, for anything that came from a 16-bit WAV)."""
+        dev = self.frontend.device
+        if isinstance(audio, str):
+            with wave.open(audio, "rb") as wf:
+                if wf.getsampwidth() != 2 or wf.getnchannels() != 1 or wf.getframerate() != 16000:
+                    raise ValueError("expected a 16 kHz mono 16-bit WAV (the pipeline's contract, media_handler.py:219-223)")
+                raw = wf.readframes(wf.getnframes())
+            return torch.frombuffer(bytearray(raw), dtype=torch.int16).to(dev)
+        t = torch.as_tensor(audio)
+        if t.dtype == torch.int16:
+            return t.to(dev)
+        q = torch.round(t.to(dev, torch.float32) * 32768.0)
+        if not torch.equal(q / 32768.0, t.to(dev, torch.float32)) or q.abs().max() > 32768:
+            raise ValueError("float audio is not int16-representable; pass the int16 samples or a WAV path")
+        return torch.clamp(q, -32768, 32767).to(torch.int16)
+
+    def log_mel_spectrogram(self, audio, n_mels: int = 80, padding: int = 0, device=None) -> torch.Tensor:
+        x = self._to_int16(audio)
+        plan = self.frontend.plan([x.numel()], n_mels=n_mels, mel_padding=padding)
+        mel = plan.log_mel(plan.pack([x]))[0].clone()
+        plan.close()
+        return mel if device is None else mel.to(device)
+
+    def feature_extractor(self, waveform, padding: int = 160, chunk_length: Optional[int] = None) -> np.ndarray:
+        x = self._to_int16(waveform)
+        if chunk_length is not None:                     # faster-whisper pads / trims to chunk_length seconds first
+            n = chunk_length * 16000
+            x = x[:n] if x.numel() >= n else torch.nn.functional.pad(x, (0, n - x.numel()))
+        return self.log_mel_spectrogram(x, self.n_mels, padding).cpu().numpy()
+
+    n_mels = 80
+
+    @staticmethod
+    def pad_or_trim(mel: torch.Tensor, length: int = N_FRAMES) -> torch.Tensor:
+        """whisper.audio.pad_or_trim along the frame axis (the 30 s window the encoder consumes)."""
+        if mel.shape[-1] > length:
+            return mel[..., :length]
+        if mel.shape[-1] < length:
+            return torch.nn.functional.pad(mel, (0, length - mel.shape[-1]))
+        return mel
+
+
+class GpuFrontEndTranscriber:
+    """TranscriberProtocol (protocols.py:119-133) adapter: same transcriber, GPU log-mel front-end."""
+
+    def __init__(self, inner, front_end: Optional[GpuLogMelFrontEnd] = None):
+        self.inner = inner
+        self.front_end = front_end or GpuLogMelFrontEnd()
+        self._installed = False
+
+    def is_loaded(self) -> bool:
+        return self.inner.is_loaded()
+
+    def load_model(self) -> None:
+        self.inner.load_model()
+        self._install()
+
+    def unload_model(self) -> None:
+        if hasattr(self.inner, "unload_model"):
+            self.inner.unload_model()
+        self._installed = False
+
+    def _install(self) -> None:
+        if self._installed:
+            return
+        model = getattr(self.inner, "_model", None)
+        if model is not None and hasattr(model, "feature_extractor"):          # faster-whisper WhisperModel
+            fe = self.front_end
+            fe.n_mels = getattr(getattr(model, "feature_extractor"), "mel_filters", np.zeros((80, 201))).shape[0]
+            model.feature_extractor = fe.feature_extractor
+            self._installed = True
+        mod = sys.modules.get("whisper.transcribe")                            # openai-whisper: patch the name it calls
+        if mod is not None and hasattr(mod, "log_mel_spectrogram"):
+            mod.log_mel_spectrogram = self.front_end.log_mel_spectrogram
+            self._installed = True
+
+    def transcribe(self, input_wav: str) -> Dict[str, Any]:
+        if not self.inner.is_loaded():
+            self.load_model()
+        self._install()
+        return self.inner.transcribe(input_wav)

@@ -398,3 +398,118 @@ def front_end(pcm: np.ndarray, sr: int = 16000, stationary: bool = True, n_mels:
     mel = log_mel_spectrogram(loud16.astype(np.float32) / np.float32(32768.0), n_mels, padding)
     return {"denoised_f32": red, "denoised_i16": den16, "noise_clip": clip, "norm_i16": norm16,
             "loud_i16": loud16, "lufs": lufs, "applied": applied, "log_mel": mel}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Next-row 1: remove_silence -- preprocessor.py:290-375 over pydub.silence / AudioSegment.append, restated on the
+# REAL stdlib audioop primitives pydub calls (audioop.rms / mul / add), per-millisecond loop exactly like pydub.
+# --------------------------------------------------------------------------------------------------------------
+
+
+def _audioop():
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import audioop
+    return audioop
+
+
+def _seg_len_ms(n: int, sr: int) -> int:
+    return int(round(1000.0 * n / sr))
+
+
+def _seg_slice(pcm: np.ndarray, sr: int, a_ms, b_ms) -> np.ndarray:
+    r = sr / 1000.0
+    return pcm[int(a_ms * r): int(b_ms * r)]
+
+
+def detect_silence_ms(pcm: np.ndarray, sr: int, min_silence_len: int = 250, offset_db: float = 40.0):
+    """pydub.silence.detect_silence(seg, min_silence_len, seg.dBFS - offset_db, seek_step=1)."""
+    audioop = _audioop()
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    seg_len = _seg_len_ms(len(pcm), sr)
+    if seg_len < min_silence_len:
+        return []
+    rms = audioop.rms(pcm.tobytes(), 2)
+    dbfs = 20 * math.log10(rms / 32768.0) if rms > 0 else -float("inf")
+    thresh = (10 ** ((dbfs - offset_db) / 20)) * 32768.0
+    starts = []
+    for i in range(0, seg_len - min_silence_len + 1):
+        sl = _seg_slice(pcm, sr, i, i + min_silence_len)
+        if audioop.rms(sl.tobytes(), 2) <= thresh:
+            starts.append(i)
+    if not starts:
+        return []
+    ranges = []
+    prev_i = starts.pop(0)
+    cur = prev_i
+    for s in starts:
+        if s != prev_i + 1 and s > prev_i + min_silence_len:
+            ranges.append([cur, prev_i + min_silence_len])
+            cur = s
+        prev_i = s
+    ranges.append([cur, prev_i + min_silence_len])
+    return ranges
+
+
+def detect_nonsilent_ms(pcm, sr, min_silence_len=250, offset_db=40.0):
+    silent = detect_silence_ms(pcm, sr, min_silence_len, offset_db)
+    len_seg = _seg_len_ms(len(pcm), sr)
+    if not silent:
+        return [[0, len_seg]]
+    if silent[0][0] == 0 and silent[0][1] == len_seg:
+        return []
+    prev_end, out, end_i = 0, [], 0
+    for start_i, end_i in silent:
+        out.append([prev_end, start_i])
+        prev_end = end_i
+    if end_i != len_seg:
+        out.append([prev_end, len_seg])
+    if out[0] == [0, 0]:
+        out.pop(0)
+    return out
+
+
+def _fade(chunk: np.ndarray, from_gain: float, to_gain: float) -> np.ndarray:
+    """AudioSegment.fade(start=0, end=inf) for durations <= 100 ms: per-frame audioop.mul with a linear gain ramp."""
+    audioop = _audioop()
+    from_power = 10 ** (from_gain / 20)
+    delta = 10 ** (to_gain / 20) - from_power
+    n = len(chunk)
+    step = delta / n
+    out = np.empty(n, dtype=np.int16)
+    for i in range(n):
+        out[i] = np.frombuffer(audioop.mul(chunk[i:i + 1].tobytes(), 2, from_power + step * i), dtype=np.int16)[0]
+    return out
+
+
+def remove_silence(pcm: np.ndarray, sr: int, min_silence_len=250, offset_db=40.0, margin=100):
+    """preprocessor.py:311-358 -> (int16 cleaned, [(processed_start, processed_end, original_start, original_end)]) or None."""
+    audioop = _audioop()
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    ranges = detect_nonsilent_ms(pcm, sr, min_silence_len, offset_db)
+    if not ranges:
+        return None
+    n_ms = _seg_len_ms(len(pcm), sr)
+    cleaned = np.zeros(0, dtype=np.int16)
+    maps, pos = [], 0
+    for start_ms, end_ms in ranges:
+        s, e = max(0, start_ms - margin), min(n_ms, end_ms + margin)
+        chunk = _seg_slice(pcm, sr, s, e)
+        dur = _seg_len_ms(len(chunk), sr)
+        maps.append((pos / 1000.0, (pos + dur) / 1000.0, s / 1000.0, e / 1000.0))
+        if len(cleaned) == 0:
+            cleaned = chunk.copy()
+        else:
+            cf = min(20, dur // 4)
+            ncf = int(cf * (sr / 1000.0))
+            if ncf > 0:
+                xf = _fade(cleaned[-ncf:], 0, -120)
+                fin = _fade(chunk[:ncf], -120, 0)
+                xf = np.frombuffer(audioop.add(xf.tobytes(), fin.tobytes(), 2), dtype=np.int16)
+                cleaned = np.concatenate([cleaned[:-ncf], xf, chunk[ncf:]])
+            else:
+                cleaned = np.concatenate([cleaned, chunk])
+            pos -= cf
+        pos += dur
+    return cleaned, maps
