@@ -125,6 +125,7 @@ struct WsBuf { long long off = 0, bytes = 0; };
 
 struct maf_plan {
     maf_ctx* ctx = nullptr;
+    int device = 0;
     maf_params p{};
     int n_items = 0, n_chunks = 0;
     std::vector<Item> items;           // den_off = workspace den16 layout
@@ -207,7 +208,7 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
     if (p.mel_padding < 0 || (p.mel_padding > 0 && p.mel_padding < W_HOP)) return fail(MAF_ERR_INVALID, "mel_padding must be 0 or >= 160");
     CU(cudaSetDevice(ctx->device));
     maf_plan* pl = new maf_plan();
-    pl->ctx = ctx; pl->p = p; pl->n_items = n_items;
+    pl->ctx = ctx; pl->device = ctx->device; pl->p = p; pl->n_items = n_items;
     if (design_taps(p.sample_rate, pl->taps)) { delete pl; return fail(MAF_ERR_UNSUPPORTED, "smoothing taps exceed kernel limits for this rate"); }
     design_kweight((double)p.sample_rate, pl->kw);
     pl->target_peak = 32768.0 * pow(10.0, -0.1 / 20.0);
@@ -358,7 +359,7 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
 
 extern "C" void maf_plan_destroy(maf_plan* pl) {
     if (!pl) return;
-    cudaSetDevice(pl->ctx->device);
+    cudaSetDevice(pl->device);
     if (pl->hstream) { cudaStreamSynchronize(pl->hstream); cudaStreamDestroy(pl->hstream); }
     for (cudaEvent_t e : pl->prof_ev) cudaEventDestroy(e);
     cudaFree(pl->tables); cudaFree(pl->h_ws); cudaFree(pl->h_pcm); cudaFree(pl->h_out); cudaFree(pl->h_mel); cudaFree(pl->h_lufs);

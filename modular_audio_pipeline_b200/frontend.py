@@ -8,6 +8,7 @@ PyTorch is used for device memory, streams and the tensor hand-off only; all ari
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -53,9 +54,12 @@ class FrontEnd:
         h = C.c_void_p()
         check(self._lib.maf_create(self.device.index, C.byref(h)))
         self._h = h
+        self._plans = weakref.WeakSet()
 
     def close(self) -> None:
         if getattr(self, "_h", None):
+            for p in list(self._plans):          # plans point into the context: release them first
+                p.close()
             self._lib.maf_destroy(self._h)
             self._h = None
 
@@ -89,6 +93,7 @@ class Plan:
         h = C.c_void_p()
         check(self._lib.maf_plan_create(fe._h, C.byref(params), descs, self.n_items, C.byref(h)))
         self._h = h
+        fe._plans.add(self)
         self.descs = descs
         self.layout: List[Layout] = []
         for i in range(self.n_items):

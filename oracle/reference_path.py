@@ -71,10 +71,8 @@ def frame_stats(audio: np.ndarray, sr: int, batch: int = 16384) -> Tuple[np.ndar
     return energies, zcrs
 
 
-def detect_noise_segments(audio: np.ndarray, sr: int, fast: bool = True) -> List[Tuple[int, int]]:
-    """preprocessor.py:92-147.  ``audio`` is float32 holding unscaled int16 values (:171)."""
-    hop_length = int(sr * 0.010)
-    energies, zcrs = (frame_stats if fast else frame_stats_loop)(audio, sr)
+def segments_from_stats(energies: np.ndarray, zcrs: np.ndarray, hop_length: int, sr: int) -> List[Tuple[int, int]]:
+    """preprocessor.py:124-147 on precomputed per-frame statistics."""
     if len(energies) == 0:
         return []
     energy_threshold = np.percentile(energies, 20)
@@ -91,6 +89,12 @@ def detect_noise_segments(audio: np.ndarray, sr: int, fast: bool = True) -> List
         if (e - s) * hop_length / sr >= 0.1:
             segs.append((int(s * hop_length), int(e * hop_length)))
     return segs
+
+
+def detect_noise_segments(audio: np.ndarray, sr: int, fast: bool = True) -> List[Tuple[int, int]]:
+    """preprocessor.py:92-147.  ``audio`` is float32 holding unscaled int16 values (:171)."""
+    energies, zcrs = (frame_stats if fast else frame_stats_loop)(audio, sr)
+    return segments_from_stats(energies, zcrs, int(sr * 0.010), sr)
 
 
 def choose_noise_clip(audio: np.ndarray, sr: int, auto_detect: bool = True,
