@@ -84,14 +84,15 @@ extern "C" int maf_create(int device, maf_ctx** out) {
     std::vector<float> win(NFFT), winv(NFFT), win4(W_NFFT);
     for (int i = 0; i < NFFT; ++i) { const double w = 0.5 - 0.5 * cos(2.0 * PI * i / NFFT); win[i] = (float)(w / 512.0); winv[i] = (float)(w * 0.5); }
     for (int i = 0; i < W_NFFT; ++i) win4[i] = (float)(0.5 - 0.5 * cos(2.0 * PI * i / W_NFFT));
-    std::vector<c32> t512(512), t1024(513), t200(200), t400(201);
-    for (int e = 0; e < 512; ++e) t512[e] = mk((float)cos(2 * PI * e / 512), (float)-sin(2 * PI * e / 512));
+    std::vector<c32> t512(FFT512_TW1), t2(FFT512_TW2), t1024(513), t200(200), t400(201);
+    for (int p = 0; p < 8; ++p) for (int t = 0; t < 64; ++t) t512[p * 64 + t] = mk((float)cos(2 * PI * (t * p) / 512), (float)-sin(2 * PI * (t * p) / 512));
+    for (int c = 0; c < 8; ++c) for (int a = 0; a < 8; ++a) t2[c * 8 + a] = mk((float)cos(2 * PI * (8 * a * c) / 512), (float)-sin(2 * PI * (8 * a * c) / 512));
     for (int e = 0; e <= 512; ++e) t1024[e] = mk((float)cos(2 * PI * e / 1024), (float)-sin(2 * PI * e / 1024));
-    for (int e = 0; e < 200; ++e) t200[e] = mk((float)cos(2 * PI * e / 200), (float)-sin(2 * PI * e / 200));
+    for (int p = 0; p < 8; ++p) for (int j = 0; j < 25; ++j) t200[p * 25 + j] = mk((float)cos(2 * PI * (j * p) / 200), (float)-sin(2 * PI * (j * p) / 200));
     for (int e = 0; e <= 200; ++e) t400[e] = mk((float)cos(2 * PI * e / 400), (float)-sin(2 * PI * e / 400));
     MelHost m80 = build_mel(80), m128 = build_mel(128);
     size_t o_win = put(win.data(), win.size() * 4), o_winv = put(winv.data(), winv.size() * 4), o_win4 = put(win4.data(), win4.size() * 4);
-    size_t o_t512 = put(t512.data(), t512.size() * 8), o_t1024 = put(t1024.data(), t1024.size() * 8);
+    size_t o_t512 = put(t512.data(), t512.size() * 8), o_t2 = put(t2.data(), t2.size() * 8), o_t1024 = put(t1024.data(), t1024.size() * 8);
     size_t o_t200 = put(t200.data(), t200.size() * 8), o_t400 = put(t400.data(), t400.size() * 8);
     size_t o80[4] = {put(m80.start.data(), 80 * 4), put(m80.count.data(), 80 * 4), put(m80.woff.data(), 80 * 4), put(m80.w.data(), m80.w.size() * 4)};
     size_t o128[4] = {put(m128.start.data(), 128 * 4), put(m128.count.data(), 128 * 4), put(m128.woff.data(), 128 * 4), put(m128.w.data(), m128.w.size() * 4)};
@@ -104,8 +105,8 @@ extern "C" int maf_create(int device, maf_ctx** out) {
     if (cudaMalloc(&ctx->scratch, 1024) != cudaSuccess) { cudaFree(ctx->blob); delete ctx; return fail(MAF_ERR_CUDA, "cudaMalloc scratch"); }
     unsigned char* b = (unsigned char*)ctx->blob;
     ctx->c.win1024 = (const float*)(b + o_win); ctx->c.winv1024 = (const float*)(b + o_winv); ctx->c.win400 = (const float*)(b + o_win4);
-    ctx->c.tw512 = (const c32*)(b + o_t512); ctx->c.tw1024 = (const c32*)(b + o_t1024);
-    ctx->c.tw200 = (const c32*)(b + o_t200); ctx->c.tw400 = (const c32*)(b + o_t400);
+    ctx->c.tw1 = (const c32*)(b + o_t512); ctx->c.tw2 = (const c32*)(b + o_t2); ctx->c.tw1024 = (const c32*)(b + o_t1024);
+    ctx->c.twA = (const c32*)(b + o_t200); ctx->c.tw400 = (const c32*)(b + o_t400);
     ctx->mel80 = MelBank{80, (const int*)(b + o80[0]), (const int*)(b + o80[1]), (const int*)(b + o80[2]), (const float*)(b + o80[3])};
     ctx->mel128 = MelBank{128, (const int*)(b + o128[0]), (const int*)(b + o128[1]), (const int*)(b + o128[2]), (const float*)(b + o128[3])};
     *out = ctx;

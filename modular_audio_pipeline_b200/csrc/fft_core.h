@@ -69,7 +69,9 @@ MAF_HD void fft5(c32& v0, c32& v1, c32& v2, c32& v3, c32& v4) {
 // 512-point complex FFT, 64 threads, thread t holds 8 points.  Shared scratch: FFT512_SMEM c32 per transform.
 //   in : v[m] = x[t + 64 m]
 //   out: v[d] = X[t + 64 d]  (fft512_out_base(t) == t)
-// tw512[e] = e^{-2 pi i e / 512}, e = 0..511.
+// Twiddle tables are laid out for conflict-free shared-memory reads (a stride-p walk through one linear table puts
+// 2-8 lanes on the same bank):  tw1[p * 64 + t] = e^{-2 pi i t p / 512}  (step 1, lanes walk t)
+//                                tw2[c * 8 + a]  = e^{-2 pi i 8 a c / 512} (step 2, lanes walk a; p is a broadcast)
 // ------------------------------------------------------------------------------------------------------------
 constexpr int FFT512_SMEM = 8 * 72;
 
@@ -80,11 +82,14 @@ MAF_HD int fft512_out_base(int t) { return t; }
 // (half-warp = 2 p's x 8 a's, fixed c) and for the step-3 readers (half-warp = 8 p's x 2 c's, fixed a).
 MAF_HD int fft512_x2(int p, int a, int c) { return ((p + 2 * a + 8 * c) & 15) + 16 * a + 128 * (c >> 1); }
 
-MAF_HD void fft512_step1(c32 (&v)[8], c32* sm, const c32* tw512, int t) {
+constexpr int FFT512_TW1 = 8 * 64;
+constexpr int FFT512_TW2 = 64;
+
+MAF_HD void fft512_step1(c32 (&v)[8], c32* sm, const c32* tw1, int t) {
     fft8(v);
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
-        c32 w = tw512[t * p];
+        c32 w = tw1[p * 64 + t];
         sm[p * 72 + t] = (p == 0) ? v[0] : cmul(v[p], w);
     }
 }
@@ -95,12 +100,12 @@ MAF_HD void fft512_step2_load(c32 (&v)[8], const c32* sm, int t) {
     for (int b = 0; b < 8; ++b) v[b] = sm[p * 72 + a + 8 * b];
 }
 // (barrier)
-MAF_HD void fft512_step2_store(c32 (&v)[8], c32* sm, const c32* tw512, int t) {
+MAF_HD void fft512_step2_store(c32 (&v)[8], c32* sm, const c32* tw2, int t) {
     const int p = t >> 3, a = t & 7;
     fft8(v);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        c32 w = tw512[8 * a * c];
+        c32 w = tw2[c * 8 + a];
         sm[fft512_x2(p, a, c)] = (c == 0) ? v[0] : cmul(v[c], w);
     }
 }
@@ -146,29 +151,37 @@ MAF_HD void irfft_merge_pair(c32 xk, c32 xnk, c32 tw1024k, c32& zck, c32& zcnk) 
 //   X[p + 8q] = sum_j W25^{jq} [ W200^{jp} sum_m x[j + 25m] W8^{mp} ]
 // step A: work item (j): 8-point FFT over m, twiddle W200^{jp}, store sm[p * 25 + j]        (25 items / transform)
 // step B: work item (p): 25-point DFT over j (5 x 5 in registers) -> X[p + 8q], q = 0..24   ( 8 items / transform)
-// tw200[e] = e^{-2 pi i e / 200}, e = 0..199.   Shared scratch: 200 c32 per transform.
+// Shared scratch: 200 c32 per transform.
 // ------------------------------------------------------------------------------------------------------------
-MAF_HD void fft200_stepA(c32 (&v)[8], c32* sm, const c32* tw200, int j) {
+// twA[p * 25 + j] = e^{-2 pi i j p / 200} (lanes walk j: conflict-free)
+MAF_HD void fft200_stepA(c32 (&v)[8], c32* sm, const c32* twA, int j) {
     fft8(v);
 #pragma unroll
-    for (int p = 0; p < 8; ++p) sm[p * 25 + j] = (p == 0) ? v[0] : cmul(v[p], tw200[j * p]);
+    for (int p = 0; p < 8; ++p) sm[p * 25 + j] = (p == 0) ? v[0] : cmul(v[p], twA[p * 25 + j]);
+}
+
+// e^{-2 pi i e / 25}: after unrolling every index is a compile-time constant, so these fold into immediates
+MAF_HD c32 w25(int e) {
+    const float re[25] = {1.0f, 0.96858316112863108f, 0.87630668004386358f, 0.72896862742141155f, 0.53582679497899655f, 0.30901699437494745f, 0.062790519529313527f, -0.1873813145857246f, -0.42577929156507272f, -0.63742398974868975f, -0.80901699437494734f, -0.92977648588825135f, -0.99211470131447776f, -0.99211470131447788f, -0.92977648588825146f, -0.80901699437494778f, -0.63742398974868952f, -0.42577929156507216f, -0.18738131458572463f, 0.062790519529312833f, 0.30901699437494723f, 0.53582679497899677f, 0.72896862742141122f, 0.87630668004386314f, 0.96858316112863097f};
+    const float im[25] = {0.0f, -0.24868988716485479f, -0.48175367410171532f, -0.68454710592868862f, -0.84432792550201508f, -0.95105651629515353f, -0.99802672842827156f, -0.98228725072868872f, -0.90482705246601947f, -0.77051324277578925f, -0.58778525229247325f, -0.36812455268467814f, -0.12533323356430454f, 0.12533323356430429f, 0.36812455268467792f, 0.58778525229247269f, 0.77051324277578936f, 0.9048270524660198f, 0.98228725072868872f, 0.99802672842827156f, 0.95105651629515364f, 0.84432792550201496f, 0.68454710592868895f, 0.4817536741017161f, 0.24868988716485535f};
+    return mk(re[e], im[e]);
 }
 
 // 25-point DFT of sm[p*25 + j], j = 0..24, result X[p + 8 q] written to out[q] (q = 0..24).
 // j = j0 + 5 j1, q = q1 + 5 q0:  W25^{jq} = W25^{j0 q1} W5^{j0 q0} W5^{j1 q1}
-MAF_HD void fft200_stepB(const c32* sm, const c32* tw200, int p, c32 (&out)[25]) {
+MAF_HD void fft200_stepB(const c32* sm, int p, c32 (&out)[25]) {
     c32 y[25];
 #pragma unroll
     for (int j0 = 0; j0 < 5; ++j0) {
         c32 a0 = sm[p * 25 + j0], a1 = sm[p * 25 + j0 + 5], a2 = sm[p * 25 + j0 + 10],
             a3 = sm[p * 25 + j0 + 15], a4 = sm[p * 25 + j0 + 20];
         fft5(a0, a1, a2, a3, a4);                 // over j1 -> q1
-        // twiddle W25^{j0 q1} = W200^{8 j0 q1}
+        // twiddle W25^{j0 q1}
         y[j0 * 5 + 0] = a0;
-        y[j0 * 5 + 1] = (j0 == 0) ? a1 : cmul(a1, tw200[8 * j0 * 1]);
-        y[j0 * 5 + 2] = (j0 == 0) ? a2 : cmul(a2, tw200[8 * j0 * 2]);
-        y[j0 * 5 + 3] = (j0 == 0) ? a3 : cmul(a3, tw200[8 * j0 * 3]);
-        y[j0 * 5 + 4] = (j0 == 0) ? a4 : cmul(a4, tw200[8 * j0 * 4]);
+        y[j0 * 5 + 1] = (j0 == 0) ? a1 : cmul(a1, w25(j0 * 1));
+        y[j0 * 5 + 2] = (j0 == 0) ? a2 : cmul(a2, w25(j0 * 2));
+        y[j0 * 5 + 3] = (j0 == 0) ? a3 : cmul(a3, w25(j0 * 3));
+        y[j0 * 5 + 4] = (j0 == 0) ? a4 : cmul(a4, w25(j0 * 4));
     }
 #pragma unroll
     for (int q1 = 0; q1 < 5; ++q1) {

@@ -23,8 +23,9 @@ __device__ __forceinline__ int gain_sample_m(int s, const Gate& gt) {
 constexpr int MEL_SPAN = (MEL_TILE - 1) * W_HOP + W_NFFT;            // 5360 samples per tile
 constexpr int Z_PITCH = 200;
 constexpr int P_PITCH = 201;
+constexpr int MEL_W_MAX = 416;                                       // packed non-zero mel weights (391 / 394 used)
 constexpr size_t LOGMEL_SMEM = sizeof(float) * MEL_SPAN + sizeof(c32) * MEL_TILE * Z_PITCH + sizeof(float) * MEL_TILE * P_PITCH +
-                               sizeof(float) * W_NFFT + sizeof(c32) * 200 + sizeof(c32) * 208;
+                               sizeof(float) * W_NFFT + sizeof(c32) * 200 + sizeof(c32) * 208 + sizeof(int) * 3 * 128 + sizeof(float) * MEL_W_MAX;
 
 __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__ den16, const Item* __restrict__ items, Consts cs,
                                                      MelBank mel, int padding, int peak_normalize, double target_peak,
@@ -36,8 +37,12 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     c32* zb = reinterpret_cast<c32*>(span + MEL_SPAN);
     float* pw = reinterpret_cast<float*>(zb + MEL_TILE * Z_PITCH);
     float* win = pw + MEL_TILE * P_PITCH;
-    c32* tw200 = reinterpret_cast<c32*>(win + W_NFFT);
-    c32* tw400 = tw200 + 200;
+    c32* twA = reinterpret_cast<c32*>(win + W_NFFT);
+    c32* tw400 = twA + 200;
+    int* m_start = reinterpret_cast<int*>(tw400 + 208);
+    int* m_count = m_start + 128;
+    int* m_woff = m_count + 128;
+    float* m_w = reinterpret_cast<float*>(m_woff + 128);
 
     const int item = blockIdx.y;
     const Item it = items[item];
@@ -46,7 +51,12 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     const int tid = threadIdx.x;
 
     for (int i = tid; i < W_NFFT; i += 256) win[i] = cs.win400[i];
-    for (int i = tid; i < 200; i += 256) tw200[i] = cs.tw200[i];
+    for (int i = tid; i < 200; i += 256) twA[i] = cs.twA[i];
+    if (tid < mel.n_mels) { m_start[tid] = mel.start[tid]; m_count[tid] = mel.count[tid]; m_woff[tid] = mel.woff[tid]; }
+    {
+        const int nw = mel.woff[mel.n_mels - 1] + mel.count[mel.n_mels - 1];
+        for (int i = tid; i < nw; i += 256) m_w[i] = mel.w[i];
+    }
     for (int i = tid; i < 201; i += 256) tw400[i] = cs.tw400[i];
 
     __shared__ double s_factor;
@@ -129,14 +139,14 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
             const float* s = span + lf * W_HOP + 2 * n;
             v[m] = mk(s[0] * win[2 * n], s[1] * win[2 * n + 1]);
         }
-        fft200_stepA(v, zb + lf * Z_PITCH, tw200, j);
+        fft200_stepA(v, zb + lf * Z_PITCH, twA, j);
     }
     __syncthreads();
     // stage B: (frame, p) -> 25-point DFT in registers; exactly one round, so the in-place write is safe after a barrier
     {
         const int lf = tid >> 3, p = tid & 7;
         c32 o[25];
-        fft200_stepB(zb + lf * Z_PITCH, tw200, p, o);
+        fft200_stepB(zb + lf * Z_PITCH, p, o);
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < 25; ++q) zb[lf * Z_PITCH + p + 8 * q] = o[q];
@@ -162,10 +172,11 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
         const bool valid = lf0 + lf < it.mel_frames;
         float bmax = -INFINITY;
         for (int m = warp; m < mel.n_mels; m += 8) {
-            const int st = mel.start[m], cnt = mel.count[m];
-            const float* wts = mel.w + mel.woff[m];
+            const int st = m_start[m], cnt = m_count[m];
+            const float* wts = m_w + m_woff[m];
+            const float* pr = pw + lf * P_PITCH + st;
             float acc = 0.f;
-            for (int i = 0; i < cnt; ++i) acc += wts[i] * pw[lf * P_PITCH + st + i];
+            for (int i = 0; i < cnt; ++i) acc += wts[i] * pr[i];
             const float lv = log10f(fmaxf(acc, 1e-10f));
             if (valid) {
                 mel_out[it.mel_off + (long long)m * it.mel_frames + lf0 + lf] = lv;

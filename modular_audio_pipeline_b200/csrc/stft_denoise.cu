@@ -20,12 +20,12 @@ namespace maf {
 // Barrier among the 64 threads (2 warps) of FFT group g only: named barriers 1..4, barrier 0 stays __syncthreads().
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory"); }
 
-__device__ __forceinline__ void group_fft512(c32 (&v)[8], c32* sm, const c32* tw512, int t, int g) {
-    fft512_step1(v, sm, tw512, t);
+__device__ __forceinline__ void group_fft512(c32 (&v)[8], c32* sm, const c32* tw1, const c32* tw2, int t, int g) {
+    fft512_step1(v, sm, tw1, t);
     group_bar(g);
     fft512_step2_load(v, sm, t);
     group_bar(g);
-    fft512_step2_store(v, sm, tw512, t);
+    fft512_step2_store(v, sm, tw2, t);
     group_bar(g);
     fft512_step3(v, sm, t);
 }
@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(256) stft1024_kernel(const int16_t* __restrict
     constexpr int SPAN = (STFT_TILE + 3) * HOP;       // samples covered by the tile's frames
     __shared__ __align__(16) int16_t span[SPAN];
     __shared__ float win[NFFT];
-    __shared__ c32 tw512[512];
+    __shared__ c32 tw1[FFT512_TW1];
+    __shared__ c32 tw2[FFT512_TW2];
     __shared__ c32 tw1024[257];
     __shared__ __align__(16) c32 fsm[4][FFT512_SMEM];
     __shared__ __align__(4) uint8_t flags[4][528];
@@ -54,7 +55,8 @@ __global__ void __launch_bounds__(256) stft1024_kernel(const int16_t* __restrict
     const int tid = threadIdx.x;
 
     for (int i = tid; i < NFFT; i += 256) win[i] = cs.win1024[i];
-    for (int i = tid; i < 512; i += 256) tw512[i] = cs.tw512[i];
+    for (int i = tid; i < FFT512_TW1; i += 256) tw1[i] = cs.tw1[i];
+    if (tid < FFT512_TW2) tw2[tid] = cs.tw2[tid];
     for (int i = tid; i < 257; i += 256) tw1024[i] = cs.tw1024[i];
 
     // stage the contiguous sample span once (frames overlap 75 %); zero outside the padded chunk and the recording
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(256) stft1024_kernel(const int16_t* __restrict
             const float2 w = win2[n];
             v[m] = mk((float)sv.x * w.x, (float)sv.y * w.y);
         }
-        group_fft512(v, fsm[g], tw512, t, g);
+        group_fft512(v, fsm[g], tw1, tw2, t, g);
         group_bar(g);
 #pragma unroll
         for (int d = 0; d < 8; ++d) fsm[g][t + 64 * d] = v[d];
@@ -185,14 +187,16 @@ __global__ void __launch_bounds__(256) noise_pass_kernel(const int16_t* __restri
                                                          const Clip* __restrict__ clips, Consts cs, unsigned* __restrict__ nmax,
                                                          double* __restrict__ partial, int n_slices) {
     __shared__ float win[NFFT];
-    __shared__ c32 tw512[512];
+    __shared__ c32 tw1[FFT512_TW1];
+    __shared__ c32 tw2[FFT512_TW2];
     __shared__ c32 tw1024[257];
     __shared__ __align__(16) c32 fsm[4][FFT512_SMEM];
     const int item = blockIdx.y;
     const Clip cl = clips[item];
     const int tid = threadIdx.x, g = tid >> 6, t = tid & 63;
     for (int i = tid; i < NFFT; i += 256) win[i] = cs.win1024[i];
-    for (int i = tid; i < 512; i += 256) tw512[i] = cs.tw512[i];
+    for (int i = tid; i < FFT512_TW1; i += 256) tw1[i] = cs.tw1[i];
+    if (tid < FFT512_TW2) tw2[tid] = cs.tw2[tid];
     for (int i = tid; i < 257; i += 256) tw1024[i] = cs.tw1024[i];
     __syncthreads();
     const int16_t* base = pcm + cl.start;
@@ -236,7 +240,7 @@ __global__ void __launch_bounds__(256) noise_pass_kernel(const int16_t* __restri
             }
             v[m] = mk(a * win[2 * n], b * win[2 * n + 1]);
         }
-        group_fft512(v, fsm[g], tw512, t, g);
+        group_fft512(v, fsm[g], tw1, tw2, t, g);
         group_bar(g);
 #pragma unroll
         for (int d = 0; d < 8; ++d) fsm[g][t + 64 * d] = v[d];
@@ -340,6 +344,8 @@ void launch_noise_threshold(const int16_t* pcm, const Clip* clips, int n_items, 
 // Deviation (documented in DESIGN.md): where Sm == 0 (an all-zero frequency row) noisereduce yields NaN; here the
 // relative excess is taken as 0 so the mask is sigmoid(-20) and the output is silence instead of NaN.
 // ============================================================================================================
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 constexpr int NS_BINS = 64;          // bins per CTA: one 512-byte segment of every S row, 256 bytes of every M0 row
 constexpr int NS_TT = 32;            // frames per streamed tile
 constexpr int NS_THREADS = 128;
@@ -378,8 +384,8 @@ __global__ void __launch_bounds__(NS_THREADS, 6) ns_mask_kernel(const c32* __res
         for (int i = 0; i < 8; ++i) {
             const int idx = tid + NS_THREADS * i, r = idx >> 5, c = idx & 31;
             if (has_nyq && c == 0) { A[r][0] = fabsf(ps[i].x); A[r][NS_BINS] = fabsf(ps[i].y); }
-            else A[r][2 * c] = sqrtf(ps[i].x * ps[i].x + ps[i].y * ps[i].y);
-            A[r][2 * c + 1] = sqrtf(ps[i].z * ps[i].z + ps[i].w * ps[i].w);
+            else A[r][2 * c] = fast_sqrt(ps[i].x * ps[i].x + ps[i].y * ps[i].y);
+            A[r][2 * c + 1] = fast_sqrt(ps[i].z * ps[i].z + ps[i].w * ps[i].w);
         }
     };
 
@@ -445,14 +451,14 @@ __global__ void __launch_bounds__(NS_THREADS, 6) ns_mask_kernel(const c32* __res
             const int idx = tid + NS_THREADS * i, r = idx >> 6, c = idx & 63;
             if (r < rows) {
                 const float sm = Y[r][c], x = A[r][c];
-                const float rr = sm > 0.f ? (x - sm) / sm : 0.f;
-                m0[(long long)(f0 + r) * M_PITCH + c] = 1.0f / (1.0f + __expf(-(rr - thresh_mult) * slope));
+                const float rr = sm > 0.f ? __fdividef(x - sm, sm) : 0.f;
+                m0[(long long)(f0 + r) * M_PITCH + c] = __fdividef(1.0f, 1.0f + __expf(-(rr - thresh_mult) * slope));
             }
         }
         if (has_nyq && tid < rows) {
             const float sm = Y[tid][NS_BINS], x = A[tid][NS_BINS];
-            const float rr = sm > 0.f ? (x - sm) / sm : 0.f;
-            M0[(ch.row0 + f0 + tid) * M_PITCH + 512] = 1.0f / (1.0f + __expf(-(rr - thresh_mult) * slope));
+            const float rr = sm > 0.f ? __fdividef(x - sm, sm) : 0.f;
+            M0[(ch.row0 + f0 + tid) * M_PITCH + 512] = __fdividef(1.0f, 1.0f + __expf(-(rr - thresh_mult) * slope));
         }
         __syncthreads();
     }
@@ -631,7 +637,7 @@ void launch_smooth_mask(const uint32_t* bits, const uint8_t* rowflag, const floa
 // ============================================================================================================
 constexpr int ISTFT_FR = ISTFT_SEG + 3;                 // 32 frames per CTA
 constexpr int OLA_LEN = (ISTFT_FR + 3) * HOP;           // 8960 floats
-constexpr size_t ISTFT_SMEM = sizeof(float) * OLA_LEN + sizeof(float) * NFFT + sizeof(c32) * 512 + sizeof(c32) * 264 +
+constexpr size_t ISTFT_SMEM = sizeof(float) * OLA_LEN + sizeof(float) * NFFT + sizeof(c32) * (FFT512_TW1 + FFT512_TW2) + sizeof(c32) * 264 +
                               sizeof(c32) * 4 * FFT512_SMEM;
 
 __global__ void __launch_bounds__(256) istft_kernel(const c32* __restrict__ S, const float* __restrict__ M,
@@ -640,8 +646,9 @@ __global__ void __launch_bounds__(256) istft_kernel(const c32* __restrict__ S, c
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* ola = reinterpret_cast<float*>(smem_raw);
     float* winv = ola + OLA_LEN;
-    c32* tw512 = reinterpret_cast<c32*>(winv + NFFT);
-    c32* tw1024 = tw512 + 512;
+    c32* tw1 = reinterpret_cast<c32*>(winv + NFFT);
+    c32* tw2 = tw1 + FFT512_TW1;
+    c32* tw1024 = tw2 + FFT512_TW2;
     c32* fsm = tw1024 + 264;
 
     const Chunk ch = chunks[blockIdx.y];
@@ -654,7 +661,8 @@ __global__ void __launch_bounds__(256) istft_kernel(const c32* __restrict__ S, c
 
     for (int i = tid; i < OLA_LEN; i += 256) ola[i] = 0.f;
     for (int i = tid; i < NFFT; i += 256) winv[i] = cs.winv1024[i];
-    for (int i = tid; i < 512; i += 256) tw512[i] = cs.tw512[i];
+    for (int i = tid; i < FFT512_TW1; i += 256) tw1[i] = cs.tw1[i];
+    if (tid < FFT512_TW2) tw2[tid] = cs.tw2[tid];
     for (int i = tid; i < 257; i += 256) tw1024[i] = cs.tw1024[i];
     __syncthreads();
 
@@ -691,7 +699,7 @@ __global__ void __launch_bounds__(256) istft_kernel(const c32* __restrict__ S, c
 #pragma unroll
         for (int m = 0; m < 8; ++m) v[m] = active ? z[t + 64 * m] : mk(0.f, 0.f);
         group_bar(g);
-        group_fft512(v, z, tw512, t, g);
+        group_fft512(v, z, tw1, tw2, t, g);
         if (active) {
             float2* o2 = reinterpret_cast<float2*>(ola + lf * HOP);
             const float2* w2 = reinterpret_cast<const float2*>(winv);

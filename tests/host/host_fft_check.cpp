@@ -10,12 +10,15 @@ using namespace maf;
 typedef std::complex<double> cd;
 static double frand() { return rand() / (double)RAND_MAX * 2.0 - 1.0; }
 
-static void fft512_emul(const std::vector<c32>& x, std::vector<c32>& X, const std::vector<c32>& tw) {
+static void fft512_emul(const std::vector<c32>& x, std::vector<c32>& X, const std::vector<c32>& tw512) {
+    std::vector<c32> tw1(FFT512_TW1), tw2(FFT512_TW2);
+    for (int p = 0; p < 8; ++p) for (int t = 0; t < 64; ++t) tw1[p * 64 + t] = tw512[t * p];
+    for (int c = 0; c < 8; ++c) for (int a = 0; a < 8; ++a) tw2[c * 8 + a] = tw512[8 * a * c];
     std::vector<c32> sm(FFT512_SMEM);
     c32 regs[64][8];
-    for (int t = 0; t < 64; ++t) { for (int m = 0; m < 8; ++m) regs[t][m] = x[t + 64 * m]; fft512_step1(regs[t], sm.data(), tw.data(), t); }
+    for (int t = 0; t < 64; ++t) { for (int m = 0; m < 8; ++m) regs[t][m] = x[t + 64 * m]; fft512_step1(regs[t], sm.data(), tw1.data(), t); }
     for (int t = 0; t < 64; ++t) fft512_step2_load(regs[t], sm.data(), t);
-    for (int t = 0; t < 64; ++t) fft512_step2_store(regs[t], sm.data(), tw.data(), t);
+    for (int t = 0; t < 64; ++t) fft512_step2_store(regs[t], sm.data(), tw2.data(), t);
     for (int t = 0; t < 64; ++t) { fft512_step3(regs[t], sm.data(), t); int u = fft512_out_base(t); for (int d = 0; d < 8; ++d) X[u + 64 * d] = regs[t][d]; }
 }
 
@@ -68,9 +71,10 @@ int main() {
     // ---- fft200 + rfft400
     {
         std::vector<float> x(400); for (auto& v : x) v = (float)frand();
-        std::vector<c32> sm(200), Z(200);
-        for (int j = 0; j < 25; ++j) { c32 v[8]; for (int m = 0; m < 8; ++m) v[m] = mk(x[2 * (j + 25 * m)], x[2 * (j + 25 * m) + 1]); fft200_stepA(v, sm.data(), tw200.data(), j); }
-        for (int p = 0; p < 8; ++p) { c32 o[25]; fft200_stepB(sm.data(), tw200.data(), p, o); for (int q = 0; q < 25; ++q) Z[p + 8 * q] = o[q]; }
+        std::vector<c32> sm(200), Z(200), twA(200);
+        for (int p = 0; p < 8; ++p) for (int j = 0; j < 25; ++j) twA[p * 25 + j] = tw200[j * p];
+        for (int j = 0; j < 25; ++j) { c32 v[8]; for (int m = 0; m < 8; ++m) v[m] = mk(x[2 * (j + 25 * m)], x[2 * (j + 25 * m) + 1]); fft200_stepA(v, sm.data(), twA.data(), j); }
+        for (int p = 0; p < 8; ++p) { c32 o[25]; fft200_stepB(sm.data(), p, o); for (int q = 0; q < 25; ++q) Z[p + 8 * q] = o[q]; }
         double err = 0;
         for (int k = 0; k <= 200; ++k) {
             c32 zk = Z[k % 200], znk = Z[(200 - k) % 200];
