@@ -7,7 +7,7 @@ __all__ = ["FrontEnd", "Plan", "GpuAudioPreprocessor", "GpuLogMelFrontEnd", "__v
 
 
 def __getattr__(name):
-    if name in ("FrontEnd", "Plan", "FrontEndResult", "MafError"):
+    if name in ("FrontEnd", "Plan", "FrontEndResult", "HostPipeline", "MafError"):
         from . import frontend
         return getattr(frontend, name)
     if name == "GpuAudioPreprocessor":

@@ -266,4 +266,69 @@ class Plan:
         return self.split_mel(mel)
 
 
-__all__ = ["FrontEnd", "Plan", "FrontEndResult", "MafError", "ItemDesc"]
+class HostPipeline:
+    """Host-buffer entry with copy / compute overlap: ``depth`` plans (each with its own device buffers and stream) are
+    used round-robin, so the H2D copy and the kernels of batch i+1 run while batch i's results travel back over PCIe.
+
+    ``submit(slot_inputs)`` is asynchronous; ``results(slot)`` waits for that slot and returns pinned host tensors
+    (final int16 PCM, float32 log-mel, float64 LUFS) in the plan's layouts.
+    """
+
+    def __init__(self, fe: FrontEnd, lengths: Sequence[int], depth: int = 2, **plan_kw):
+        self.fe = fe
+        self.depth = depth
+        self.plans = [fe.plan(lengths, **plan_kw) for _ in range(depth)]
+        p0 = self.plans[0]
+        dev = fe.device
+        self.streams = [torch.cuda.Stream(dev) for _ in range(depth)]
+        self.d_in = [torch.empty(max(p0.total_pcm, 8), dtype=torch.int16, device=dev) for _ in range(depth)]
+        self.d_out = [torch.empty(max(p0.total_out, 8), dtype=torch.int16, device=dev) for _ in range(depth)]
+        self.d_mel = [torch.empty(max(p0.total_mel, 4), dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.h_in = [torch.empty(max(p0.total_pcm, 8), dtype=torch.int16).pin_memory() for _ in range(depth)]
+        self.h_out = [torch.empty(max(p0.total_out, 8), dtype=torch.int16).pin_memory() for _ in range(depth)]
+        self.h_mel = [torch.empty(max(p0.total_mel, 4), dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.h_lufs = [torch.empty(p0.n_items, dtype=torch.float64).pin_memory() for _ in range(depth)]
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        self._n = 0
+        for p in self.plans:
+            _ = p.workspace
+
+    @property
+    def h2d_bytes(self) -> int:
+        return 2 * self.plans[0].total_pcm
+
+    @property
+    def d2h_bytes(self) -> int:
+        p = self.plans[0]
+        return 2 * p.total_out + 4 * p.total_mel + 8 * p.n_items
+
+    def submit(self) -> int:
+        """Process the batch currently in ``h_in[slot]`` (slot = submission count mod depth).  Returns the slot."""
+        slot = self._n % self.depth
+        self._n += 1
+        plan, st = self.plans[slot], self.streams[slot]
+        self.done[slot].synchronize()                      # the slot's previous results must have been consumed
+        with torch.cuda.stream(st):
+            self.d_in[slot].copy_(self.h_in[slot], non_blocking=True)
+            res = plan.process(self.d_in[slot], out_pcm=self.d_out[slot], mel=self.d_mel[slot] if plan.params.n_mels else None)
+            self.h_out[slot].copy_(self.d_out[slot], non_blocking=True)
+            if plan.params.n_mels:
+                self.h_mel[slot].copy_(self.d_mel[slot], non_blocking=True)
+            self.h_lufs[slot].copy_(res.lufs, non_blocking=True)
+            self.done[slot].record(st)
+        return slot
+
+    def next_slot(self) -> int:
+        return self._n % self.depth
+
+    def results(self, slot: int):
+        self.done[slot].synchronize()
+        p = self.plans[slot]
+        return p.split_out(self.h_out[slot]), (p.split_mel(self.h_mel[slot]) if p.params.n_mels else []), self.h_lufs[slot]
+
+    def drain(self) -> None:
+        for e in self.done:
+            e.synchronize()
+
+
+__all__ = ["FrontEnd", "Plan", "FrontEndResult", "HostPipeline", "MafError", "ItemDesc"]

@@ -239,3 +239,26 @@ def test_process_host_matches_device(frontend):
     assert torch.equal(plan.split_out(hout)[0], res.pcm[0].cpu())
     assert torch.equal(plan.split_mel(hmel)[0], res.log_mel[0].cpu())
     assert hl.item() == res.lufs.item()
+
+
+def test_host_pipeline_overlap_matches_device(frontend):
+    """HostPipeline (double-buffered H2D / kernels / D2H) must return exactly what the device entry returns."""
+    from modular_audio_pipeline_b200 import HostPipeline
+    clips = [gen(12, 30 + i) for i in range(3)]
+    lengths = [c.numel() for c in clips]
+    pipe = HostPipeline(frontend, lengths, depth=2, n_mels=80)
+    want = []
+    for rep in range(3):                                   # three submissions through two slots
+        batch = [torch.roll(c, rep * 1000) for c in clips]
+        slot = pipe.next_slot()
+        pipe.plans[slot].pack(batch, out=pipe.h_in[slot])
+        assert pipe.submit() == slot
+        plan = frontend.plan(lengths, n_mels=80)
+        want.append((slot, plan.process(plan.pack(batch))))
+        if rep >= 1:                                       # check the previous submission while this one is in flight
+            pslot, pres = want[rep - 1]
+            out, mel, lufs = pipe.results(pslot)
+            for i in range(3):
+                assert torch.equal(out[i], pres.pcm[i].cpu()) and torch.equal(mel[i], pres.log_mel[i].cpu())
+            assert torch.equal(lufs, pres.lufs.cpu())
+    pipe.drain()
