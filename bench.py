@@ -93,11 +93,31 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+STAGE_KERNELS = {"stft": ["stft1024_kernel"], "ns_mask": ["ns_scan_kernel", "ns_mask_smooth_kernel"], "smooth_mask": ["smooth_mask_kernel"],
+                 "istft": ["istft_kernel"], "kweight": ["kweight_energy_kernel"], "gate": ["gate_kernel"], "logmel": ["logmel_kernel"],
+                 "mel_finalize": ["mel_finalize_kernel"], "noise": ["frame_stats_kernel", "select_clip_kernel", "noise_pass_kernel", "noise_finalize_kernel"]}
+
+
+def ncu_traffic(workload, stage):
+    """DRAM bytes per launch of the stage's kernels from the committed `ncu --set full` capture of this workload
+    (profiles/traffic_<workload>.json, written by profiles/summarize.py); None when there is no capture."""
+    path = os.path.join(ROOT, "profiles", f"traffic_{workload}.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        t = json.load(f)
+    vals = [t["bytes_per_launch"].get(k) for k in STAGE_KERNELS.get(stage, [])]
+    vals = [v for v in vals if v is not None]
+    return (float(sum(vals)) if vals else None), t.get("tag")
+
+
 def stage_bytes(plan, lengths, stationary, n_mels, padding):
     """Algorithmic bytes per launch of every stage = each kernel's mandatory inputs + outputs."""
     rows = 0
     need_rows = 0
     pad_samples = 0
+    tiles16 = 0
+    tiles32 = 0
     for n in lengths:
         if n > 600000:
             chunks = [(min(600000, n - s), 660000) for s in range(0, n, 600000)]
@@ -105,15 +125,19 @@ def stage_bytes(plan, lengths, stationary, n_mels, padding):
             chunks = [(n, n + 60000)]
         for keep, L in chunks:
             rows += L // 256 + 1
+            tiles16 += (L // 256 + 1 + 15) // 16
+            tiles32 += (L // 256 + 1 + 3 + 31) // 32
             need_rows += (30000 + keep - 1) // 256 - 30000 // 256 + 1 + 3
             pad_samples += L
     n_tot = sum(lengths)
     mel_frames = sum((n + padding) // 160 for n in lengths)
     b = {}
     b["noise"] = 2 * n_tot if stationary else 0
-    b["stft"] = 2 * pad_samples + rows * 4096 + (rows * 68 if stationary else 0)
-    b["ns_mask"] = 0 if stationary else rows * (4096 + 513 * 4)
-    b["smooth_mask"] = (rows * 68 if stationary else rows * 513 * 4) + rows * 513 * 4
+    # non-stationary: the STFT kernel also writes the scan partials P, Q (one float each per 16-frame tile and bin); the
+    # mask stage = scan (reads P, Q, writes the tile-end states) + mask kernel (reads S once, the states, writes M)
+    b["stft"] = 2 * pad_samples + rows * 4096 + (rows * 68 if stationary else tiles16 * 513 * 8)
+    b["ns_mask"] = 0 if stationary else rows * (4096 + 513 * 4) + tiles16 * 513 * 16 + tiles32 * 513 * 8
+    b["smooth_mask"] = (rows * 68 + rows * 513 * 4) if stationary else 0
     b["istft"] = need_rows * (4096 + 513 * 4) + 2 * n_tot
     b["kweight"] = 2 * n_tot
     b["gate"] = 0
@@ -247,8 +271,9 @@ def main():
     hbm_peak, peak_kind = peaks()
     dom = max(stage, key=lambda k: stage[k])
     achieved = sbytes[dom] / (stage[dom] * 1e-3) / 1e9 if stage[dom] > 0 else 0.0
+    traffic, traffic_tag = ncu_traffic(args.workload, dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_kind": peak_kind, "algorithmic_bytes_per_launch": sbytes[dom],
+                "traffic": traffic, "traffic_source": f"profiles/{traffic_tag}_ncu.md" if traffic_tag else None, "peak_kind": peak_kind, "algorithmic_bytes_per_launch": sbytes[dom],
                 "kernel_ms": stage[dom],
                 "stages": {k: {"ms": round(stage[k], 4), "GBps": round(sbytes[k] / (stage[k] * 1e-3) / 1e9, 1) if stage[k] > 0 else 0.0}
                            for k in stage}}

@@ -144,7 +144,9 @@ struct maf_plan {
     double target_peak = 0.0, inv_block = 0.0;
     KWeight kw{};
     SmoothTaps taps{};
-    WsBuf S, M, M0, bits, rowflag, T2, T2hi, nmax, partial, E, ZC, clips, seg, den16, peak, peak_norm, mel_max, sub, gates;
+    NsParams ns{}; void* d_ns = nullptr;
+    long long total_tiles = 0;
+    WsBuf S, M, P, Q, Yend, Zend, bits, rowflag, T2, T2hi, nmax, partial, E, ZC, clips, seg, den16, peak, peak_norm, mel_max, sub, gates;
     long long ws_bytes = 0;
     long long launches = 0;
     // optional per-stage CUDA-event timing (maf_plan_profile): ring of event sets, one per maf_process call
@@ -212,6 +214,14 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
     pl->ctx = ctx; pl->device = ctx->device; pl->p = p; pl->n_items = n_items;
     if (design_taps(p.sample_rate, pl->taps)) { delete pl; return fail(MAF_ERR_UNSUPPORTED, "smoothing taps exceed kernel limits for this rate"); }
     design_kweight((double)p.sample_rate, pl->kw);
+    {   // noisereduce non-stationary defaults: time_constant_s = 2.0, thresh_n_mult_nonstationary = 2, sigmoid_slope_nonstationary = 10
+        const double t = 2.0 * p.sample_rate / HOP;
+        NsParams& ns = pl->ns;
+        ns.b = (sqrt(1.0 + 4.0 * t * t) - 1.0) / (2.0 * t * t);
+        ns.a = 1.0 - ns.b; ns.inv_a = 1.0 / ns.a; ns.inv_1ma2 = 1.0 / (1.0 - ns.a * ns.a);
+        for (int i = 0; i <= 32; ++i) ns.apow[i] = pow(ns.a, (double)i);
+        ns.thresh = 2.0f; ns.slope = 10.0f;
+    }
     pl->target_peak = 32768.0 * pow(10.0, -0.1 / 20.0);
     pl->inv_block = 1.0 / (0.4 * (double)p.sample_rate);
     pl->frame_len = (int)(p.sample_rate * 0.025);
@@ -220,7 +230,7 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
     pl->tile_len = (int)(0.4 * (1 * 0.25) * (double)p.sample_rate);
     std::vector<Clip> fixed(n_items);
     std::vector<long long> foff(n_items); std::vector<int> fcount(n_items);
-    long long pcm_cur = 0, out_cur = 0, den_cur = 0, mel_cur = 0, row_cur = 0, sf_cur = 0; int kt_cur = 0;
+    long long pcm_cur = 0, out_cur = 0, den_cur = 0, mel_cur = 0, row_cur = 0, sf_cur = 0, tile_cur = 0; int kt_cur = 0;
     for (int i = 0; i < n_items; ++i) {
         const maf_item_desc& d = descs[i];
         const bool whole = d.g0 == 0 && d.own_len == d.n_global;
@@ -257,6 +267,7 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
             c.s_local = d.origin + (long long)k * CHUNK;
             c.row0 = row_cur; row_cur += c.n_frames;
             c.out_off = (long long)k * CHUNK;
+            c.tile0 = tile_cur; tile_cur += (c.n_frames + STFT_TILE - 1) / STFT_TILE;
             pl->chunks.push_back(c);
             pl->max_chunk_frames = std::max(pl->max_chunk_frames, c.n_frames);
         }
@@ -316,13 +327,16 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
     }
     pl->n_chunks = (int)pl->chunks.size();
     pl->total_pcm = pcm_cur; pl->total_out = out_cur; pl->total_mel = mel_cur; pl->total_rows = row_cur;
-    pl->total_sframes = sf_cur; pl->total_den = den_cur; pl->total_ktiles = kt_cur;
+    pl->total_sframes = sf_cur; pl->total_den = den_cur; pl->total_ktiles = kt_cur; pl->total_tiles = tile_cur;
     pl->n_slices = std::max(1, std::min(32, (592 + n_items - 1) / n_items));
     // workspace layout
     long long cur = 0;
     pl->S = carve(cur, pl->total_rows * S_PITCH * (long long)sizeof(c32));
     pl->M = carve(cur, pl->total_rows * M_PITCH * 4LL);
-    pl->M0 = carve(cur, p.stationary ? 0 : pl->total_rows * M_PITCH * 4LL);
+    {
+        const long long tb = p.stationary ? 0 : pl->total_tiles * T_PITCH * 4LL;
+        pl->P = carve(cur, tb); pl->Q = carve(cur, tb); pl->Yend = carve(cur, tb); pl->Zend = carve(cur, tb);
+    }
     pl->bits = carve(cur, p.stationary ? pl->total_rows * B_PITCH * 4LL : 0);
     pl->rowflag = carve(cur, (long long)pl->n_chunks * M_PITCH);
     pl->T2 = carve(cur, (long long)n_items * T_PITCH * 4);
@@ -348,12 +362,14 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
     const size_t o_it = put(pl->items.data(), sizeof(Item) * n_items), o_io = put(io.data(), sizeof(Item) * n_items);
     const size_t o_ch = put(pl->chunks.data(), sizeof(Chunk) * pl->chunks.size());
     const size_t o_fo = put(foff.data(), 8 * n_items), o_fc = put(fcount.data(), 4 * n_items), o_cl = put(fixed.data(), sizeof(Clip) * n_items);
+    const size_t o_ns = put(&pl->ns, sizeof(NsParams));
     cudaError_t e = cudaMalloc(&pl->tables, host.size());
     if (e == cudaSuccess) e = cudaMemcpy(pl->tables, host.data(), host.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { if (pl->tables) cudaFree(pl->tables); delete pl; return fail(MAF_ERR_CUDA, std::string("plan tables: ") + cudaGetErrorString(e)); }
     unsigned char* b = (unsigned char*)pl->tables;
     pl->d_items = (Item*)(b + o_it); pl->d_items_io = (Item*)(b + o_io); pl->d_chunks = (Chunk*)(b + o_ch);
     pl->d_foff = (long long*)(b + o_fo); pl->d_fcount = (int*)(b + o_fc); pl->d_clips_fixed = (Clip*)(b + o_cl);
+    pl->d_ns = (void*)(b + o_ns);
     *out = pl;
     return MAF_OK;
 }
@@ -489,23 +505,26 @@ static int run_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pc
     }
     mark(pl, ST_NOISE, st);
     launch_stft(pcm, pl->d_items, pl->d_chunks, pl->n_chunks, pl->max_chunk_frames, pl->ctx->c, p.stationary, ws_ptr<float>(ws, pl->T2),
-                ws_ptr<float>(ws, pl->T2hi), ws_ptr<c32>(ws, pl->S), ws_ptr<uint32_t>(ws, pl->bits), ws_ptr<uint8_t>(ws, pl->rowflag), st);
+                ws_ptr<float>(ws, pl->T2hi), ws_ptr<c32>(ws, pl->S), ws_ptr<uint32_t>(ws, pl->bits), ws_ptr<uint8_t>(ws, pl->rowflag),
+                (const NsParams*)pl->d_ns, ws_ptr<float>(ws, pl->P), ws_ptr<float>(ws, pl->Q), st);
     pl->launches += 1;
     mark(pl, ST_STFT, st);
     if (!p.stationary) {
-        // noisereduce non-stationary defaults: time_constant_s = 2.0, thresh_n_mult = 2, sigmoid_slope = 10
-        const double t = 2.0 * p.sample_rate / HOP;
-        const double b = (sqrt(1.0 + 4.0 * t * t) - 1.0) / (2.0 * t * t);
-        launch_ns_mask(ws_ptr<c32>(ws, pl->S), pl->d_chunks, pl->n_chunks, b, 2.0f, 10.0f, ws_ptr<float>(ws, pl->M0), st);
-        pl->launches += 1;
+        launch_ns_mask(ws_ptr<c32>(ws, pl->S), pl->d_chunks, pl->n_chunks, pl->max_chunk_frames, pl->ns, ws_ptr<float>(ws, pl->P),
+                       ws_ptr<float>(ws, pl->Q), ws_ptr<float>(ws, pl->Yend), ws_ptr<float>(ws, pl->Zend), p.prop_decrease, pl->taps,
+                       ws_ptr<float>(ws, pl->M), st);
+        pl->launches += 2;
     }
     mark(pl, ST_NSMASK, st);
-    launch_smooth_mask(ws_ptr<uint32_t>(ws, pl->bits), ws_ptr<uint8_t>(ws, pl->rowflag), ws_ptr<float>(ws, pl->M0), pl->d_chunks, pl->n_chunks,
-                       pl->max_chunk_frames, p.stationary, p.prop_decrease, pl->taps, ws_ptr<float>(ws, pl->M), st);
+    if (p.stationary) {
+        launch_smooth_mask(ws_ptr<uint32_t>(ws, pl->bits), ws_ptr<uint8_t>(ws, pl->rowflag), pl->d_chunks, pl->n_chunks,
+                           pl->max_chunk_frames, p.prop_decrease, pl->taps, ws_ptr<float>(ws, pl->M), st);
+        pl->launches += 1;
+    }
     mark(pl, ST_SMOOTH, st);
     launch_istft(ws_ptr<c32>(ws, pl->S), ws_ptr<float>(ws, pl->M), pl->d_items, pl->d_chunks, pl->n_chunks, pl->ctx->c,
                  den_dst, to_out, out_f32, ws_ptr<int>(ws, pl->peak), st);
-    pl->launches += 2;
+    pl->launches += 1;
     mark(pl, ST_ISTFT, st);
     CU(cudaGetLastError());
     return MAF_OK;

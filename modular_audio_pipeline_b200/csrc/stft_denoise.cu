@@ -4,8 +4,10 @@
 //   noise_threshold_*  per-bin mean + 1.5 std of the noise clip's dB spectrogram  -> power thresholds T2 / T2hi
 //   stft1024_kernel    K1: int16 PCM -> windowed real FFT 1024 / hop 256 on each chunk's own frame grid
 //                          -> S (complex64, 4 KB per frame) + 513 raw-mask bits per frame (stationary)
-//   ns_mask_kernel     K2a (non-stationary): forward-backward one-pole smoothing along time + sigmoid mask
-//   smooth_mask_kernel K2: separable 7(time) x 33(freq) triangular smoothing of the raw mask -> M (fp32)
+//   ns_scan_kernel / ns_mask_smooth_kernel
+//                      K2a (non-stationary): forward-backward one-pole smoothing along time as a tile scan, sigmoid
+//                          mask and the separable smoothing, S read once -> M (fp32)
+//   smooth_mask_kernel K2 (stationary): separable 7(time) x 33(freq) triangular smoothing of the raw bits -> M (fp32)
 //   istft_kernel       K3: S * M -> inverse real FFT -> windowed overlap-add -> / 1.5 -> int16 (+ peak)
 //
 // The stationary gate "dB > thresh" is evaluated without a logarithm: 20 log10(|X| + eps) > t  <=>
@@ -33,12 +35,20 @@ __device__ __forceinline__ void group_fft512(c32 (&v)[8], c32* sm, const c32* tw
 // ============================================================================================================
 // K1  forward STFT
 // ============================================================================================================
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// Non-stationary mode additionally emits, per (16-frame tile, bin), the two weighted sums of |X| from which the scan
+// kernel rebuilds the forward / backward one-pole states at every tile boundary (see ns_scan_kernel):
+//   P = sum_s b a^(n-1-s) |X_s|                      zero-state forward response at the end of the tile
+//   Q = sum_s b^2 a^s (1 - a^(2(n-s))) / (1 - a^2) |X_s|   zero-state backward response (of the zero-state forward one)
+//                                                    at the start of the tile;  n = frames in the tile, s = 0..n-1
 template <bool STATIONARY>
-__global__ void __launch_bounds__(256) stft1024_kernel(const int16_t* __restrict__ pcm, const Item* __restrict__ items,
+__global__ void __launch_bounds__(256, 4) stft1024_kernel(const int16_t* __restrict__ pcm, const Item* __restrict__ items,
                                                        const Chunk* __restrict__ chunks, Consts cs,
                                                        const float* __restrict__ T2, const float* __restrict__ T2hi,
                                                        c32* __restrict__ S, uint32_t* __restrict__ bits,
-                                                       uint8_t* __restrict__ rowflag) {
+                                                       uint8_t* __restrict__ rowflag, const NsParams* __restrict__ nsp,
+                                                       float* __restrict__ P, float* __restrict__ Q) {
     constexpr int SPAN = (STFT_TILE + 3) * HOP;       // samples covered by the tile's frames
     __shared__ __align__(16) int16_t span[SPAN];
     __shared__ float win[NFFT];
@@ -46,13 +56,23 @@ __global__ void __launch_bounds__(256) stft1024_kernel(const int16_t* __restrict
     __shared__ c32 tw2[FFT512_TW2];
     __shared__ c32 tw1024[257];
     __shared__ __align__(16) c32 fsm[4][FFT512_SMEM];
-    __shared__ __align__(4) uint8_t flags[4][528];
+    __shared__ __align__(4) uint8_t flags[STATIONARY ? 4 : 1][528];
+    __shared__ float wpq[2][STFT_TILE];
 
     const Chunk ch = chunks[blockIdx.y];
     const int f0 = blockIdx.x * STFT_TILE;
     if (f0 >= ch.n_frames) return;
     const Item it = items[ch.item];
     const int tid = threadIdx.x;
+    if (!STATIONARY && tid < STFT_TILE) {
+        const int n = min(STFT_TILE, ch.n_frames - f0);
+        float wp = 0.f, wq = 0.f;
+        if (tid < n) {
+            wp = (float)(nsp->b * nsp->apow[n - 1 - tid]);
+            wq = (float)(nsp->b * nsp->b * nsp->apow[tid] * (1.0 - nsp->apow[2 * (n - tid)]) * nsp->inv_1ma2);
+        }
+        wpq[0][tid] = wp; wpq[1][tid] = wq;
+    }
 
     for (int i = tid; i < NFFT; i += 256) win[i] = cs.win1024[i];
     for (int i = tid; i < FFT512_TW1; i += 256) tw1[i] = cs.tw1[i];
@@ -91,10 +111,14 @@ __global__ void __launch_bounds__(256) stft1024_kernel(const int16_t* __restrict
     // the four 64-thread groups run decoupled from here on: span / tables are read-only, fsm / flags are per group
     const short2* span2 = reinterpret_cast<const short2*>(span);
     const float2* win2 = reinterpret_cast<const float2*>(win);
+    float accP[9], accQ[9];                                   // bins t + 64 q -> 2q, 512 - (t + 64 q) -> 2q + 1, 256 -> 8
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { accP[i] = 0.f; accQ[i] = 0.f; }
     for (int r = 0; r < STFT_TILE / 4; ++r) {
         const int lf = r * 4 + g;
         const int f = f0 + lf;
         const bool active = f < ch.n_frames;
+        const float wp = STATIONARY ? 0.f : wpq[0][lf], wq = STATIONARY ? 0.f : wpq[1][lf];
         c32 v[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
@@ -126,6 +150,10 @@ __global__ void __launch_bounds__(256) stft1024_kernel(const int16_t* __restrict
                         if (p0 > t2hi[0]) rf[0] = 1;
                         if (pn > t2hi[512]) rf[512] = 1;
                         if (pm > t2hi[256]) rf[256] = 1;
+                    } else {
+                        const float a0 = fabsf(x0), an = fabsf(xn), am = fast_sqrt(xm.x * xm.x + xm.y * xm.y);
+                        accP[0] += wp * a0; accQ[0] += wq * a0; accP[1] += wp * an; accQ[1] += wq * an;
+                        accP[8] += wp * am; accQ[8] += wq * am;
                     }
                 } else {
                     c32 xk, xnk;
@@ -137,6 +165,9 @@ __global__ void __launch_bounds__(256) stft1024_kernel(const int16_t* __restrict
                         flags[g][k] = pk > t2[k]; flags[g][512 - k] = pnk > t2[512 - k];
                         if (pk > t2hi[k]) rf[k] = 1;
                         if (pnk > t2hi[512 - k]) rf[512 - k] = 1;
+                    } else {
+                        const float ak = fast_sqrt(xk.x * xk.x + xk.y * xk.y), ank = fast_sqrt(xnk.x * xnk.x + xnk.y * xnk.y);
+                        accP[2 * q] += wp * ak; accQ[2 * q] += wq * ak; accP[2 * q + 1] += wp * ank; accQ[2 * q + 1] += wq * ank;
                     }
                 }
             }
@@ -158,11 +189,36 @@ __global__ void __launch_bounds__(256) stft1024_kernel(const int16_t* __restrict
         }
         group_bar(g);
     }
+    if (!STATIONARY) {
+        // combine the four groups' partial sums in a fixed order (group g's scratch is free after its last barrier)
+        float* gp = reinterpret_cast<float*>(fsm[g]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = t + 64 * q;
+            if (k == 0) {
+                gp[0] = accP[0]; gp[512] = accP[1]; gp[256] = accP[8];
+                gp[T_PITCH] = accQ[0]; gp[T_PITCH + 512] = accQ[1]; gp[T_PITCH + 256] = accQ[8];
+            } else {
+                gp[k] = accP[2 * q]; gp[512 - k] = accP[2 * q + 1];
+                gp[T_PITCH + k] = accQ[2 * q]; gp[T_PITCH + 512 - k] = accQ[2 * q + 1];
+            }
+        }
+        __syncthreads();
+        const long long trow = (ch.tile0 + blockIdx.x) * T_PITCH;
+        for (int k = tid; k < NBIN; k += 256) {
+            const float* g0p = reinterpret_cast<const float*>(fsm[0]);
+            const float* g1p = reinterpret_cast<const float*>(fsm[1]);
+            const float* g2p = reinterpret_cast<const float*>(fsm[2]);
+            const float* g3p = reinterpret_cast<const float*>(fsm[3]);
+            P[trow + k] = (g0p[k] + g1p[k]) + (g2p[k] + g3p[k]);
+            Q[trow + k] = (g0p[T_PITCH + k] + g1p[T_PITCH + k]) + (g2p[T_PITCH + k] + g3p[T_PITCH + k]);
+        }
+    }
 }
 
 void launch_stft(const int16_t* pcm, const Item* items, const Chunk* chunks, int n_chunks, int max_frames,
                  const Consts& c, int stationary, const float* T2, const float* T2hi, c32* S, uint32_t* bits,
-                 uint8_t* rowflag, cudaStream_t st) {
+                 uint8_t* rowflag, const NsParams* ns, float* P, float* Q, cudaStream_t st) {
     if (n_chunks <= 0) return;
     const int tiles = (max_frames + STFT_TILE - 1) / STFT_TILE;
     for (int y0 = 0; y0 < n_chunks; y0 += 32768) {
@@ -170,9 +226,9 @@ void launch_stft(const int16_t* pcm, const Item* items, const Chunk* chunks, int
         dim3 grid(tiles, ny);
         if (stationary)
             stft1024_kernel<true><<<grid, 256, 0, st>>>(pcm, items, chunks + y0, c, T2, T2hi, S, bits,
-                                                        rowflag + (long long)y0 * M_PITCH);
+                                                        rowflag + (long long)y0 * M_PITCH, nullptr, nullptr, nullptr);
         else
-            stft1024_kernel<false><<<grid, 256, 0, st>>>(pcm, items, chunks + y0, c, nullptr, nullptr, S, nullptr, nullptr);
+            stft1024_kernel<false><<<grid, 256, 0, st>>>(pcm, items, chunks + y0, c, nullptr, nullptr, S, nullptr, nullptr, ns, P, Q);
     }
 }
 
@@ -338,156 +394,247 @@ void launch_noise_threshold(const int16_t* pcm, const Clip* clips, int n_items, 
 }
 
 // ============================================================================================================
-// K2a  non-stationary raw mask: Sm = filtfilt([b], [1, b-1], |S|) along time, M0 = sigmoid(((|S|-Sm)/Sm - 2) * 10)
-// One thread per (chunk, bin); consecutive threads read consecutive bins of a frame row (coalesced).  The
-// recurrence runs in float64 (cheap on B200, keeps the 0.992-pole accumulation at 1e-16).
+// K2a  non-stationary mask (noisereduce spectralgate/nonstationary.py): Sm = filtfilt([b], [1, b-1], |S|) along time
+// (padtype=None: both passes start in steady state), raw = sigmoid(((|S| - Sm) / Sm - 2) * 10), then the same
+// separable triangular smoothing as the stationary gate and the prop_decrease blend.
+//
+// The forward-backward one-pole recurrence spans the whole chunk (pole 0.992: no usable warm-up length), so it is
+// evaluated as a two-level scan instead of a serial sweep over HBM:
+//   level 1 (inside stft1024_kernel)  per 16-frame tile two weighted sums P, Q of |X|
+//   level 2 (ns_scan_kernel)          one thread per (chunk, bin) walks the ~162 tiles twice in float64:
+//                                       y_e(j) = a^n y_e(j-1) + P_j                     y_e(-1) = |X_0|
+//                                       z_e(j-1) = Q_j + c_n y_e(j-1) + a^n z_e(j)      z_e(last) = y_e(last)
+//                                     with c_n = b a (1 - a^2n) / (1 - a^2); y_e(j) = yf at the tile's last frame,
+//                                     z_e(j) = backward state entering the tile from the right
+//   level 3 (ns_mask_smooth_kernel)   a CTA owns 32 output frames; one thread per bin walks the 32 + 2 nt frames it
+//                                     needs DOWNWARDS from a tile boundary: z = b yf + a z, yf' = (yf - b |X|) / a
+//                                     (the forward recurrence run in reverse: error growth a^-38 = 1.36), sigmoid,
+//                                     time taps in a register window, rows to shared memory; then the frequency
+//                                     taps as in smooth_mask_kernel.  S is read once (+ 2 nt / 32 halo), M written once.
 // Deviation (documented in DESIGN.md): where Sm == 0 (an all-zero frequency row) noisereduce yields NaN; here the
 // relative excess is taken as 0 so the mask is sigmoid(-20) and the output is silence instead of NaN.
 // ============================================================================================================
-__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-
-constexpr int NS_BINS = 64;          // bins per CTA: one 512-byte segment of every S row, 256 bytes of every M0 row
-constexpr int NS_TT = 32;            // frames per streamed tile
-constexpr int NS_THREADS = 128;
-constexpr int NS_PITCH = NS_BINS + 1;
-
-// A CTA owns (chunk, 64 bins) -- plus bin 512, which shares slot 0 with bin 0, for group 0 -- and streams the chunk's
-// frames through shared memory in tiles of 32: all threads load the tile with 16-byte coalesced accesses (the next tile
-// is prefetched into registers while the current one is processed), lanes 0..64 run the serial one-pole recurrence over
-// the tile from shared memory, all threads write the tile back.  Forward pass writes yf into M0, the backward pass
-// re-reads S and yf in reverse and overwrites M0 with the sigmoid mask.  8 groups x chunks CTAs, all resident at once.
-__global__ void __launch_bounds__(NS_THREADS, 6) ns_mask_kernel(const c32* __restrict__ S, const Chunk* __restrict__ chunks, double b,
-                                                                float thresh_mult, float slope, float* __restrict__ M0) {
-    __shared__ float A[NS_TT][NS_PITCH];
-    __shared__ float Y[NS_TT][NS_PITCH];
-    const Chunk ch = chunks[blockIdx.y];
-    const int gi = blockIdx.x;
+__global__ void __launch_bounds__(128) ns_scan_kernel(const c32* __restrict__ S, const Chunk* __restrict__ chunks, int n_chunks,
+                                                      NsParams ns, const float* __restrict__ P, const float* __restrict__ Q,
+                                                      float* __restrict__ Yend, float* __restrict__ Zend) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (int)(idx / NBIN), k = (int)(idx - (long long)c * NBIN);
+    if (c >= n_chunks) return;
+    const Chunk ch = chunks[c];
     const int F = ch.n_frames;
-    const int tid = threadIdx.x;
-    const bool has_nyq = gi == 0;
-    const int nser = has_nyq ? NS_BINS + 1 : NS_BINS;
-    const float4* s4 = reinterpret_cast<const float4*>(S + ch.row0 * S_PITCH + gi * NS_BINS);   // row pitch = 256 float4
-    float* m0 = M0 + ch.row0 * M_PITCH + gi * NS_BINS;
-    const double a = 1.0 - b;
-    const int n_tiles = (F + NS_TT - 1) / NS_TT;
-
-    float4 ps[8];                                   // prefetched S tile: element idx = tid + 128 i -> row idx/32, float4 idx%32
-    auto load_s = [&](int f0) {
+    const int nt = (F + STFT_TILE - 1) / STFT_TILE;
+    const int n_last = F - (nt - 1) * STFT_TILE;
+    const c32 s0 = S[ch.row0 * S_PITCH + (k & 511)];
+    const double a0 = (double)(k == 0 ? fabsf(s0.x) : k == 512 ? fabsf(s0.y) : fast_sqrt(s0.x * s0.x + s0.y * s0.y));
+    const double aN = ns.apow[STFT_TILE], aL = ns.apow[n_last];
+    const double cN = ns.b * ns.a * (1.0 - ns.apow[2 * STFT_TILE]) * ns.inv_1ma2;
+    const double cL = ns.b * ns.a * (1.0 - ns.apow[2 * n_last]) * ns.inv_1ma2;
+    const float* p = P + ch.tile0 * T_PITCH + k;
+    const float* q = Q + ch.tile0 * T_PITCH + k;
+    float* ye = Yend + ch.tile0 * T_PITCH + k;
+    float* ze = Zend + ch.tile0 * T_PITCH + k;
+    double y = a0;
+    int j = 0;
+    for (; j + 8 <= nt - 1; j += 8) {
+        float pv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int idx = tid + NS_THREADS * i, r = idx >> 5, c = idx & 31;
-            ps[i] = (f0 + r < F) ? __ldg(s4 + (long long)(f0 + r) * (S_PITCH / 2) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-    auto put_abs = [&]() {
+        for (int u = 0; u < 8; ++u) pv[u] = p[(long long)(j + u) * T_PITCH];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int idx = tid + NS_THREADS * i, r = idx >> 5, c = idx & 31;
-            if (has_nyq && c == 0) { A[r][0] = fabsf(ps[i].x); A[r][NS_BINS] = fabsf(ps[i].y); }
-            else A[r][2 * c] = fast_sqrt(ps[i].x * ps[i].x + ps[i].y * ps[i].y);
-            A[r][2 * c + 1] = fast_sqrt(ps[i].z * ps[i].z + ps[i].w * ps[i].w);
-        }
-    };
-
-    // ---------------- forward pass (steady-state start: y[-1] = x[0]) ----------------
-    double y = 0.0;
-    load_s(0);
-    for (int tI = 0; tI < n_tiles; ++tI) {
-        const int f0 = tI * NS_TT;
-        const int rows = min(NS_TT, F - f0);
-        put_abs();
-        __syncthreads();
-        if (tI + 1 < n_tiles) load_s(f0 + NS_TT);
-        if (tid < nser) {
-            if (tI == 0) y = (double)A[0][tid];
-#pragma unroll 8
-            for (int r = 0; r < rows; ++r) { y = b * (double)A[r][tid] + a * y; Y[r][tid] = (float)y; }
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-            const int idx = tid + NS_THREADS * i, r = idx >> 6, c = idx & 63;
-            if (r < rows) m0[(long long)(f0 + r) * M_PITCH + c] = Y[r][c];
-        }
-        if (has_nyq && tid < rows) M0[(ch.row0 + f0 + tid) * M_PITCH + 512] = Y[tid][NS_BINS];
-        // the next iteration's put_abs only touches A, and Y is rewritten after the next barrier: no extra barrier needed
+        for (int u = 0; u < 8; ++u) { y = aN * y + (double)pv[u]; ye[(long long)(j + u) * T_PITCH] = (float)y; }
     }
-    // ---------------- backward pass over yf, again started in steady state ----------------
-    double z = (double)(float)y;                    // yf[F - 1] as stored
-    float4 py[4];
-    auto load_y = [&](int f0) {
+    for (; j < nt - 1; ++j) { y = aN * y + (double)p[(long long)j * T_PITCH]; ye[(long long)j * T_PITCH] = (float)y; }
+    y = aL * y + (double)p[(long long)(nt - 1) * T_PITCH];
+    ye[(long long)(nt - 1) * T_PITCH] = (float)y;
+    // backward: z enters tile j from the right
+    double z = (double)(float)y;
+    ze[(long long)(nt - 1) * T_PITCH] = (float)z;
+    {
+        const double yprev = nt > 1 ? (double)ye[(long long)(nt - 2) * T_PITCH] : a0;
+        z = (double)q[(long long)(nt - 1) * T_PITCH] + cL * yprev + aL * z;
+    }
+    j = nt - 2;
+    for (; j - 8 >= 0; j -= 8) {
+        float qv[8], yv[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int idx = tid + NS_THREADS * i, r = idx >> 4, c = idx & 15;
-            py[i] = (f0 + r < F) ? *reinterpret_cast<const float4*>(m0 + (long long)(f0 + r) * M_PITCH + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-    __syncthreads();
-    load_s((n_tiles - 1) * NS_TT);
-    load_y((n_tiles - 1) * NS_TT);
-    float ynyq = (has_nyq && tid < NS_TT && (n_tiles - 1) * NS_TT + tid < F) ? M0[(ch.row0 + (n_tiles - 1) * NS_TT + tid) * M_PITCH + 512] : 0.f;
-    for (int tI = n_tiles - 1; tI >= 0; --tI) {
-        const int f0 = tI * NS_TT;
-        const int rows = min(NS_TT, F - f0);
-        put_abs();
+        for (int u = 0; u < 8; ++u) { qv[u] = q[(long long)(j - u) * T_PITCH]; yv[u] = ye[(long long)(j - u - 1) * T_PITCH]; }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int idx = tid + NS_THREADS * i, r = idx >> 4, c = idx & 15;
-            Y[r][4 * c] = py[i].x; Y[r][4 * c + 1] = py[i].y; Y[r][4 * c + 2] = py[i].z; Y[r][4 * c + 3] = py[i].w;
+        for (int u = 0; u < 8; ++u) { ze[(long long)(j - u) * T_PITCH] = (float)z; z = (double)qv[u] + cN * (double)yv[u] + aN * z; }
+    }
+    for (; j >= 0; --j) {
+        ze[(long long)j * T_PITCH] = (float)z;
+        const double yprev = j > 0 ? (double)ye[(long long)(j - 1) * T_PITCH] : a0;
+        z = (double)q[(long long)j * T_PITCH] + cN * yprev + aN * z;
+    }
+}
+
+constexpr int SM_ROW = MAX_NF + 520 + MAX_NF;     // 584 floats, multiple of 4: a mask row with zero halos for the frequency taps
+constexpr int NSM_THREADS = 544;                  // 17 warps: one thread per bin in the recurrence phase
+constexpr size_t NSM_SMEM = sizeof(float) * NS_TILE * SM_ROW;
+
+// frequency taps on one shared-memory row segment: 8 consecutive outputs starting at bin k0 (src = &row[MAX_NF + k0])
+__device__ __forceinline__ void freq_taps8(const float* src, int nf, const float* vf, float (&out)[8]) {
+#pragma unroll
+    for (int o = 0; o < 8; ++o) out[o] = 0.f;
+    if (nf == 16) {
+        // triangle(33) = box(17) * box(17) / 289: two running sums restarted per work item (<= 23 updates each)
+        float in[40];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const float4 q = *reinterpret_cast<const float4*>(src - 16 + 4 * i);
+            in[4 * i] = q.x; in[4 * i + 1] = q.y; in[4 * i + 2] = q.z; in[4 * i + 3] = q.w;
         }
-        if (has_nyq && tid < NS_TT) Y[tid][NS_BINS] = ynyq;
-        __syncthreads();
-        if (tI > 0) {
-            load_s(f0 - NS_TT); load_y(f0 - NS_TT);
-            if (has_nyq && tid < NS_TT) ynyq = M0[(ch.row0 + f0 - NS_TT + tid) * M_PITCH + 512];
+        float b1[24];                                   // b1[i] = sum in[i .. i + 16]  (centre k0 - 8 + i)
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 17; ++i) acc += in[i];
+        b1[0] = acc;
+#pragma unroll
+        for (int i = 1; i < 24; ++i) { acc += in[i + 16] - in[i - 1]; b1[i] = acc; }
+        float a2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 17; ++i) a2 += b1[i];
+        out[0] = a2;
+#pragma unroll
+        for (int o = 1; o < 8; ++o) { a2 += b1[o + 16] - b1[o - 1]; out[o] = a2; }
+#pragma unroll
+        for (int o = 0; o < 8; ++o) out[o] *= (1.0f / 289.0f);
+    } else {
+        for (int tp = 0; tp <= 2 * nf; ++tp) {
+            const float wt = vf[tp];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) out[o] += wt * src[o + tp - nf];
         }
-        if (tid < nser) {
-#pragma unroll 8
-            for (int r = rows - 1; r >= 0; --r) { z = b * (double)Y[r][tid] + a * z; Y[r][tid] = (float)z; }
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-            const int idx = tid + NS_THREADS * i, r = idx >> 6, c = idx & 63;
-            if (r < rows) {
-                const float sm = Y[r][c], x = A[r][c];
-                const float rr = sm > 0.f ? __fdividef(x - sm, sm) : 0.f;
-                m0[(long long)(f0 + r) * M_PITCH + c] = __fdividef(1.0f, 1.0f + __expf(-(rr - thresh_mult) * slope));
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NSM_THREADS, 2) ns_mask_smooth_kernel(const c32* __restrict__ S, const Chunk* __restrict__ chunks,
+                                                                        NsParams ns, const float* __restrict__ Yend,
+                                                                        const float* __restrict__ Zend, float prop, SmoothTaps taps,
+                                                                        float* __restrict__ M) {
+    extern __shared__ __align__(16) float rows[];                 // [NS_TILE][SM_ROW]
+    constexpr int W = NS_TILE + 2 * NT;                           // frames walked per bin
+    const Chunk ch = chunks[blockIdx.y];
+    const int F = ch.n_frames;
+    const int base = NS_TILE * blockIdx.x;                        // outputs [base - NT, base + 32 - NT), walked frames [base - 2 NT, base + 32)
+    if (base - NT >= F) return;
+    const int tid = threadIdx.x;
+    // zero halos left and right of the 513 bins
+    for (int i = tid; i < NS_TILE * (SM_ROW - NBIN); i += NSM_THREADS) {
+        const int r = i / (SM_ROW - NBIN), c = i - r * (SM_ROW - NBIN);
+        rows[r * SM_ROW + (c < MAX_NF ? c : c + NBIN)] = 0.f;
+    }
+    if (tid < NBIN) {
+        const int k = tid;
+        const int e = min(base + NS_TILE, F);                    // the walk starts at frame e - 1; states are known at tile ends
+        const long long srow = (ch.tile0 + (e + STFT_TILE - 1) / STFT_TILE - 1) * T_PITCH + k;
+        double y = (double)Yend[srow], z = (double)Zend[srow];
+        const c32* sp = S + ch.row0 * S_PITCH + (k & 511);
+        const double b = ns.b, a = ns.a, ia = ns.inv_a;
+        float w[2 * NT + 1];
+#pragma unroll
+        for (int i = 0; i < 2 * NT + 1; ++i) w[i] = 0.f;
+#pragma unroll
+        for (int b0 = 0; b0 < W; b0 += 8) {
+            c32 pv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int rr = base + NS_TILE - 1 - (b0 + u);
+                pv[u] = (b0 + u < W && rr >= 0 && rr < F) ? sp[(long long)rr * S_PITCH] : mk(0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = b0 + u;
+                if (i < W) {
+                    const int rr = base + NS_TILE - 1 - i;
+                    float R = 0.f;
+                    if (rr >= 0 && rr < F) {
+                        const float A = k == 0 ? fabsf(pv[u].x) : k == 512 ? fabsf(pv[u].y) : fast_sqrt(pv[u].x * pv[u].x + pv[u].y * pv[u].y);
+                        z = b * y + a * z;
+                        y = (y - b * (double)A) * ia;
+                        const float sm = (float)z;
+                        const float rel = sm > 0.f ? __fdividef(A - sm, sm) : 0.f;
+                        R = __fdividef(1.0f, 1.0f + __expf(-(rel - ns.thresh) * ns.slope));
+                    }
+#pragma unroll
+                    for (int j = 2 * NT; j > 0; --j) w[j] = w[j - 1];
+                    w[0] = R;                                     // w[j] = raw mask of frame rr + j
+                    if (i >= 2 * NT) {
+                        const int lr = NS_TILE - 1 + 2 * NT - i;  // output frame rr + NT = base - NT + lr
+                        float acc = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 2 * NT + 1; ++j) acc += taps.vt[j] * w[j];
+                        rows[lr * SM_ROW + MAX_NF + k] = acc;
+                    }
+                }
             }
         }
-        if (has_nyq && tid < rows) {
-            const float sm = Y[tid][NS_BINS], x = A[tid][NS_BINS];
-            const float rr = sm > 0.f ? __fdividef(x - sm, sm) : 0.f;
-            M0[(ch.row0 + f0 + tid) * M_PITCH + 512] = __fdividef(1.0f, 1.0f + __expf(-(rr - thresh_mult) * slope));
+    }
+    __syncthreads();
+    // frequency taps + blend, 8 consecutive outputs per work item
+    const int nf = taps.nf;
+    for (int wi = tid; wi < NS_TILE * 65; wi += NSM_THREADS) {
+        const int lr = wi / 65, seg = wi - lr * 65;
+        const int f = base - NT + lr;
+        if (f < 0 || f >= F) continue;
+        const int k0 = 8 * seg;
+        float out[8];
+        freq_taps8(&rows[lr * SM_ROW + MAX_NF + k0], nf, taps.vf, out);
+        float* dst = M + (ch.row0 + f) * M_PITCH + k0;
+        if (k0 + 8 <= NBIN) {
+            *reinterpret_cast<float4*>(dst) = make_float4(out[0] * prop + (1.0f - prop), out[1] * prop + (1.0f - prop),
+                                                          out[2] * prop + (1.0f - prop), out[3] * prop + (1.0f - prop));
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(out[4] * prop + (1.0f - prop), out[5] * prop + (1.0f - prop),
+                                                              out[6] * prop + (1.0f - prop), out[7] * prop + (1.0f - prop));
+        } else {
+            dst[0] = out[0] * prop + (1.0f - prop);               // bin 512
         }
-        __syncthreads();
     }
 }
 
-void launch_ns_mask(const c32* S, const Chunk* chunks, int n_chunks, double b, float thresh_mult, float slope,
-                    float* M0, cudaStream_t st) {
+template <int NT>
+static void launch_nsm(dim3 grid, cudaStream_t st, const c32* S, const Chunk* chunks, const NsParams& ns, const float* Yend,
+                       const float* Zend, float prop, const SmoothTaps& taps, float* M) {
+    cudaFuncSetAttribute(ns_mask_smooth_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NSM_SMEM);
+    ns_mask_smooth_kernel<NT><<<grid, NSM_THREADS, NSM_SMEM, st>>>(S, chunks, ns, Yend, Zend, prop, taps, M);
+}
+
+void launch_ns_mask(const c32* S, const Chunk* chunks, int n_chunks, int max_frames, const NsParams& ns, const float* P,
+                    const float* Q, float* Yend, float* Zend, float prop, const SmoothTaps& taps, float* M,
+                    cudaStream_t st) {
     if (n_chunks <= 0) return;
+    {
+        const long long threads = (long long)n_chunks * NBIN;
+        ns_scan_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(S, chunks, n_chunks, ns, P, Q, Yend, Zend);
+    }
+    const int tiles = (max_frames + taps.nt + NS_TILE - 1) / NS_TILE;
     for (int y0 = 0; y0 < n_chunks; y0 += 32768) {
         const int ny = n_chunks - y0 < 32768 ? n_chunks - y0 : 32768;
-        dim3 grid(S_PITCH / NS_BINS, ny);
-        ns_mask_kernel<<<grid, NS_THREADS, 0, st>>>(S, chunks + y0, b, thresh_mult, slope, M0);
+        dim3 grid(tiles, ny);
+        switch (taps.nt) {
+            case 1: launch_nsm<1>(grid, st, S, chunks + y0, ns, Yend, Zend, prop, taps, M); break;
+            case 2: launch_nsm<2>(grid, st, S, chunks + y0, ns, Yend, Zend, prop, taps, M); break;
+            case 3: launch_nsm<3>(grid, st, S, chunks + y0, ns, Yend, Zend, prop, taps, M); break;
+            case 4: launch_nsm<4>(grid, st, S, chunks + y0, ns, Yend, Zend, prop, taps, M); break;
+            case 5: launch_nsm<5>(grid, st, S, chunks + y0, ns, Yend, Zend, prop, taps, M); break;
+            case 6: launch_nsm<6>(grid, st, S, chunks + y0, ns, Yend, Zend, prop, taps, M); break;
+            case 7: launch_nsm<7>(grid, st, S, chunks + y0, ns, Yend, Zend, prop, taps, M); break;
+            case 8: launch_nsm<8>(grid, st, S, chunks + y0, ns, Yend, Zend, prop, taps, M); break;
+            default: launch_nsm<9>(grid, st, S, chunks + y0, ns, Yend, Zend, prop, taps, M); break;
+        }
     }
 }
 
 // ============================================================================================================
-// K2  separable triangular smoothing (scipy.signal.fftconvolve(mask, outer(vf, vt)/sum, 'same'), zero padded)
-//   stationary    : raw = bit | rowflag ? 1 : 1 - prop          (blend, then smooth)
-//   non-stationary: raw = M0 ; out = smooth(raw) * prop + 1 - prop   (smooth, then blend)
-// Phase 1 applies the time taps while reading the raw rows from global/L2 (each row is re-read by at most
-// 2 nt + 1 neighbouring output rows of the same CTA), writing rows into shared memory with MAX_NF zeros on both
-// sides; phase 2 applies the frequency taps from shared memory, 8 outputs per thread in registers.
+// K2  separable triangular smoothing of the stationary gate (scipy.signal.fftconvolve(mask, outer(vf, vt)/sum, 'same'),
+// zero padded): raw = bit | rowflag ? 1 : 1 - prop (blend, then smooth).
+// Phase 1 applies the time taps while expanding the raw bit rows (17 words per frame, L2 resident), writing rows into
+// shared memory with MAX_NF zeros on both sides; phase 2 applies the frequency taps from shared memory, 8 outputs per
+// thread in registers.
 // ============================================================================================================
-constexpr int SM_ROW = MAX_NF + 520 + MAX_NF;     // 584 floats, multiple of 4
-
-template <bool STATIONARY>
 __global__ void __launch_bounds__(256) smooth_mask_kernel(const uint32_t* __restrict__ bits, const uint8_t* __restrict__ rowflag,
-                                                          const float* __restrict__ M0, const Chunk* __restrict__ chunks,
-                                                          float prop, SmoothTaps taps, float* __restrict__ M) {
+                                                          const Chunk* __restrict__ chunks, float prop, SmoothTaps taps,
+                                                          float* __restrict__ M) {
     __shared__ __align__(16) float rows[MASK_TILE][SM_ROW];
     __shared__ uint32_t rfbits[17];
     const Chunk ch = chunks[blockIdx.y];
@@ -496,14 +643,14 @@ __global__ void __launch_bounds__(256) smooth_mask_kernel(const uint32_t* __rest
     const int tid = threadIdx.x;
     const int nt = taps.nt, nf = taps.nf;
     for (int i = tid; i < MASK_TILE * SM_ROW; i += 256) (&rows[0][0])[i] = 0.f;
-    if (STATIONARY && tid < 17) {
+    if (tid < 17) {
         const uint8_t* rf = rowflag + (long long)blockIdx.y * M_PITCH;
         uint32_t w = 0;
         for (int b = 0; b < 32; ++b) { const int k = 32 * tid + b; if (k < NBIN && rf[k]) w |= 1u << b; }
         rfbits[tid] = w;
     }
     __syncthreads();
-    if (STATIONARY) {
+    {
         const float lo = 1.0f - prop;
         for (int w = tid; w < MASK_TILE * 17; w += 256) {
             const int lf = w / 17, wi = w % 17;
@@ -525,44 +672,6 @@ __global__ void __launch_bounds__(256) smooth_mask_kernel(const uint32_t* __rest
 #pragma unroll
             for (int b = 0; b < 32; ++b) if (b < nb) rows[lf][MAX_NF + 32 * wi + b] = acc[b];
         }
-    } else if (nt == 3) {
-        // one work item = 4 consecutive bins x 8 output frames: 14 float4 row loads feed 8 outputs (sliding window)
-        for (int w = tid; w < 2 * 129; w += 256) {
-            const int q = w >> 1, h = w & 1;
-            const int fa = f0 + 8 * h;                       // first output frame of this item
-            const float* src = M0 + ch.row0 * M_PITCH + 4 * q;
-            float4 x[14];
-#pragma unroll
-            for (int j = 0; j < 14; ++j) {
-                const int ff = fa - 3 + j;
-                x[j] = (ff >= 0 && ff < ch.n_frames) ? *reinterpret_cast<const float4*>(src + (long long)ff * M_PITCH) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            const float t0 = taps.vt[0], t1 = taps.vt[1], t2 = taps.vt[2], t3 = taps.vt[3];
-#pragma unroll
-            for (int o = 0; o < 8; ++o) {
-                if (fa + o >= ch.n_frames) break;
-                float4 r;
-                r.x = t0 * (x[o].x + x[o + 6].x) + t1 * (x[o + 1].x + x[o + 5].x) + t2 * (x[o + 2].x + x[o + 4].x) + t3 * x[o + 3].x;
-                r.y = t0 * (x[o].y + x[o + 6].y) + t1 * (x[o + 1].y + x[o + 5].y) + t2 * (x[o + 2].y + x[o + 4].y) + t3 * x[o + 3].y;
-                r.z = t0 * (x[o].z + x[o + 6].z) + t1 * (x[o + 1].z + x[o + 5].z) + t2 * (x[o + 2].z + x[o + 4].z) + t3 * x[o + 3].z;
-                r.w = t0 * (x[o].w + x[o + 6].w) + t1 * (x[o + 1].w + x[o + 5].w) + t2 * (x[o + 2].w + x[o + 4].w) + t3 * x[o + 3].w;
-                if (q == 128) { r.y = 0.f; r.z = 0.f; r.w = 0.f; }           // bins 513..515 are row padding
-                *reinterpret_cast<float4*>(&rows[8 * h + o][MAX_NF + 4 * q]) = r;
-            }
-        }
-    } else {
-        for (int e = tid; e < MASK_TILE * NBIN; e += 256) {
-            const int lf = e / NBIN, k = e - lf * NBIN;
-            const int f = f0 + lf;
-            if (f >= ch.n_frames) continue;
-            float acc = 0.f;
-            for (int j = -nt; j <= nt; ++j) {
-                const int ff = f + j;
-                if (ff < 0 || ff >= ch.n_frames) continue;
-                acc += taps.vt[j + nt] * M0[(ch.row0 + ff) * M_PITCH + k];
-            }
-            rows[lf][MAX_NF + k] = acc;
-        }
     }
     __syncthreads();
     // phase 2: frequency taps, 8 consecutive outputs per work item
@@ -572,59 +681,23 @@ __global__ void __launch_bounds__(256) smooth_mask_kernel(const uint32_t* __rest
         if (f >= ch.n_frames) continue;
         const int k0 = 8 * seg;
         float out[8];
-#pragma unroll
-        for (int o = 0; o < 8; ++o) out[o] = 0.f;
-        const float* src = &rows[lf][MAX_NF + k0];
-        if (nf == 16) {
-            // triangle(33) = box(17) * box(17) / 289: two running sums restarted per work item (<= 23 updates each)
-            float in[40];
-#pragma unroll
-            for (int i = 0; i < 10; ++i) {
-                const float4 q = *reinterpret_cast<const float4*>(src - 16 + 4 * i);
-                in[4 * i] = q.x; in[4 * i + 1] = q.y; in[4 * i + 2] = q.z; in[4 * i + 3] = q.w;
-            }
-            float b1[24];                                   // b1[i] = sum in[i .. i + 16]  (centre k0 - 8 + i)
-            float acc = 0.f;
-#pragma unroll
-            for (int i = 0; i < 17; ++i) acc += in[i];
-            b1[0] = acc;
-#pragma unroll
-            for (int i = 1; i < 24; ++i) { acc += in[i + 16] - in[i - 1]; b1[i] = acc; }
-            float a2 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 17; ++i) a2 += b1[i];
-            out[0] = a2;
-#pragma unroll
-            for (int o = 1; o < 8; ++o) { a2 += b1[o + 16] - b1[o - 1]; out[o] = a2; }
-#pragma unroll
-            for (int o = 0; o < 8; ++o) out[o] *= (1.0f / 289.0f);
-        } else {
-            for (int tp = 0; tp <= 2 * nf; ++tp) {
-                const float wt = taps.vf[tp];
-#pragma unroll
-                for (int o = 0; o < 8; ++o) out[o] += wt * src[o + tp - nf];
-            }
-        }
+        freq_taps8(&rows[lf][MAX_NF + k0], nf, taps.vf, out);
         float* dst = M + (ch.row0 + f) * M_PITCH + k0;
 #pragma unroll
         for (int o = 0; o < 8; ++o) {
-            if (k0 + o < NBIN) dst[o] = STATIONARY ? out[o] : out[o] * prop + (1.0f - prop);
+            if (k0 + o < NBIN) dst[o] = out[o];
         }
     }
 }
 
-void launch_smooth_mask(const uint32_t* bits, const uint8_t* rowflag, const float* M0, const Chunk* chunks,
-                        int n_chunks, int max_frames, int stationary, float prop, const SmoothTaps& taps, float* M,
-                        cudaStream_t st) {
+void launch_smooth_mask(const uint32_t* bits, const uint8_t* rowflag, const Chunk* chunks, int n_chunks,
+                        int max_frames, float prop, const SmoothTaps& taps, float* M, cudaStream_t st) {
     if (n_chunks <= 0) return;
     const int tiles = (max_frames + MASK_TILE - 1) / MASK_TILE;
     for (int y0 = 0; y0 < n_chunks; y0 += 32768) {
         const int ny = n_chunks - y0 < 32768 ? n_chunks - y0 : 32768;
         dim3 grid(tiles, ny);
-        if (stationary)
-            smooth_mask_kernel<true><<<grid, 256, 0, st>>>(bits, rowflag + (long long)y0 * M_PITCH, nullptr, chunks + y0, prop, taps, M);
-        else
-            smooth_mask_kernel<false><<<grid, 256, 0, st>>>(nullptr, nullptr, M0, chunks + y0, prop, taps, M);
+        smooth_mask_kernel<<<grid, 256, 0, st>>>(bits, rowflag + (long long)y0 * M_PITCH, chunks + y0, prop, taps, M);
     }
 }
 
