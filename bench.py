@@ -125,7 +125,7 @@ def stage_bytes(plan, lengths, stationary, n_mels, padding):
             chunks = [(n, n + 60000)]
         for keep, L in chunks:
             rows += L // 256 + 1
-            tiles16 += (L // 256 + 1 + 15) // 16
+            tiles16 += (L // 256 + 1 + 31) // 32     # STFT_TILE frames per scan partial
             tiles32 += (L // 256 + 1 + 3 + 31) // 32
             need_rows += (30000 + keep - 1) // 256 - 30000 // 256 + 1 + 3
             pad_samples += L

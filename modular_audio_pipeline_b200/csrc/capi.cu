@@ -145,6 +145,7 @@ struct maf_plan {
     KWeight kw{};
     SmoothTaps taps{};
     NsParams ns{}; void* d_ns = nullptr;
+    KwGeom kgeo{}; KwScan kscan{}; void* d_kscan = nullptr; int max_kgroups = 0;
     long long total_tiles = 0;
     WsBuf S, M, P, Q, Yend, Zend, bits, rowflag, T2, T2hi, nmax, partial, E, ZC, clips, seg, den16, peak, peak_norm, mel_max, sub, gates;
     long long ws_bytes = 0;
@@ -177,6 +178,50 @@ static void design_kweight(double rate, KWeight& kw) {
         const double a0 = 1 + alpha, a1 = -2 * cos(w0), a2 = 1 - alpha;
         kw.b2[0] = b0 / a0; kw.b2[1] = b1 / a0; kw.b2[2] = b2 / a0; kw.a2[0] = 1.0; kw.a2[1] = a1 / a0; kw.a2[2] = a2 / a0;
     }
+}
+
+// Segmentation of the loudness sub-blocks for kweight_energy_kernel and the powers of the homogeneous state transition.
+static int design_kwscan(const KWeight& kw, int tile_len, KwGeom& g, KwScan& t) {
+    int best = 0;
+    for (int d = 16; d <= 128; ++d)
+        if (tile_len % d == 0 && 2 * (tile_len / d) <= KW_MAX_THREADS && (!best || abs(d - 50) < abs(best - 50))) best = d;
+    if (!best) return -1;
+    g.seg = best; g.lpt = tile_len / best;
+    g.tpc = std::min(15, std::min(KW_MAX_THREADS / g.lpt - 1, 26000 / tile_len - 1));
+    if (g.tpc < 1) return -1;
+    g.threads = ((g.tpc + 1) * g.lpt + 31) / 32 * 32;
+    // one homogeneous step (x = 0) of the cascade on (z10, z11, z20, z21); see kw_step in loudness.cu
+    typedef long double ld;
+    memset(&t, 0, sizeof(t));
+    ld A[16] = {0};
+    A[0] = -(ld)kw.a1[1]; A[1] = 1;                                   // z10' = z11 - a11 z10
+    A[4] = -(ld)kw.a1[2];                                             // z11' = -a12 z10
+    A[8] = (ld)kw.b2[1] - (ld)kw.a2[1] * (ld)kw.b2[0]; A[10] = -(ld)kw.a2[1]; A[11] = 1;   // y1 = z10, y2 = b20 z10 + z20
+    A[12] = (ld)kw.b2[2] - (ld)kw.a2[2] * (ld)kw.b2[0]; A[14] = -(ld)kw.a2[2];
+    auto mul = [](const ld* x, const ld* y, ld* o) {
+        ld r[16];
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { ld a = 0; for (int k = 0; k < 4; ++k) a += x[4 * i + k] * y[4 * k + j]; r[4 * i + j] = a; }
+        for (int i = 0; i < 16; ++i) o[i] = r[i];
+    };
+    ld P[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    for (int i = 0; i < g.seg; ++i) mul(A, P, P);                     // P = A^seg
+    ld L[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    for (int l = 0; l < 32; ++l) { for (int i = 0; i < 16; ++i) t.Mlane[l][i] = (double)L[i]; mul(P, L, L); }
+    for (int i = 0; i < 16; ++i) t.Mwarp[i] = (double)L[i];           // A^(32 seg)
+    {   // state after one step from zero state with x = 1, then i homogeneous steps
+        const ld b10 = kw.b1[0], b20 = kw.b2[0];
+        ld v[4] = {(ld)kw.b1[1] - (ld)kw.a1[1] * b10, (ld)kw.b1[2] - (ld)kw.a1[2] * b10,
+                   ((ld)kw.b2[1] - (ld)kw.a2[1] * b20) * b10, ((ld)kw.b2[2] - (ld)kw.a2[2] * b20) * b10};
+        for (int i = g.seg - 1; i >= 0; --i) {
+            for (int r = 0; r < 4; ++r) t.H[i][r] = (float)(v[r] / 32768.0L);
+            ld nv[4];
+            for (int r = 0; r < 4; ++r) nv[r] = A[4 * r] * v[0] + A[4 * r + 1] * v[1] + A[4 * r + 2] * v[2] + A[4 * r + 3] * v[3];
+            for (int r = 0; r < 4; ++r) v[r] = nv[r];
+        }
+    }
+    ld S[16]; for (int i = 0; i < 16; ++i) S[i] = P[i];
+    for (int k = 0; k < 5; ++k) { for (int i = 0; i < 16; ++i) t.Mstep[k][i] = (double)S[i]; mul(S, S, S); }
+    return 0;
 }
 
 static int design_taps(int sr, SmoothTaps& t) {
@@ -219,7 +264,7 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
         NsParams& ns = pl->ns;
         ns.b = (sqrt(1.0 + 4.0 * t * t) - 1.0) / (2.0 * t * t);
         ns.a = 1.0 - ns.b; ns.inv_a = 1.0 / ns.a; ns.inv_1ma2 = 1.0 / (1.0 - ns.a * ns.a);
-        for (int i = 0; i <= 32; ++i) ns.apow[i] = pow(ns.a, (double)i);
+        for (int i = 0; i <= 2 * STFT_TILE; ++i) ns.apow[i] = pow(ns.a, (double)i);
         ns.thresh = 2.0f; ns.slope = 10.0f;
     }
     pl->target_peak = 32768.0 * pow(10.0, -0.1 / 20.0);
@@ -228,6 +273,7 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
     pl->frame_hop = (int)(p.sample_rate * 0.010);
     if (pl->frame_len >= 2048) { delete pl; return fail(MAF_ERR_UNSUPPORTED, "frame length too large for the ZCR histogram"); }
     pl->tile_len = (int)(0.4 * (1 * 0.25) * (double)p.sample_rate);
+    if (design_kwscan(pl->kw, pl->tile_len, pl->kgeo, pl->kscan)) { delete pl; return fail(MAF_ERR_UNSUPPORTED, "no loudness sub-block segmentation at this rate"); }
     std::vector<Clip> fixed(n_items);
     std::vector<long long> foff(n_items); std::vector<int> fcount(n_items);
     long long pcm_cur = 0, out_cur = 0, den_cur = 0, mel_cur = 0, row_cur = 0, sf_cur = 0, tile_cur = 0; int kt_cur = 0;
@@ -297,6 +343,11 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
             it.n_ktiles = (int)((d.own_len + pl->tile_len - 1) / pl->tile_len);
             kt_cur += it.n_ktiles;
             pl->max_ktiles = std::max(pl->max_ktiles, it.n_ktiles);
+            {
+                const long long t0 = d.g0 / pl->tile_len;
+                const long long groups = (t0 + it.n_ktiles - 1) / pl->kgeo.tpc - t0 / pl->kgeo.tpc + 1;
+                pl->max_kgroups = std::max<int>(pl->max_kgroups, (int)groups);
+            }
             const double T = (double)d.n_global / (double)p.sample_rate;
             if ((double)d.n_global < 0.4 * (double)p.sample_rate) { pl->too_short = true; it.n_blocks = 0; }
             else {
@@ -363,6 +414,7 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
     const size_t o_ch = put(pl->chunks.data(), sizeof(Chunk) * pl->chunks.size());
     const size_t o_fo = put(foff.data(), 8 * n_items), o_fc = put(fcount.data(), 4 * n_items), o_cl = put(fixed.data(), sizeof(Clip) * n_items);
     const size_t o_ns = put(&pl->ns, sizeof(NsParams));
+    const size_t o_ks = put(&pl->kscan, sizeof(KwScan));
     cudaError_t e = cudaMalloc(&pl->tables, host.size());
     if (e == cudaSuccess) e = cudaMemcpy(pl->tables, host.data(), host.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { if (pl->tables) cudaFree(pl->tables); delete pl; return fail(MAF_ERR_CUDA, std::string("plan tables: ") + cudaGetErrorString(e)); }
@@ -370,6 +422,7 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
     pl->d_items = (Item*)(b + o_it); pl->d_items_io = (Item*)(b + o_io); pl->d_chunks = (Chunk*)(b + o_ch);
     pl->d_foff = (long long*)(b + o_fo); pl->d_fcount = (int*)(b + o_fc); pl->d_clips_fixed = (Clip*)(b + o_cl);
     pl->d_ns = (void*)(b + o_ns);
+    pl->d_kscan = (void*)(b + o_ks);
     *out = pl;
     return MAF_OK;
 }
@@ -534,7 +587,7 @@ static int run_loudness_stats(maf_plan* pl, const int16_t* src, const Item* item
     if (pl->too_short) return fail(MAF_ERR_TOO_SHORT, "Audio must have length greater than the block size");
     const int n = pl->n_items;
     CU(cudaMemsetAsync(ws_ptr<int>(ws, pl->peak_norm), 0, 4LL * n, st));
-    launch_kweight_energy(src, items, n, pl->max_ktiles, pl->tile_len, pl->kw, peak_normalize, pl->target_peak, ws_ptr<int>(ws, pl->peak),
+    launch_kweight_energy(src, items, n, pl->max_kgroups, pl->tile_len, pl->kgeo, pl->kw, (const KwScan*)pl->d_kscan, peak_normalize, pl->target_peak, ws_ptr<int>(ws, pl->peak),
                           ws_ptr<double>(ws, pl->sub), ws_ptr<int>(ws, pl->peak_norm), st);
     pl->launches += 1;
     mark(pl, ST_KWEIGHT, st);

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     const long long np_global = it.n_global + padding;            // length of the zero-padded recording
     __syncthreads();
     const double factor = s_factor;
+    const PeakNorm pnv = make_peak_norm(factor);
 
     // Stage the tile's samples: global index i = 160 f - 200 + e, reflected at the true ends of the zero-padded
     // recording.  The tile also writes the final PCM of the 32 hops it is centred on (the last tile up to the item's
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
                 float a[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    if (pn) sv[e] = peak_norm_sample(sv[e], factor);
+                    if (pn) sv[e] = peak_norm_sample_fast(sv[e], pnv);
                     sv[e] = gain_sample_m(sv[e], gt);
                     a[e] = (float)sv[e] * (1.0f / 32768.0f);
                 }
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
                     const long long l = r - it.g0;                    // item-relative index into the denoised samples
                     if (l >= -(long long)it.lo_avail && l < it.own_len + it.hi_avail) {
                         int sv = x[l];
-                        if (pn) sv = peak_norm_sample(sv, factor);
+                        if (pn) sv = peak_norm_sample_fast(sv, pnv);
                         const int q = gain_sample_m(sv, gt);
                         a = (float)q * (1.0f / 32768.0f);
                         if (out16 && r == i && i >= own_lo && i < own_hi && l >= 0 && l < it.own_len) out16[it.out_off + l] = (int16_t)q;
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
             const float* pr = pw + lf * P_PITCH + st;
             float acc = 0.f;
             for (int i = 0; i < cnt; ++i) acc += wts[i] * pr[i];
-            const float lv = log10f(fmaxf(acc, 1e-10f));
+            const float lv = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;   // lg2.approx: |err| < 1e-6 in log10 units
             if (valid) {
                 mel_out[it.mel_off + (long long)m * it.mel_frames + lf0 + lf] = lv;
                 bmax = fmaxf(bmax, lv);

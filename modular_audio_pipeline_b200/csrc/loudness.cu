@@ -4,9 +4,8 @@
 //
 //   kweight_energy_kernel  K4: peak-normalise on load, the two K-weighting biquads (float64 recurrences, float32
 //                          re-quantisation between and after the stages exactly as lfilter's float32 round trips
-//                          do), and the 100 ms sub-block energies.  The recurrence is parallelised as independent
-//                          tiles: every thread owns one sub-block and first runs KW_WARM = 2048 warm-up samples
-//                          from zero state (|pole| <= 0.9852 -> residual 5.6e-14).
+//                          do), and the 100 ms sub-block energies.  The recurrence is parallelised as a segmented
+//                          scan over 2x2 / 4x4 state transitions (see the kernel).
 //   gate_kernel            400 ms / 75 % overlap block energies = 4 consecutive sub-blocks, absolute (-70 LUFS) and
 //                          relative (-10 LU) gates, integrated loudness, float32 gain and limiter peak per recording.
 //   apply_gain_kernel      gain / limiter / int16 truncation when the log-mel kernel (which fuses it) is not run.
@@ -14,70 +13,162 @@
 
 namespace maf {
 
-__global__ void __launch_bounds__(128) kweight_energy_kernel(const int16_t* __restrict__ den16, const Item* __restrict__ items,
-                                                             int tile_len, KWeight kw, int peak_normalize, double target_peak,
-                                                             const int* __restrict__ peak, double* __restrict__ sub_energy,
-                                                             int* __restrict__ peak_norm) {
+__device__ __forceinline__ void mat4_apply_add(const double* __restrict__ m, const double (&v)[4], double (&acc)[4]) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] += m[4 * r] * v[0] + m[4 * r + 1] * v[1] + m[4 * r + 2] * v[2] + m[4 * r + 3] * v[3];
+}
+
+// K4.  The two-biquad recurrence over a recording is evaluated as a segmented scan instead of a serial sweep:
+// a CTA owns `tpc` consecutive 100 ms sub-blocks plus one sub-block of warm-up before them (the slowest mode, the
+// double pole of the 38 Hz high pass, decays by e^(-2 pi 3.8) per 100 ms at every rate: the state left over from
+// before the warm-up block is below 1e-7 of its value).  The CTA's samples are staged in shared memory once (peak
+// normalisation applied on the way) and cut into one `seg`-sample segment per thread:
+//   pass 1   zero-state end state of every segment as four dot products with the precomputed state impulse responses
+//            H_i = A^(seg-1-i) B (float32: it only seeds the scan)                             -> e_l
+//   scan     inclusive Kogge-Stone over the lanes with the precomputed powers A^(seg 2^i) of the homogeneous
+//            transition (float64), then a serial hop over the warps (A^(32 seg))               -> state at segment start
+//   pass 2   every thread runs its segment from that state -- direct form II transposed like scipy.signal.lfilter, the
+//            benign shelf stage (poles 0.63) in float32, the high pass (double pole 0.985) in float64, float32 output
+//            as lfilter returns for float32 input -- and sums the squares; the lanes of a sub-block are added in a
+//            fixed order.
+// Critical path per thread: 2 seg steps + ~40 dependent FP64 operations instead of sub-block + 2048 warm-up samples.
+// Against the float64 lfilter cascade the float32 shelf stage moves samples by ~1e-7 relative and LUFS by < 1e-6 LU.
+__global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const int16_t* __restrict__ den16, const Item* __restrict__ items,
+                                                                        int tile_len, int seg, int lpt, int tpc, KWeight kw,
+                                                                        const KwScan* __restrict__ tab, int peak_normalize,
+                                                                        double target_peak, const int* __restrict__ peak,
+                                                                        double* __restrict__ sub_energy, int* __restrict__ peak_norm) {
+    extern __shared__ __align__(16) unsigned char kw_smem[];
+    double* e_lane = reinterpret_cast<double*>(kw_smem);                         // [blockDim.x] lane energies
+    double* e_warp = e_lane + blockDim.x;                                        // [32][4] zero-state end state of each warp
+    float4* hs = reinterpret_cast<float4*>(e_warp + 32 * 4);                     // [KW_MAX_SEG] state impulse responses
+    int16_t* xs = reinterpret_cast<int16_t*>(hs + KW_MAX_SEG);                   // [(tpc + 1) * tile_len] staged samples
+
     const int item = blockIdx.y;
     const Item it = items[item];
-    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long t0 = it.g0 / tile_len;                                       // global index of the item's first sub-block
+    const long long G = t0 / tpc + blockIdx.x;                                   // CTA groups are aligned to GLOBAL sub-block indices
+    const long long first_tile = G * tpc - t0;                                   // item-relative index of the group's first sub-block
+    if (first_tile >= it.n_ktiles) return;
+    const int tid = threadIdx.x;
+    const long long c0 = (first_tile - 1) * tile_len;                            // item-relative index of the first staged sample
+    const int span = (tpc + 1) * tile_len;
+    if (tid < seg) hs[tid] = make_float4(tab->H[tid][0], tab->H[tid][1], tab->H[tid][2], tab->H[tid][3]);
+
+    const int pkin = peak_normalize ? peak[item] : 0;
+    const bool pn = peak_normalize && pkin > 0;
+    const double factor = pn ? peak_factor(pkin, target_peak) : 1.0;
+    const PeakNorm pnv = make_peak_norm(factor);
+    const int16_t* x = den16 + it.den_off;
     int pk = 0;
-    if (tile < it.n_ktiles) {
-        const int pkin = peak_normalize ? peak[item] : 0;
-        const bool pn = peak_normalize && pkin > 0;
-        const double factor = pn ? peak_factor(pkin, target_peak) : 1.0;
-        const int16_t* x = den16 + it.den_off;
-        const long long start = (long long)tile * tile_len;
-        long long begin = start - KW_WARM;
-        if (begin < -(long long)it.lo_avail) begin = -(long long)it.lo_avail;
-        long long end = start + tile_len;
-        if (end > it.own_len) end = it.own_len;
-        // direct form II transposed, like scipy.signal.lfilter.  Samples are fetched and converted eight at a time so
-        // that only the four dependent DFMAs per sample sit on the recurrence's critical path.
-        double z10 = 0.0, z11 = 0.0, z20 = 0.0, z21 = 0.0;
-        double acc = 0.0;
-        auto step = [&](float xin, int s, bool own) {
-            const double xd = (double)xin;
-            const double y1 = kw.b1[0] * xd + z10;
-            z10 = (kw.b1[1] * xd + z11) - kw.a1[1] * y1;
-            z11 = kw.b1[2] * xd - kw.a1[2] * y1;
-            const double x2 = (double)(float)y1;
+    for (int g8 = tid; g8 < span / 8; g8 += blockDim.x) {
+        const long long li = c0 + 8 * g8;
+        int sv[8];
+        if (li >= -(long long)it.lo_avail && li + 8 <= it.own_len && ((it.den_off + li) & 7) == 0) {
+            const uint4 v = *reinterpret_cast<const uint4*>(x + li);
+            sv[0] = (short)(v.x & 0xffff); sv[1] = (short)(v.x >> 16); sv[2] = (short)(v.y & 0xffff); sv[3] = (short)(v.y >> 16);
+            sv[4] = (short)(v.z & 0xffff); sv[5] = (short)(v.z >> 16); sv[6] = (short)(v.w & 0xffff); sv[7] = (short)(v.w >> 16);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sv[e] = (li + e >= -(long long)it.lo_avail && li + e < it.own_len) ? (int)x[li + e] : 0;
+        }
+        if (pn) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sv[e] = peak_norm_sample_fast(sv[e], pnv);
+        }
+        if (li >= 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pk = max(pk, abs(sv[e]));
+        } else if (li + 8 > 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) if (li + e >= 0) pk = max(pk, abs(sv[e]));
+        }
+        uint4 o;
+        o.x = (uint32_t)(sv[0] & 0xffff) | ((uint32_t)sv[1] << 16); o.y = (uint32_t)(sv[2] & 0xffff) | ((uint32_t)sv[3] << 16);
+        o.z = (uint32_t)(sv[4] & 0xffff) | ((uint32_t)sv[5] << 16); o.w = (uint32_t)(sv[6] & 0xffff) | ((uint32_t)sv[7] << 16);
+        *reinterpret_cast<uint4*>(xs + 8 * g8) = o;
+    }
+    for (int i = (span / 8) * 8 + tid; i < span; i += blockDim.x) {              // tail when tile_len is not a multiple of 8
+        const long long li = c0 + i;
+        int sv = (li >= -(long long)it.lo_avail && li < it.own_len) ? (int)x[li] : 0;
+        if (pn) sv = peak_norm_sample_fast(sv, pnv);
+        if (li >= 0) pk = max(pk, abs(sv));
+        xs[i] = (int16_t)sv;
+    }
+    __syncthreads();
+
+    const int lane = tid & 31, warp = tid >> 5;
+    const int n_lanes = (tpc + 1) * lpt;
+    const bool live = tid < n_lanes;
+    const int16_t* xl = xs + (live ? tid * seg : 0);
+    // pass 1: zero-state end state of the segment (H carries the 1 / 32768 scale)
+    double e[4] = {0.0, 0.0, 0.0, 0.0};
+    if (live) {
+        float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+#pragma unroll 5
+        for (int i = 0; i < seg; ++i) {
+            const float xv = (float)xl[i];
+            const float4 h = hs[i];
+            f0 = fmaf(h.x, xv, f0); f1 = fmaf(h.y, xv, f1); f2 = fmaf(h.z, xv, f2); f3 = fmaf(h.w, xv, f3);
+        }
+        e[0] = (double)f0; e[1] = (double)f1; e[2] = (double)f2; e[3] = (double)f3;
+    }
+    // inclusive scan over the warp's lanes: e_l <- e_l + A^(seg d) e_(l-d)
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const int d = 1 << i;
+        double o[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) o[r] = __shfl_up_sync(0xffffffffu, e[r], d);
+        if (lane >= d) mat4_apply_add(tab->Mstep[i], o, e);
+    }
+    if (lane == 31) { e_warp[4 * warp] = e[0]; e_warp[4 * warp + 1] = e[1]; e_warp[4 * warp + 2] = e[2]; e_warp[4 * warp + 3] = e[3]; }
+    __syncthreads();
+    // state at the start of this warp: hop over the preceding warps
+    double sw[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int w = 0; w < warp; ++w) {
+        double nx[4] = {e_warp[4 * w], e_warp[4 * w + 1], e_warp[4 * w + 2], e_warp[4 * w + 3]};
+        mat4_apply_add(tab->Mwarp, sw, nx);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) sw[r] = nx[r];
+    }
+    // state at the start of this lane's segment
+    double z[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { const double up = __shfl_up_sync(0xffffffffu, e[r], 1); z[r] = lane > 0 ? up : 0.0; }
+    mat4_apply_add(tab->Mlane[lane], sw, z);
+    // pass 2
+    float acc = 0.f;
+    if (live) {
+        const float b10 = (float)kw.b1[0], b11 = (float)kw.b1[1], b12 = (float)kw.b1[2], a11 = (float)kw.a1[1], a12 = (float)kw.a1[2];
+        float s0 = (float)z[0], s1 = (float)z[1];
+        double z20 = z[2], z21 = z[3];
+        const long long li0 = c0 + (long long)tid * seg;
+        const int n_own = (int)max(0LL, min((long long)seg, it.own_len - li0));      // samples of this segment inside the recording
+#pragma unroll 2
+        for (int i = 0; i < n_own; ++i) {
+            const float xv = (float)xl[i] * (1.0f / 32768.0f);
+            const float y1 = fmaf(b10, xv, s0);
+            s0 = fmaf(-a11, y1, fmaf(b11, xv, s1));
+            s1 = fmaf(-a12, y1, b12 * xv);
+            const double x2 = (double)y1;
             const double y2 = kw.b2[0] * x2 + z20;
             z20 = (kw.b2[1] * x2 + z21) - kw.a2[1] * y2;
             z21 = kw.b2[2] * x2 - kw.a2[2] * y2;
             const float d = (float)y2;
-            if (own) {
-                acc += (double)__fmul_rn(d, d);
-                pk = max(pk, s < 0 ? -s : s);
-            }
-        };
-        long long i = begin;
-        const bool aligned = ((it.den_off + begin) & 7) == 0;
-        for (; i + 8 <= end; i += 8) {
-            int sv[8];
-            if (aligned) {
-                const uint4 v = *reinterpret_cast<const uint4*>(x + i);
-                sv[0] = (short)(v.x & 0xffff); sv[1] = (short)(v.x >> 16); sv[2] = (short)(v.y & 0xffff); sv[3] = (short)(v.y >> 16);
-                sv[4] = (short)(v.z & 0xffff); sv[5] = (short)(v.z >> 16); sv[6] = (short)(v.w & 0xffff); sv[7] = (short)(v.w >> 16);
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) sv[e] = x[i + e];
-            }
-            float xin[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                if (pn) sv[e] = peak_norm_sample(sv[e], factor);
-                xin[e] = (float)sv[e] * (1.0f / 32768.0f);
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) step(xin[e], sv[e], i + e >= start);
+            acc = fmaf(d, d, acc);
         }
-        for (; i < end; ++i) {
-            int sv = x[i];
-            if (pn) sv = peak_norm_sample(sv, factor);
-            step((float)sv * (1.0f / 32768.0f), sv, i >= start);
+    }
+    e_lane[tid] = (double)acc;
+    __syncthreads();
+    if (tid < tpc) {
+        const long long tile = first_tile + tid;
+        if (tile >= 0 && tile < it.n_ktiles) {
+            double sum = 0.0;
+            const double* el = e_lane + (tid + 1) * lpt;
+            for (int l = 0; l < lpt; ++l) sum += el[l];
+            sub_energy[it.ktile_first + tile] = sum;
         }
-        sub_energy[it.ktile_first + tile] = acc;
     }
     pk = max(pk, __shfl_xor_sync(0xffffffffu, pk, 16));
     pk = max(pk, __shfl_xor_sync(0xffffffffu, pk, 8));
@@ -87,15 +178,17 @@ __global__ void __launch_bounds__(128) kweight_energy_kernel(const int16_t* __re
     if ((threadIdx.x & 31) == 0 && pk > 0) atomicMax(&peak_norm[item], pk);
 }
 
-void launch_kweight_energy(const int16_t* den16, const Item* items, int n_items, int max_tiles, int tile_len,
-                           const KWeight& kw, int peak_normalize, double target_peak, const int* peak,
+void launch_kweight_energy(const int16_t* den16, const Item* items, int n_items, int max_groups, int tile_len, const KwGeom& geo,
+                           const KWeight& kw, const KwScan* tab, int peak_normalize, double target_peak, const int* peak,
                            double* sub_energy, int* peak_norm, cudaStream_t st) {
-    if (n_items <= 0 || max_tiles <= 0) return;
+    if (n_items <= 0 || max_groups <= 0) return;
+    const size_t smem = sizeof(double) * (geo.threads + 128) + sizeof(float4) * KW_MAX_SEG + sizeof(int16_t) * (size_t)(geo.tpc + 1) * tile_len + 16;
+    cudaFuncSetAttribute(kweight_energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int y0 = 0; y0 < n_items; y0 += 32768) {
         const int ny = n_items - y0 < 32768 ? n_items - y0 : 32768;
-        dim3 grid((max_tiles + 127) / 128, ny);
-        kweight_energy_kernel<<<grid, 128, 0, st>>>(den16, items + y0, tile_len, kw, peak_normalize, target_peak,
-                                                    peak ? peak + y0 : nullptr, sub_energy, peak_norm + y0);
+        dim3 grid(max_groups, ny);
+        kweight_energy_kernel<<<grid, geo.threads, smem, st>>>(den16, items + y0, tile_len, geo.seg, geo.lpt, geo.tpc, kw, tab, peak_normalize,
+                                                               target_peak, peak ? peak + y0 : nullptr, sub_energy, peak_norm + y0);
     }
 }
 
@@ -191,11 +284,12 @@ __global__ void __launch_bounds__(256) apply_gain_kernel(const int16_t* __restri
     const int pkin = peak_normalize ? peak[item] : 0;
     const bool pn = peak_normalize && pkin > 0;
     const double factor = pn ? peak_factor(pkin, target_peak) : 1.0;
+    const PeakNorm pnv = make_peak_norm(factor);
     Gate gt; gt.applied = 0;
     if (use_gate) gt = gates[item];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < it.own_len; i += (long long)gridDim.x * blockDim.x) {
         int s = den16[it.den_off + i];
-        if (pn) s = peak_norm_sample(s, factor);
+        if (pn) s = peak_norm_sample_fast(s, pnv);
         if (use_gate) s = gain_sample(s, gt);
         out16[it.out_off + i] = (int16_t)s;
     }

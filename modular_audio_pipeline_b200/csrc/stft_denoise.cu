@@ -37,7 +37,9 @@ __device__ __forceinline__ void group_fft512(c32 (&v)[8], c32* sm, const c32* tw
 // ============================================================================================================
 __device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-// Non-stationary mode additionally emits, per (16-frame tile, bin), the two weighted sums of |X| from which the scan
+constexpr int STFT_SPAN = (STFT_TILE + 3) * HOP;
+
+// Non-stationary mode additionally emits, per (STFT_TILE-frame tile, bin), the two weighted sums of |X| from which the scan
 // kernel rebuilds the forward / backward one-pole states at every tile boundary (see ns_scan_kernel):
 //   P = sum_s b a^(n-1-s) |X_s|                      zero-state forward response at the end of the tile
 //   Q = sum_s b^2 a^s (1 - a^(2(n-s))) / (1 - a^2) |X_s|   zero-state backward response (of the zero-state forward one)
@@ -49,15 +51,15 @@ __global__ void __launch_bounds__(256, 4) stft1024_kernel(const int16_t* __restr
                                                        c32* __restrict__ S, uint32_t* __restrict__ bits,
                                                        uint8_t* __restrict__ rowflag, const NsParams* __restrict__ nsp,
                                                        float* __restrict__ P, float* __restrict__ Q) {
-    constexpr int SPAN = (STFT_TILE + 3) * HOP;       // samples covered by the tile's frames
-    __shared__ __align__(16) int16_t span[SPAN];
+    constexpr int SPAN = STFT_SPAN;                   // samples covered by the tile's frames
+    extern __shared__ __align__(16) int16_t span[];   // [SPAN] (dynamic: static + dynamic exceeds the 48 KB default limit)
     __shared__ float win[NFFT];
     __shared__ c32 tw1[FFT512_TW1];
     __shared__ c32 tw2[FFT512_TW2];
     __shared__ c32 tw1024[257];
     __shared__ __align__(16) c32 fsm[4][FFT512_SMEM];
     __shared__ __align__(4) uint8_t flags[STATIONARY ? 4 : 1][528];
-    __shared__ float wpq[2][STFT_TILE];
+    __shared__ float wpq[2][STATIONARY ? 1 : STFT_TILE];
 
     const Chunk ch = chunks[blockIdx.y];
     const int f0 = blockIdx.x * STFT_TILE;
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(256, 4) stft1024_kernel(const int16_t* __restr
         const int lf = r * 4 + g;
         const int f = f0 + lf;
         const bool active = f < ch.n_frames;
-        const float wp = STATIONARY ? 0.f : wpq[0][lf], wq = STATIONARY ? 0.f : wpq[1][lf];
+        const float wp = STATIONARY ? 0.f : wpq[0][STATIONARY ? 0 : lf], wq = STATIONARY ? 0.f : wpq[1][STATIONARY ? 0 : lf];
         c32 v[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
@@ -221,14 +223,17 @@ void launch_stft(const int16_t* pcm, const Item* items, const Chunk* chunks, int
                  uint8_t* rowflag, const NsParams* ns, float* P, float* Q, cudaStream_t st) {
     if (n_chunks <= 0) return;
     const int tiles = (max_frames + STFT_TILE - 1) / STFT_TILE;
+    constexpr int dyn = STFT_SPAN * (int)sizeof(int16_t);
+    cudaFuncSetAttribute(stft1024_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    cudaFuncSetAttribute(stft1024_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     for (int y0 = 0; y0 < n_chunks; y0 += 32768) {
         const int ny = n_chunks - y0 < 32768 ? n_chunks - y0 : 32768;
         dim3 grid(tiles, ny);
         if (stationary)
-            stft1024_kernel<true><<<grid, 256, 0, st>>>(pcm, items, chunks + y0, c, T2, T2hi, S, bits,
+            stft1024_kernel<true><<<grid, 256, dyn, st>>>(pcm, items, chunks + y0, c, T2, T2hi, S, bits,
                                                         rowflag + (long long)y0 * M_PITCH, nullptr, nullptr, nullptr);
         else
-            stft1024_kernel<false><<<grid, 256, 0, st>>>(pcm, items, chunks + y0, c, nullptr, nullptr, S, nullptr, nullptr, ns, P, Q);
+            stft1024_kernel<false><<<grid, 256, dyn, st>>>(pcm, items, chunks + y0, c, nullptr, nullptr, S, nullptr, nullptr, ns, P, Q);
     }
 }
 
@@ -414,7 +419,7 @@ void launch_noise_threshold(const int16_t* pcm, const Clip* clips, int n_items, 
 // Deviation (documented in DESIGN.md): where Sm == 0 (an all-zero frequency row) noisereduce yields NaN; here the
 // relative excess is taken as 0 so the mask is sigmoid(-20) and the output is silence instead of NaN.
 // ============================================================================================================
-__global__ void __launch_bounds__(128) ns_scan_kernel(const c32* __restrict__ S, const Chunk* __restrict__ chunks, int n_chunks,
+__global__ void __launch_bounds__(64) ns_scan_kernel(const c32* __restrict__ S, const Chunk* __restrict__ chunks, int n_chunks,
                                                       NsParams ns, const float* __restrict__ P, const float* __restrict__ Q,
                                                       float* __restrict__ Yend, float* __restrict__ Zend) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -433,37 +438,57 @@ __global__ void __launch_bounds__(128) ns_scan_kernel(const c32* __restrict__ S,
     const float* q = Q + ch.tile0 * T_PITCH + k;
     float* ye = Yend + ch.tile0 * T_PITCH + k;
     float* ze = Zend + ch.tile0 * T_PITCH + k;
+    // Loads do not depend on the recurrence: they are issued SCAN_B tiles ahead (double-buffered batches) so that the
+    // walk is bound by the FP64 chain, not by one memory latency per tile.
+    constexpr int SCAN_B = 16;
+    const int nfull = nt - 1;                                  // tiles of 16 frames; the last one has n_last
     double y = a0;
-    int j = 0;
-    for (; j + 8 <= nt - 1; j += 8) {
-        float pv[8];
+    {
+        float cur[SCAN_B], nxt[SCAN_B];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) pv[u] = p[(long long)(j + u) * T_PITCH];
+        for (int u = 0; u < SCAN_B; ++u) cur[u] = u < nfull ? p[(long long)u * T_PITCH] : 0.f;
+        for (int j = 0; j < nfull; j += SCAN_B) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { y = aN * y + (double)pv[u]; ye[(long long)(j + u) * T_PITCH] = (float)y; }
+            for (int u = 0; u < SCAN_B; ++u) nxt[u] = j + SCAN_B + u < nfull ? p[(long long)(j + SCAN_B + u) * T_PITCH] : 0.f;
+#pragma unroll
+            for (int u = 0; u < SCAN_B; ++u) {
+                if (j + u < nfull) { y = aN * y + (double)cur[u]; ye[(long long)(j + u) * T_PITCH] = (float)y; }
+            }
+#pragma unroll
+            for (int u = 0; u < SCAN_B; ++u) cur[u] = nxt[u];
+        }
     }
-    for (; j < nt - 1; ++j) { y = aN * y + (double)p[(long long)j * T_PITCH]; ye[(long long)j * T_PITCH] = (float)y; }
+    const double y_before_last = y;
     y = aL * y + (double)p[(long long)(nt - 1) * T_PITCH];
     ye[(long long)(nt - 1) * T_PITCH] = (float)y;
     // backward: z enters tile j from the right
     double z = (double)(float)y;
     ze[(long long)(nt - 1) * T_PITCH] = (float)z;
+    z = (double)q[(long long)(nt - 1) * T_PITCH] + cL * (nt > 1 ? (double)(float)y_before_last : a0) + aL * z;
     {
-        const double yprev = nt > 1 ? (double)ye[(long long)(nt - 2) * T_PITCH] : a0;
-        z = (double)q[(long long)(nt - 1) * T_PITCH] + cL * yprev + aL * z;
-    }
-    j = nt - 2;
-    for (; j - 8 >= 0; j -= 8) {
-        float qv[8], yv[8];
+        // tile j = nfull - 1 - i (i ascending); y_e(j - 1) is re-read from the array written above (j = 0 uses |X_0|)
+        float cq[SCAN_B], cy[SCAN_B], nq[SCAN_B], ny[SCAN_B];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { qv[u] = q[(long long)(j - u) * T_PITCH]; yv[u] = ye[(long long)(j - u - 1) * T_PITCH]; }
+        for (int u = 0; u < SCAN_B; ++u) {
+            const int j = nfull - 1 - u;
+            cq[u] = j >= 0 ? q[(long long)j * T_PITCH] : 0.f;
+            cy[u] = j >= 1 ? ye[(long long)(j - 1) * T_PITCH] : (float)a0;
+        }
+        for (int i = 0; i < nfull; i += SCAN_B) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { ze[(long long)(j - u) * T_PITCH] = (float)z; z = (double)qv[u] + cN * (double)yv[u] + aN * z; }
-    }
-    for (; j >= 0; --j) {
-        ze[(long long)j * T_PITCH] = (float)z;
-        const double yprev = j > 0 ? (double)ye[(long long)(j - 1) * T_PITCH] : a0;
-        z = (double)q[(long long)j * T_PITCH] + cN * yprev + aN * z;
+            for (int u = 0; u < SCAN_B; ++u) {
+                const int j = nfull - 1 - (i + SCAN_B + u);
+                nq[u] = j >= 0 ? q[(long long)j * T_PITCH] : 0.f;
+                ny[u] = j >= 1 ? ye[(long long)(j - 1) * T_PITCH] : (float)a0;
+            }
+#pragma unroll
+            for (int u = 0; u < SCAN_B; ++u) {
+                const int j = nfull - 1 - (i + u);
+                if (j >= 0) { ze[(long long)j * T_PITCH] = (float)z; z = (double)cq[u] + cN * (double)cy[u] + aN * z; }
+            }
+#pragma unroll
+            for (int u = 0; u < SCAN_B; ++u) { cq[u] = nq[u]; cy[u] = ny[u]; }
+        }
     }
 }
 
@@ -507,13 +532,68 @@ __device__ __forceinline__ void freq_taps8(const float* src, int nf, const float
     }
 }
 
+// Recurrence phase of one bin: walks W = 32 + 2 NT frames downwards from frame base + 31, writes the time-smoothed raw
+// mask of the 32 output frames into column k of `rows`.  INTERIOR = every walked frame lies inside the chunk.
+template <int NT, bool INTERIOR>
+__device__ __forceinline__ void ns_walk(const c32* __restrict__ sp, int k, int base, int F, double y, double z, const NsParams& ns,
+                                        const SmoothTaps& taps, float* __restrict__ rows) {
+    constexpr int W = NS_TILE + 2 * NT;
+    const double b = ns.b, a = ns.a, ia = ns.inv_a;
+    // sigmoid(((A - sm) / sm - thresh) * slope) = 1 / (1 + 2^(c0 - c1 A / sm))
+    const float c1 = ns.slope * 1.4426950408889634f, c0 = ns.slope * (1.0f + ns.thresh) * 1.4426950408889634f;
+    float w[2 * NT + 1];
+#pragma unroll
+    for (int i = 0; i < 2 * NT + 1; ++i) w[i] = 0.f;
+    float vt[2 * NT + 1];
+#pragma unroll
+    for (int i = 0; i < 2 * NT + 1; ++i) vt[i] = taps.vt[i];
+#pragma unroll
+    for (int b0 = 0; b0 < W; b0 += 8) {
+        c32 pv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int rr = base + NS_TILE - 1 - (b0 + u);
+            if (b0 + u < W) pv[u] = (INTERIOR || (rr >= 0 && rr < F)) ? sp[(long long)rr * S_PITCH] : mk(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = b0 + u;
+            if (i < W) {
+                const int rr = base + NS_TILE - 1 - i;
+                float R = 0.f;
+                if (INTERIOR || (rr >= 0 && rr < F)) {
+                    const float A = k == 0 ? fabsf(pv[u].x) : k == 512 ? fabsf(pv[u].y) : fast_sqrt(pv[u].x * pv[u].x + pv[u].y * pv[u].y);
+                    z = b * y + a * z;
+                    y = (y - b * (double)A) * ia;
+                    const float sm = (float)z;
+                    float inv;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(sm));
+                    const float ratio = sm > 0.f ? A * inv : 1.0f;
+                    float ex;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(-c1, ratio, c0)));
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(R) : "f"(1.0f + ex));
+                }
+#pragma unroll
+                for (int j = 2 * NT; j > 0; --j) w[j] = w[j - 1];
+                w[0] = R;                                     // w[j] = raw mask of frame rr + j
+                if (i >= 2 * NT) {
+                    const int lr = NS_TILE - 1 + 2 * NT - i;  // output frame rr + NT = base - NT + lr
+                    float acc = vt[0] * w[0];
+#pragma unroll
+                    for (int j = 1; j < 2 * NT + 1; ++j) acc = fmaf(vt[j], w[j], acc);
+                    rows[lr * SM_ROW + MAX_NF + k] = acc;
+                }
+            }
+        }
+    }
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NSM_THREADS, 2) ns_mask_smooth_kernel(const c32* __restrict__ S, const Chunk* __restrict__ chunks,
                                                                         NsParams ns, const float* __restrict__ Yend,
                                                                         const float* __restrict__ Zend, float prop, SmoothTaps taps,
                                                                         float* __restrict__ M) {
     extern __shared__ __align__(16) float rows[];                 // [NS_TILE][SM_ROW]
-    constexpr int W = NS_TILE + 2 * NT;                           // frames walked per bin
     const Chunk ch = chunks[blockIdx.y];
     const int F = ch.n_frames;
     const int base = NS_TILE * blockIdx.x;                        // outputs [base - NT, base + 32 - NT), walked frames [base - 2 NT, base + 32)
@@ -528,51 +608,15 @@ __global__ void __launch_bounds__(NSM_THREADS, 2) ns_mask_smooth_kernel(const c3
         const int k = tid;
         const int e = min(base + NS_TILE, F);                    // the walk starts at frame e - 1; states are known at tile ends
         const long long srow = (ch.tile0 + (e + STFT_TILE - 1) / STFT_TILE - 1) * T_PITCH + k;
-        double y = (double)Yend[srow], z = (double)Zend[srow];
+        const double y = (double)Yend[srow], z = (double)Zend[srow];
         const c32* sp = S + ch.row0 * S_PITCH + (k & 511);
-        const double b = ns.b, a = ns.a, ia = ns.inv_a;
-        float w[2 * NT + 1];
-#pragma unroll
-        for (int i = 0; i < 2 * NT + 1; ++i) w[i] = 0.f;
-#pragma unroll
-        for (int b0 = 0; b0 < W; b0 += 8) {
-            c32 pv[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int rr = base + NS_TILE - 1 - (b0 + u);
-                pv[u] = (b0 + u < W && rr >= 0 && rr < F) ? sp[(long long)rr * S_PITCH] : mk(0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = b0 + u;
-                if (i < W) {
-                    const int rr = base + NS_TILE - 1 - i;
-                    float R = 0.f;
-                    if (rr >= 0 && rr < F) {
-                        const float A = k == 0 ? fabsf(pv[u].x) : k == 512 ? fabsf(pv[u].y) : fast_sqrt(pv[u].x * pv[u].x + pv[u].y * pv[u].y);
-                        z = b * y + a * z;
-                        y = (y - b * (double)A) * ia;
-                        const float sm = (float)z;
-                        const float rel = sm > 0.f ? __fdividef(A - sm, sm) : 0.f;
-                        R = __fdividef(1.0f, 1.0f + __expf(-(rel - ns.thresh) * ns.slope));
-                    }
-#pragma unroll
-                    for (int j = 2 * NT; j > 0; --j) w[j] = w[j - 1];
-                    w[0] = R;                                     // w[j] = raw mask of frame rr + j
-                    if (i >= 2 * NT) {
-                        const int lr = NS_TILE - 1 + 2 * NT - i;  // output frame rr + NT = base - NT + lr
-                        float acc = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 2 * NT + 1; ++j) acc += taps.vt[j] * w[j];
-                        rows[lr * SM_ROW + MAX_NF + k] = acc;
-                    }
-                }
-            }
-        }
+        if (base - 2 * NT >= 0 && base + NS_TILE <= F) ns_walk<NT, true>(sp, k, base, F, y, z, ns, taps, rows);
+        else ns_walk<NT, false>(sp, k, base, F, y, z, ns, taps, rows);
     }
     __syncthreads();
     // frequency taps + blend, 8 consecutive outputs per work item
     const int nf = taps.nf;
+    const float lo = 1.0f - prop;
     for (int wi = tid; wi < NS_TILE * 65; wi += NSM_THREADS) {
         const int lr = wi / 65, seg = wi - lr * 65;
         const int f = base - NT + lr;
@@ -582,12 +626,10 @@ __global__ void __launch_bounds__(NSM_THREADS, 2) ns_mask_smooth_kernel(const c3
         freq_taps8(&rows[lr * SM_ROW + MAX_NF + k0], nf, taps.vf, out);
         float* dst = M + (ch.row0 + f) * M_PITCH + k0;
         if (k0 + 8 <= NBIN) {
-            *reinterpret_cast<float4*>(dst) = make_float4(out[0] * prop + (1.0f - prop), out[1] * prop + (1.0f - prop),
-                                                          out[2] * prop + (1.0f - prop), out[3] * prop + (1.0f - prop));
-            *reinterpret_cast<float4*>(dst + 4) = make_float4(out[4] * prop + (1.0f - prop), out[5] * prop + (1.0f - prop),
-                                                              out[6] * prop + (1.0f - prop), out[7] * prop + (1.0f - prop));
+            *reinterpret_cast<float4*>(dst) = make_float4(fmaf(out[0], prop, lo), fmaf(out[1], prop, lo), fmaf(out[2], prop, lo), fmaf(out[3], prop, lo));
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(fmaf(out[4], prop, lo), fmaf(out[5], prop, lo), fmaf(out[6], prop, lo), fmaf(out[7], prop, lo));
         } else {
-            dst[0] = out[0] * prop + (1.0f - prop);               // bin 512
+            dst[0] = fmaf(out[0], prop, lo);                      // bin 512
         }
     }
 }
@@ -605,7 +647,7 @@ void launch_ns_mask(const c32* S, const Chunk* chunks, int n_chunks, int max_fra
     if (n_chunks <= 0) return;
     {
         const long long threads = (long long)n_chunks * NBIN;
-        ns_scan_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(S, chunks, n_chunks, ns, P, Q, Yend, Zend);
+        ns_scan_kernel<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(S, chunks, n_chunks, ns, P, Q, Yend, Zend);
     }
     const int tiles = (max_frames + taps.nt + NS_TILE - 1) / NS_TILE;
     for (int y0 = 0; y0 < n_chunks; y0 += 32768) {
