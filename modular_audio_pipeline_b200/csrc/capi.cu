@@ -25,7 +25,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 static inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
 
 // ---- context --------------------------------------------------------------------------------------------------
-struct MelHost { std::vector<int> start, count, woff; std::vector<float> w; };
+struct MelHost { std::vector<int> start, count, woff; std::vector<float> w; std::vector<int> qstart, qcount, qoff; std::vector<float> wq; };
 
 struct maf_ctx {
     int device = 0;
@@ -69,6 +69,22 @@ static MelHost build_mel(int n_mels) {
         h.start.push_back(st < 0 ? 0 : st); h.count.push_back(cnt); h.woff.push_back((int)h.w.size());
         h.w.insert(h.w.end(), row.begin(), row.end());
     }
+    // quads of adjacent rows: contiguous bin run covering the four rows, one float4 of weights per bin
+    for (int q = 0; q < n_mels / 4; ++q) {
+        int lo = W_NBIN, hi = 0;
+        for (int j = 0; j < 4; ++j) {
+            const int m = 4 * q + j;
+            if (h.count[m] > 0) { lo = std::min(lo, h.start[m]); hi = std::max(hi, h.start[m] + h.count[m]); }
+        }
+        if (hi <= lo) { lo = 0; hi = 0; }
+        h.qstart.push_back(lo); h.qcount.push_back(hi - lo); h.qoff.push_back((int)h.wq.size() / 4);
+        for (int k = lo; k < hi; ++k)
+            for (int j = 0; j < 4; ++j) {
+                const int m = 4 * q + j;
+                const bool in = k >= h.start[m] && k < h.start[m] + h.count[m];
+                h.wq.push_back(in ? h.w[h.woff[m] + k - h.start[m]] : 0.0f);
+            }
+    }
     return h;
 }
 
@@ -94,8 +110,9 @@ extern "C" int maf_create(int device, maf_ctx** out) {
     size_t o_win = put(win.data(), win.size() * 4), o_winv = put(winv.data(), winv.size() * 4), o_win4 = put(win4.data(), win4.size() * 4);
     size_t o_t512 = put(t512.data(), t512.size() * 8), o_t2 = put(t2.data(), t2.size() * 8), o_t1024 = put(t1024.data(), t1024.size() * 8);
     size_t o_t200 = put(t200.data(), t200.size() * 8), o_t400 = put(t400.data(), t400.size() * 8);
-    size_t o80[4] = {put(m80.start.data(), 80 * 4), put(m80.count.data(), 80 * 4), put(m80.woff.data(), 80 * 4), put(m80.w.data(), m80.w.size() * 4)};
-    size_t o128[4] = {put(m128.start.data(), 128 * 4), put(m128.count.data(), 128 * 4), put(m128.woff.data(), 128 * 4), put(m128.w.data(), m128.w.size() * 4)};
+    if (m80.wq.size() / 4 > MEL_WQ_MAX || m128.wq.size() / 4 > MEL_WQ_MAX) return fail(MAF_ERR_UNSUPPORTED, "mel quad table exceeds MEL_WQ_MAX");
+    size_t o80[4] = {put(m80.qstart.data(), 20 * 4), put(m80.qcount.data(), 20 * 4), put(m80.qoff.data(), 20 * 4), put(m80.wq.data(), m80.wq.size() * 4)};
+    size_t o128[4] = {put(m128.qstart.data(), 32 * 4), put(m128.qcount.data(), 32 * 4), put(m128.qoff.data(), 32 * 4), put(m128.wq.data(), m128.wq.size() * 4)};
     maf_ctx* ctx = new maf_ctx();
     ctx->device = device;
     cudaError_t e = cudaMalloc(&ctx->blob, host.size());
@@ -107,8 +124,8 @@ extern "C" int maf_create(int device, maf_ctx** out) {
     ctx->c.win1024 = (const float*)(b + o_win); ctx->c.winv1024 = (const float*)(b + o_winv); ctx->c.win400 = (const float*)(b + o_win4);
     ctx->c.tw1 = (const c32*)(b + o_t512); ctx->c.tw2 = (const c32*)(b + o_t2); ctx->c.tw1024 = (const c32*)(b + o_t1024);
     ctx->c.twA = (const c32*)(b + o_t200); ctx->c.tw400 = (const c32*)(b + o_t400);
-    ctx->mel80 = MelBank{80, (const int*)(b + o80[0]), (const int*)(b + o80[1]), (const int*)(b + o80[2]), (const float*)(b + o80[3])};
-    ctx->mel128 = MelBank{128, (const int*)(b + o128[0]), (const int*)(b + o128[1]), (const int*)(b + o128[2]), (const float*)(b + o128[3])};
+    ctx->mel80 = MelBank{80, (int)m80.wq.size() / 4, (const int*)(b + o80[0]), (const int*)(b + o80[1]), (const int*)(b + o80[2]), (const float4*)(b + o80[3])};
+    ctx->mel128 = MelBank{128, (int)m128.wq.size() / 4, (const int*)(b + o128[0]), (const int*)(b + o128[1]), (const int*)(b + o128[2]), (const float4*)(b + o128[3])};
     *out = ctx;
     return MAF_OK;
 }

@@ -23,9 +23,8 @@ __device__ __forceinline__ int gain_sample_m(int s, const Gate& gt) {
 constexpr int MEL_SPAN = (MEL_TILE - 1) * W_HOP + W_NFFT;            // 5360 samples per tile
 constexpr int Z_PITCH = 200;
 constexpr int P_PITCH = 201;
-constexpr int MEL_W_MAX = 416;                                       // packed non-zero mel weights (391 / 394 used)
 constexpr size_t LOGMEL_SMEM = sizeof(float) * MEL_SPAN + sizeof(c32) * MEL_TILE * Z_PITCH + sizeof(float) * MEL_TILE * P_PITCH +
-                               sizeof(float) * W_NFFT + sizeof(c32) * 200 + sizeof(c32) * 208 + sizeof(int) * 3 * 128 + sizeof(float) * MEL_W_MAX;
+                               sizeof(float) * W_NFFT + sizeof(c32) * 200 + sizeof(c32) * 208 + sizeof(int) * 3 * 32 + sizeof(float4) * MEL_WQ_MAX;
 
 __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__ den16, const Item* __restrict__ items, Consts cs,
                                                      MelBank mel, int padding, int peak_normalize, double target_peak,
@@ -39,10 +38,10 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     float* win = pw + MEL_TILE * P_PITCH;
     c32* twA = reinterpret_cast<c32*>(win + W_NFFT);
     c32* tw400 = twA + 200;
-    int* m_start = reinterpret_cast<int*>(tw400 + 208);
-    int* m_count = m_start + 128;
-    int* m_woff = m_count + 128;
-    float* m_w = reinterpret_cast<float*>(m_woff + 128);
+    float4* m_wq = reinterpret_cast<float4*>(tw400 + 208);               // 16-byte aligned: every array before it is a multiple of 16 bytes
+    int* m_qstart = reinterpret_cast<int*>(m_wq + MEL_WQ_MAX);
+    int* m_qcount = m_qstart + 32;
+    int* m_qoff = m_qcount + 32;
 
     const int item = blockIdx.y;
     const Item it = items[item];
@@ -52,11 +51,8 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
 
     for (int i = tid; i < W_NFFT; i += 256) win[i] = cs.win400[i];
     for (int i = tid; i < 200; i += 256) twA[i] = cs.twA[i];
-    if (tid < mel.n_mels) { m_start[tid] = mel.start[tid]; m_count[tid] = mel.count[tid]; m_woff[tid] = mel.woff[tid]; }
-    {
-        const int nw = mel.woff[mel.n_mels - 1] + mel.count[mel.n_mels - 1];
-        for (int i = tid; i < nw; i += 256) m_w[i] = mel.w[i];
-    }
+    if (tid < mel.n_mels / 4) { m_qstart[tid] = mel.qstart[tid]; m_qcount[tid] = mel.qcount[tid]; m_qoff[tid] = mel.qoff[tid]; }
+    for (int i = tid; i < mel.n_wq; i += 256) m_wq[i] = mel.wq[i];
     for (int i = tid; i < 201; i += 256) tw400[i] = cs.tw400[i];
 
     __shared__ double s_factor;
@@ -153,35 +149,44 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
         for (int q = 0; q < 25; ++q) zb[lf * Z_PITCH + p + 8 * q] = o[q];
     }
     __syncthreads();
-    // real split + power: warp w takes frames w, w + 8, ...; lanes stride over the 201 bins
-    {
-        const int lane = tid & 31, warp = tid >> 5;
-        for (int lf = warp; lf < MEL_TILE; lf += 8) {
-            const c32* z = zb + lf * Z_PITCH;
-            for (int k = lane; k < W_NBIN; k += 32) {
-                const c32 zk = z[k == 200 ? 0 : k], znk = z[k == 0 ? 0 : 200 - k];
-                const c32 X = rfft400_bin(zk, znk, tw400[k]);
-                pw[lf * P_PITCH + k] = X.x * X.x + X.y * X.y;
-            }
-        }
+    // real split + power: one work item = (frame, k <= 100) produces bins k and 200 - k from the same two loads
+    for (int idx = tid; idx < MEL_TILE * 101; idx += 256) {
+        const int lf = idx / 101, k = idx - lf * 101;
+        const c32* z = zb + lf * Z_PITCH;
+        const c32 za = z[k], zn = z[k == 0 ? 0 : 200 - k];
+        const c32 tw = tw400[k];
+        const c32 Xa = rfft400_bin(za, zn, tw);
+        const c32 Xb = rfft400_bin(zn, za, mk(-tw.x, tw.y));            // e^{-2 pi i (200 - k) / 400} = -conj(e^{-2 pi i k / 400})
+        pw[lf * P_PITCH + k] = Xa.x * Xa.x + Xa.y * Xa.y;
+        pw[lf * P_PITCH + 200 - k] = Xb.x * Xb.x + Xb.y * Xb.y;
     }
     __syncthreads();
-    // mel projection: warp-uniform mel row, lane = frame (coalesced 128 B row segments of the [n_mels, frames] output)
+    // mel projection: warp-uniform quad of four adjacent mel rows, lane = frame (coalesced 128 B row segments of the
+    // [n_mels, frames] output); each power bin of the quad's run is read once and feeds four accumulators
     {
         const int lane = tid & 31, warp = tid >> 5;
         const int lf = lane;
         const bool valid = lf0 + lf < it.mel_frames;
         float bmax = -INFINITY;
-        for (int m = warp; m < mel.n_mels; m += 8) {
-            const int st = m_start[m], cnt = m_count[m];
-            const float* wts = m_w + m_woff[m];
-            const float* pr = pw + lf * P_PITCH + st;
-            float acc = 0.f;
-            for (int i = 0; i < cnt; ++i) acc += wts[i] * pr[i];
-            const float lv = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;   // lg2.approx: |err| < 1e-6 in log10 units
+        float* orow = mel_out + it.mel_off + lf0 + lf;
+        for (int q = warp; q < mel.n_mels / 4; q += 8) {
+            const int cnt = m_qcount[q];
+            const float4* wts = m_wq + m_qoff[q];
+            const float* pr = pw + lf * P_PITCH + m_qstart[q];
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+            for (int i = 0; i < cnt; ++i) {
+                const float pv = pr[i];
+                const float4 w = wts[i];
+                a0 = fmaf(w.x, pv, a0); a1 = fmaf(w.y, pv, a1); a2 = fmaf(w.z, pv, a2); a3 = fmaf(w.w, pv, a3);
+            }
+            // lg2.approx: |err| < 3e-6 in log10 units
+            const float l0 = __log2f(fmaxf(a0, 1e-10f)) * 0.30102999566398120f, l1 = __log2f(fmaxf(a1, 1e-10f)) * 0.30102999566398120f;
+            const float l2 = __log2f(fmaxf(a2, 1e-10f)) * 0.30102999566398120f, l3 = __log2f(fmaxf(a3, 1e-10f)) * 0.30102999566398120f;
             if (valid) {
-                mel_out[it.mel_off + (long long)m * it.mel_frames + lf0 + lf] = lv;
-                bmax = fmaxf(bmax, lv);
+                float* o = orow + (long long)(4 * q) * it.mel_frames;
+                o[0] = l0; o[it.mel_frames] = l1; o[2LL * it.mel_frames] = l2; o[3LL * it.mel_frames] = l3;
+                bmax = fmaxf(fmaxf(bmax, fmaxf(l0, l1)), fmaxf(l2, l3));
             }
         }
         bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, 16));

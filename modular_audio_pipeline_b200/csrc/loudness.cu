@@ -63,29 +63,30 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
     int pk = 0;
     for (int g8 = tid; g8 < span / 8; g8 += blockDim.x) {
         const long long li = c0 + 8 * g8;
-        int sv[8];
-        if (li >= -(long long)it.lo_avail && li + 8 <= it.own_len && ((it.den_off + li) & 7) == 0) {
-            const uint4 v = *reinterpret_cast<const uint4*>(x + li);
-            sv[0] = (short)(v.x & 0xffff); sv[1] = (short)(v.x >> 16); sv[2] = (short)(v.y & 0xffff); sv[3] = (short)(v.y >> 16);
-            sv[4] = (short)(v.z & 0xffff); sv[5] = (short)(v.z >> 16); sv[6] = (short)(v.w & 0xffff); sv[7] = (short)(v.w >> 16);
-        } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) sv[e] = (li + e >= -(long long)it.lo_avail && li + e < it.own_len) ? (int)x[li + e] : 0;
-        }
-        if (pn) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) sv[e] = peak_norm_sample_fast(sv[e], pnv);
-        }
-        if (li >= 0) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) pk = max(pk, abs(sv[e]));
-        } else if (li + 8 > 0) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) if (li + e >= 0) pk = max(pk, abs(sv[e]));
-        }
         uint4 o;
-        o.x = (uint32_t)(sv[0] & 0xffff) | ((uint32_t)sv[1] << 16); o.y = (uint32_t)(sv[2] & 0xffff) | ((uint32_t)sv[3] << 16);
-        o.z = (uint32_t)(sv[4] & 0xffff) | ((uint32_t)sv[5] << 16); o.w = (uint32_t)(sv[6] & 0xffff) | ((uint32_t)sv[7] << 16);
+        if (li >= 0 && li + 8 <= it.own_len && ((it.den_off + li) & 7) == 0) {
+            // interior: eight samples of the recording in one 16-byte load
+            o = *reinterpret_cast<const uint4*>(x + li);
+            uint32_t wv[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                int s0 = (int)(short)(wv[h] & 0xffffu), s1 = (int)wv[h] >> 16;
+                if (pn) { s0 = peak_norm_sample_fast(s0, pnv); s1 = peak_norm_sample_fast(s1, pnv); }
+                pk = max(pk, max(abs(s0), abs(s1)));
+                wv[h] = ((uint32_t)s0 & 0xffffu) | ((uint32_t)s1 << 16);
+            }
+            o = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        } else {
+            int sv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                sv[e] = (li + e >= -(long long)it.lo_avail && li + e < it.own_len) ? (int)x[li + e] : 0;
+                if (pn) sv[e] = peak_norm_sample_fast(sv[e], pnv);
+                if (li + e >= 0) pk = max(pk, abs(sv[e]));
+            }
+            o.x = (uint32_t)(sv[0] & 0xffff) | ((uint32_t)sv[1] << 16); o.y = (uint32_t)(sv[2] & 0xffff) | ((uint32_t)sv[3] << 16);
+            o.z = (uint32_t)(sv[4] & 0xffff) | ((uint32_t)sv[5] << 16); o.w = (uint32_t)(sv[6] & 0xffff) | ((uint32_t)sv[7] << 16);
+        }
         *reinterpret_cast<uint4*>(xs + 8 * g8) = o;
     }
     for (int i = (span / 8) * 8 + tid; i < span; i += blockDim.x) {              // tail when tile_len is not a multiple of 8

@@ -538,33 +538,43 @@ template <int NT, bool INTERIOR>
 __device__ __forceinline__ void ns_walk(const c32* __restrict__ sp, int k, int base, int F, double y, double z, const NsParams& ns,
                                         const SmoothTaps& taps, float* __restrict__ rows) {
     constexpr int W = NS_TILE + 2 * NT;
-    const double b = ns.b, a = ns.a, ia = ns.inv_a;
+    constexpr int NB = 4;                                     // frames per load batch (double-buffered)
+    // with u = b y:  z_r = u_r + a z_(r+1),  u_(r-1) = u_r / a - (b^2 / a) |X_r|
+    const double a = ns.a, ia = ns.inv_a, b2ia = ns.b * ns.b * ns.inv_a;
+    double u = ns.b * y;
     // sigmoid(((A - sm) / sm - thresh) * slope) = 1 / (1 + 2^(c0 - c1 A / sm))
     const float c1 = ns.slope * 1.4426950408889634f, c0 = ns.slope * (1.0f + ns.thresh) * 1.4426950408889634f;
+    // bins 0 and 512 share slot 0 as (re X_0, re X_512): select the component, zero the other one
+    const bool use_y = k == 512, real_only = k == 0 || k == 512;
     float w[2 * NT + 1];
 #pragma unroll
     for (int i = 0; i < 2 * NT + 1; ++i) w[i] = 0.f;
     float vt[2 * NT + 1];
 #pragma unroll
     for (int i = 0; i < 2 * NT + 1; ++i) vt[i] = taps.vt[i];
+    c32 cur[NB], nxt[NB];
+    auto load = [&](c32 (&dst)[NB], int b0) {
 #pragma unroll
-    for (int b0 = 0; b0 < W; b0 += 8) {
-        c32 pv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int rr = base + NS_TILE - 1 - (b0 + u);
-            if (b0 + u < W) pv[u] = (INTERIOR || (rr >= 0 && rr < F)) ? sp[(long long)rr * S_PITCH] : mk(0.f, 0.f);
+        for (int q = 0; q < NB; ++q) {
+            const int rr = base + NS_TILE - 1 - (b0 + q);
+            if (b0 + q < W) dst[q] = (INTERIOR || (rr >= 0 && rr < F)) ? sp[(long long)rr * S_PITCH] : mk(0.f, 0.f);
         }
+    };
+    load(cur, 0);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = b0 + u;
+    for (int b0 = 0; b0 < W; b0 += NB) {
+        if (b0 + NB < W) load(nxt, b0 + NB);
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            const int i = b0 + q;
             if (i < W) {
                 const int rr = base + NS_TILE - 1 - i;
                 float R = 0.f;
                 if (INTERIOR || (rr >= 0 && rr < F)) {
-                    const float A = k == 0 ? fabsf(pv[u].x) : k == 512 ? fabsf(pv[u].y) : fast_sqrt(pv[u].x * pv[u].x + pv[u].y * pv[u].y);
-                    z = b * y + a * z;
-                    y = (y - b * (double)A) * ia;
+                    const float xr = use_y ? cur[q].y : cur[q].x, xi = real_only ? 0.f : cur[q].y;
+                    const float A = fast_sqrt(fmaf(xr, xr, xi * xi));
+                    z = fma(a, z, u);
+                    u = fma(u, ia, -b2ia * (double)A);
                     const float sm = (float)z;
                     float inv;
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(sm));
@@ -585,6 +595,8 @@ __device__ __forceinline__ void ns_walk(const c32* __restrict__ sp, int k, int b
                 }
             }
         }
+#pragma unroll
+        for (int q = 0; q < NB; ++q) cur[q] = nxt[q];
     }
 }
 
