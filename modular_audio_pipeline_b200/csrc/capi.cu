@@ -164,7 +164,7 @@ struct maf_plan {
     NsParams ns{}; void* d_ns = nullptr;
     KwGeom kgeo{}; KwScan kscan{}; void* d_kscan = nullptr; int max_kgroups = 0;
     long long total_tiles = 0;
-    WsBuf S, M, P, Q, Yend, Zend, bits, rowflag, T2, T2hi, nmax, partial, E, ZC, clips, seg, den16, peak, peak_norm, mel_max, sub, gates;
+    WsBuf S, M, P, Q, Yend, Zend, bits, rowflag, T2, T2hi, nmax, partial, E, ZC, clips, seg, den16, peak, pnorm, peak_norm, mel_max, sub, gates;
     long long ws_bytes = 0;
     long long launches = 0;
     // optional per-stage CUDA-event timing (maf_plan_profile): ring of event sets, one per maf_process call
@@ -417,6 +417,7 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
     pl->seg = carve(cur, (long long)n_items * 2 * 4);
     pl->den16 = carve(cur, pl->total_den * 2);
     pl->peak = carve(cur, (long long)n_items * 4);
+    pl->pnorm = carve(cur, (long long)n_items * sizeof(PeakNorm));
     pl->peak_norm = carve(cur, (long long)n_items * 4);
     pl->mel_max = carve(cur, (long long)n_items * 4);
     pl->sub = carve(cur, std::max(1, pl->total_ktiles) * 8LL);
@@ -604,7 +605,8 @@ static int run_loudness_stats(maf_plan* pl, const int16_t* src, const Item* item
     if (pl->too_short) return fail(MAF_ERR_TOO_SHORT, "Audio must have length greater than the block size");
     const int n = pl->n_items;
     CU(cudaMemsetAsync(ws_ptr<int>(ws, pl->peak_norm), 0, 4LL * n, st));
-    launch_kweight_energy(src, items, n, pl->max_kgroups, pl->tile_len, pl->kgeo, pl->kw, (const KwScan*)pl->d_kscan, peak_normalize, pl->target_peak, ws_ptr<int>(ws, pl->peak),
+    if (peak_normalize) { launch_peak_factor(ws_ptr<int>(ws, pl->peak), n, pl->target_peak, ws_ptr<PeakNorm>(ws, pl->pnorm), st); pl->launches += 1; }
+    launch_kweight_energy(src, items, n, pl->max_kgroups, pl->tile_len, pl->kgeo, pl->kw, (const KwScan*)pl->d_kscan, peak_normalize, ws_ptr<PeakNorm>(ws, pl->pnorm),
                           ws_ptr<double>(ws, pl->sub), ws_ptr<int>(ws, pl->peak_norm), st);
     pl->launches += 1;
     mark(pl, ST_KWEIGHT, st);
@@ -625,8 +627,8 @@ static int run_logmel(maf_plan* pl, const int16_t* src, const Item* items, int p
                       float* mel, bool finalize, cudaStream_t st) {
     const int n = pl->n_items;
     fill_int_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws_ptr<int>(ws, pl->mel_max), n, (int)0x80000001);
-    launch_logmel(src, items, n, pl->max_mel_tiles, pl->ctx->c, pick_mel(pl), pl->p.mel_padding, peak_normalize, pl->target_peak,
-                  ws_ptr<int>(ws, pl->peak), gates, out16, mel, ws_ptr<int>(ws, pl->mel_max), st);
+    launch_logmel(src, items, n, pl->max_mel_tiles, pl->ctx->c, pick_mel(pl), pl->p.mel_padding, peak_normalize,
+                  ws_ptr<PeakNorm>(ws, pl->pnorm), gates, out16, mel, ws_ptr<int>(ws, pl->mel_max), st);
     pl->launches += 2;
     mark(pl, ST_LOGMEL, st);
     if (finalize) {
@@ -657,7 +659,7 @@ extern "C" int maf_process(maf_plan* pl, const int16_t* pcm, const int16_t* nois
         rc = run_logmel(pl, den16, pl->d_items, pl->p.peak_normalize, gates, ws, out_pcm, mel, true, st);
         if (rc) return rc;
     } else {
-        launch_apply_gain(den16, pl->d_items, pl->n_items, pl->max_own, pl->p.peak_normalize, pl->target_peak, ws_ptr<int>(ws, pl->peak), gates, 1,
+        launch_apply_gain(den16, pl->d_items, pl->n_items, pl->max_own, pl->p.peak_normalize, ws_ptr<PeakNorm>(ws, pl->pnorm), gates, 1,
                           out_pcm, st);
         pl->launches += 1;
     }
@@ -720,7 +722,8 @@ extern "C" int maf_peak_normalize(maf_plan* pl, const int16_t* pcm, void* ws, in
     long long bx = std::max<long long>(1, std::min<long long>(1024, (pl->max_own + 4095) / 4096));
     dim3 grid((unsigned)bx, pl->n_items);
     abs_max_kernel<<<grid, 256, 0, st>>>(pcm, pl->d_items_io, ws_ptr<int>(ws, pl->peak));
-    launch_apply_gain(pcm, pl->d_items_io, pl->n_items, pl->max_own, 1, pl->target_peak, ws_ptr<int>(ws, pl->peak), nullptr, 0, out_pcm, st);
+    launch_peak_factor(ws_ptr<int>(ws, pl->peak), pl->n_items, pl->target_peak, ws_ptr<PeakNorm>(ws, pl->pnorm), st);
+    launch_apply_gain(pcm, pl->d_items_io, pl->n_items, pl->max_own, 1, ws_ptr<PeakNorm>(ws, pl->pnorm), nullptr, 0, out_pcm, st);
     pl->launches += 2;
     CU(cudaGetLastError());
     return MAF_OK;
@@ -736,7 +739,7 @@ extern "C" int maf_loudness(maf_plan* pl, const int16_t* pcm, void* ws, int16_t*
     rc = run_gate(pl, pl->d_items_io, ws, st);
     if (rc) return rc;
     const Gate* gates = ws_ptr<Gate>(ws, pl->gates);
-    launch_apply_gain(pcm, pl->d_items_io, pl->n_items, pl->max_own, 0, pl->target_peak, nullptr, gates, 1, out_pcm, st);
+    launch_apply_gain(pcm, pl->d_items_io, pl->n_items, pl->max_own, 0, nullptr, gates, 1, out_pcm, st);
     pl->launches += 1;
     if (lufs) { gather_lufs_kernel<<<(pl->n_items + 255) / 256, 256, 0, st>>>(gates, pl->n_items, lufs); pl->launches += 1; }
     CU(cudaGetLastError());

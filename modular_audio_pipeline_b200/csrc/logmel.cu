@@ -13,11 +13,11 @@ namespace maf {
 
 __device__ __forceinline__ int gain_sample_m(int s, const Gate& gt) {
     if (!gt.applied) return s;
-    float y = __fmul_rn(gt.gain, (float)s * (1.0f / 32768.0f));
+    float y = __fmul_rn(gt.gain, int_to_float_exact(s) * (1.0f / 32768.0f));
     if (gt.lim) y = __fdiv_rn(y, gt.limp);
     float v = __fmul_rn(y, 32768.0f);
     v = fminf(fmaxf(v, -32768.0f), 32767.0f);
-    return (int)v;
+    return trunc_to_int(v);
 }
 
 constexpr int MEL_SPAN = (MEL_TILE - 1) * W_HOP + W_NFFT;            // 5360 samples per tile
@@ -27,8 +27,8 @@ constexpr size_t LOGMEL_SMEM = sizeof(float) * MEL_SPAN + sizeof(c32) * MEL_TILE
                                sizeof(float) * W_NFFT + sizeof(c32) * 200 + sizeof(c32) * 208 + sizeof(int) * 3 * 32 + sizeof(float4) * MEL_WQ_MAX;
 
 __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__ den16, const Item* __restrict__ items, Consts cs,
-                                                     MelBank mel, int padding, int peak_normalize, double target_peak,
-                                                     const int* __restrict__ peak, const Gate* __restrict__ gates,
+                                                     MelBank mel, int padding, int peak_normalize,
+                                                     const PeakNorm* __restrict__ pnorm, const Gate* __restrict__ gates,
                                                      int16_t* __restrict__ out16, float* __restrict__ mel_out,
                                                      int* __restrict__ mel_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -55,17 +55,14 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     for (int i = tid; i < mel.n_wq; i += 256) m_wq[i] = mel.wq[i];
     for (int i = tid; i < 201; i += 256) tw400[i] = cs.tw400[i];
 
-    __shared__ double s_factor;
-    const int pkin = peak_normalize ? peak[item] : 0;
-    const bool pn = peak_normalize && pkin > 0;
-    if (tid == 0) s_factor = pn ? peak_factor(pkin, target_peak) : 1.0;     // pow / log10 in float64: once per CTA
+    PeakNorm pnv; pnv.active = 0;
+    if (peak_normalize) pnv = pnorm[item];
+    const bool pn = pnv.active != 0;
     Gate gt; gt.applied = 0;
     if (gates) gt = gates[item];
     const int16_t* x = den16 + it.den_off;
     const long long np_global = it.n_global + padding;            // length of the zero-padded recording
     __syncthreads();
-    const double factor = s_factor;
-    const PeakNorm pnv = make_peak_norm(factor);
 
     // Stage the tile's samples: global index i = 160 f - 200 + e, reflected at the true ends of the zero-padded
     // recording.  The tile also writes the final PCM of the 32 hops it is centred on (the last tile up to the item's
@@ -91,7 +88,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
                 for (int e = 0; e < 8; ++e) {
                     if (pn) sv[e] = peak_norm_sample_fast(sv[e], pnv);
                     sv[e] = gain_sample_m(sv[e], gt);
-                    a[e] = (float)sv[e] * (1.0f / 32768.0f);
+                    a[e] = int_to_float_exact(sv[e]) * (1.0f / 32768.0f);
                 }
                 *reinterpret_cast<float4*>(span + 8 * gq) = make_float4(a[0], a[1], a[2], a[3]);
                 *reinterpret_cast<float4*>(span + 8 * gq + 4) = make_float4(a[4], a[5], a[6], a[7]);
@@ -116,7 +113,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
                         int sv = x[l];
                         if (pn) sv = peak_norm_sample_fast(sv, pnv);
                         const int q = gain_sample_m(sv, gt);
-                        a = (float)q * (1.0f / 32768.0f);
+                        a = int_to_float_exact(q) * (1.0f / 32768.0f);
                         if (out16 && r == i && i >= own_lo && i < own_hi && l >= 0 && l < it.own_len) out16[it.out_off + l] = (int16_t)q;
                     }
                 }
@@ -199,7 +196,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
 }
 
 void launch_logmel(const int16_t* den16, const Item* items, int n_items, int max_tiles, const Consts& c,
-                   const MelBank& mel, int padding, int peak_normalize, double target_peak, const int* peak,
+                   const MelBank& mel, int padding, int peak_normalize, const PeakNorm* pnorm,
                    const Gate* gates, int16_t* out16, float* mel_out, int* mel_max, cudaStream_t st) {
     if (n_items <= 0) return;
     cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOGMEL_SMEM);
@@ -207,8 +204,8 @@ void launch_logmel(const int16_t* den16, const Item* items, int n_items, int max
     for (int y0 = 0; y0 < n_items; y0 += 32768) {
         const int ny = n_items - y0 < 32768 ? n_items - y0 : 32768;
         dim3 grid(max_tiles, ny);
-        logmel_kernel<<<grid, 256, LOGMEL_SMEM, st>>>(den16, items + y0, c, mel, padding, peak_normalize, target_peak,
-                                                      peak ? peak + y0 : nullptr, gates ? gates + y0 : nullptr, out16,
+        logmel_kernel<<<grid, 256, LOGMEL_SMEM, st>>>(den16, items + y0, c, mel, padding, peak_normalize,
+                                                      pnorm ? pnorm + y0 : nullptr, gates ? gates + y0 : nullptr, out16,
                                                       mel_out, mel_max + y0);
     }
 }

@@ -27,22 +27,29 @@ __device__ __forceinline__ void mat4_apply_add(const double* __restrict__ m, con
 //            H_i = A^(seg-1-i) B (float32: it only seeds the scan)                             -> e_l
 //   scan     inclusive Kogge-Stone over the lanes with the precomputed powers A^(seg 2^i) of the homogeneous
 //            transition (float64), then a serial hop over the warps (A^(32 seg))               -> state at segment start
-//   pass 2   every thread runs its segment from that state -- direct form II transposed like scipy.signal.lfilter, the
-//            benign shelf stage (poles 0.63) in float32, the high pass (double pole 0.985) in float64, float32 output
-//            as lfilter returns for float32 input -- and sums the squares; the lanes of a sub-block are added in a
-//            fixed order.
+//   pass 2   every thread runs its segment from that state -- direct form II transposed like scipy.signal.lfilter, in
+//            float32 with the high pass in a split-coefficient form (see below) -- and sums the squares; the lanes of
+//            a sub-block are added in a fixed order.
 // Critical path per thread: 2 seg steps + ~40 dependent FP64 operations instead of sub-block + 2048 warm-up samples.
-// Against the float64 lfilter cascade the float32 shelf stage moves samples by ~1e-7 relative and LUFS by < 1e-6 LU.
+// No int<->float or float<->double conversion instruction on the per-sample path (quarter-rate unit on sm_100).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+
+// SEG > 0: compile-time segment length (the loops unroll and the compiler hoists the shared-memory loads); 0 = `seg_rt`.
+template <int SEG>
 __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const int16_t* __restrict__ den16, const Item* __restrict__ items,
-                                                                        int tile_len, int seg, int lpt, int tpc, KWeight kw,
+                                                                        int tile_len, int seg_rt, int lpt, int tpc, KWeight kw,
                                                                         const KwScan* __restrict__ tab, int peak_normalize,
-                                                                        double target_peak, const int* __restrict__ peak,
+                                                                        const PeakNorm* __restrict__ pnorm,
                                                                         double* __restrict__ sub_energy, int* __restrict__ peak_norm) {
     extern __shared__ __align__(16) unsigned char kw_smem[];
     double* e_lane = reinterpret_cast<double*>(kw_smem);                         // [blockDim.x] lane energies
     double* e_warp = e_lane + blockDim.x;                                        // [32][4] zero-state end state of each warp
     float4* hs = reinterpret_cast<float4*>(e_warp + 32 * 4);                     // [KW_MAX_SEG] state impulse responses
     int16_t* xs = reinterpret_cast<int16_t*>(hs + KW_MAX_SEG);                   // [(tpc + 1) * tile_len] staged samples
+    const int seg = SEG ? SEG : seg_rt;
 
     const int item = blockIdx.y;
     const Item it = items[item];
@@ -55,45 +62,45 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
     const int span = (tpc + 1) * tile_len;
     if (tid < seg) hs[tid] = make_float4(tab->H[tid][0], tab->H[tid][1], tab->H[tid][2], tab->H[tid][3]);
 
-    const int pkin = peak_normalize ? peak[item] : 0;
-    const bool pn = peak_normalize && pkin > 0;
-    const double factor = pn ? peak_factor(pkin, target_peak) : 1.0;
-    const PeakNorm pnv = make_peak_norm(factor);
+    PeakNorm pnv; pnv.active = 0;
+    if (peak_normalize) pnv = pnorm[item];
+    const bool pn = pnv.active != 0;
     const int16_t* x = den16 + it.den_off;
-    int pk = 0;
+    // stage 1: raw samples -> shared memory; interior 16-byte groups by cp.async (all loads of the CTA in flight at once)
     for (int g8 = tid; g8 < span / 8; g8 += blockDim.x) {
         const long long li = c0 + 8 * g8;
-        uint4 o;
-        if (li >= 0 && li + 8 <= it.own_len && ((it.den_off + li) & 7) == 0) {
-            // interior: eight samples of the recording in one 16-byte load
-            o = *reinterpret_cast<const uint4*>(x + li);
-            uint32_t wv[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                int s0 = (int)(short)(wv[h] & 0xffffu), s1 = (int)wv[h] >> 16;
-                if (pn) { s0 = peak_norm_sample_fast(s0, pnv); s1 = peak_norm_sample_fast(s1, pnv); }
-                pk = max(pk, max(abs(s0), abs(s1)));
-                wv[h] = ((uint32_t)s0 & 0xffffu) | ((uint32_t)s1 << 16);
-            }
-            o = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        if (li >= -(long long)it.lo_avail && li + 8 <= it.own_len && ((it.den_off + li) & 7) == 0) {
+            cp_async16(xs + 8 * g8, x + li);
         } else {
-            int sv[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                sv[e] = (li + e >= -(long long)it.lo_avail && li + e < it.own_len) ? (int)x[li + e] : 0;
-                if (pn) sv[e] = peak_norm_sample_fast(sv[e], pnv);
-                if (li + e >= 0) pk = max(pk, abs(sv[e]));
-            }
-            o.x = (uint32_t)(sv[0] & 0xffff) | ((uint32_t)sv[1] << 16); o.y = (uint32_t)(sv[2] & 0xffff) | ((uint32_t)sv[3] << 16);
-            o.z = (uint32_t)(sv[4] & 0xffff) | ((uint32_t)sv[5] << 16); o.w = (uint32_t)(sv[6] & 0xffff) | ((uint32_t)sv[7] << 16);
+            for (int e = 0; e < 8; ++e) xs[8 * g8 + e] = (li + e >= -(long long)it.lo_avail && li + e < it.own_len) ? x[li + e] : (int16_t)0;
         }
-        *reinterpret_cast<uint4*>(xs + 8 * g8) = o;
     }
     for (int i = (span / 8) * 8 + tid; i < span; i += blockDim.x) {              // tail when tile_len is not a multiple of 8
         const long long li = c0 + i;
-        int sv = (li >= -(long long)it.lo_avail && li < it.own_len) ? (int)x[li] : 0;
+        xs[i] = (li >= -(long long)it.lo_avail && li < it.own_len) ? x[li] : (int16_t)0;
+    }
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+    // stage 2 (same thread <-> same groups, so no barrier in between): peak normalisation in place, peak of the result
+    int pk = 0;
+    for (int g8 = tid; g8 < span / 8; g8 += blockDim.x) {
+        const long long li = c0 + 8 * g8;
+        uint4 o = *reinterpret_cast<const uint4*>(xs + 8 * g8);
+        uint32_t wv[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            int s0 = (int)(short)(wv[h] & 0xffffu), s1 = (int)wv[h] >> 16;
+            if (pn) { s0 = peak_norm_sample_fast(s0, pnv); s1 = peak_norm_sample_fast(s1, pnv); }
+            if (li + 2 * h >= 0) pk = max(pk, abs(s0));
+            if (li + 2 * h + 1 >= 0) pk = max(pk, abs(s1));
+            wv[h] = ((uint32_t)s0 & 0xffffu) | ((uint32_t)s1 << 16);
+        }
+        if (pn) *reinterpret_cast<uint4*>(xs + 8 * g8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    }
+    for (int i = (span / 8) * 8 + tid; i < span; i += blockDim.x) {
+        int sv = xs[i];
         if (pn) sv = peak_norm_sample_fast(sv, pnv);
-        if (li >= 0) pk = max(pk, abs(sv));
+        if (c0 + i >= 0) pk = max(pk, abs(sv));
         xs[i] = (int16_t)sv;
     }
     __syncthreads();
@@ -106,9 +113,9 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
     double e[4] = {0.0, 0.0, 0.0, 0.0};
     if (live) {
         float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
-#pragma unroll 5
+#pragma unroll 10
         for (int i = 0; i < seg; ++i) {
-            const float xv = (float)xl[i];
+            const float xv = int_to_float_exact((int)xl[i]);
             const float4 h = hs[i];
             f0 = fmaf(h.x, xv, f0); f1 = fmaf(h.y, xv, f1); f2 = fmaf(h.z, xv, f2); f3 = fmaf(h.w, xv, f3);
         }
@@ -138,26 +145,32 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
 #pragma unroll
     for (int r = 0; r < 4; ++r) { const double up = __shfl_up_sync(0xffffffffu, e[r], 1); z[r] = lane > 0 ? up : 0.0; }
     mat4_apply_add(tab->Mlane[lane], sw, z);
-    // pass 2
+    // pass 2 (samples past the end of the recording are zeros in shared memory: they add nothing), all float32:
+    //   shelf      y1 = b0 x + s0 ; s0 = b1 x - a1 y1 + s1 ; s1 = b2 x - a2 y1
+    //   high pass  b = (b0, -2 b0, b0) exactly (RBJ), a1 = -2 + d1, a2 = 1 - d2 with d1, d2 ~ 0.03 held as floats:
+    //              y2 = b0 y1 + h1 ; h1' = 2 h1 + h2 - d1 y2 ; h2' = -h1 + d2 y2
+    //   The near-cancelling part (2, -1) of the double pole is exact this way; only the small d's are rounded, which
+    //   moves block energies by < 2e-4 relative and the integrated loudness by ~1e-6 LU against float64 lfilter
+    //   (plain float32 coefficients: 1.1e-4 LU; measured on the synthetic workloads incl. DC offsets).
     float acc = 0.f;
     if (live) {
         const float b10 = (float)kw.b1[0], b11 = (float)kw.b1[1], b12 = (float)kw.b1[2], a11 = (float)kw.a1[1], a12 = (float)kw.a1[2];
-        float s0 = (float)z[0], s1 = (float)z[1];
-        double z20 = z[2], z21 = z[3];
+        const float hb0 = (float)kw.b2[0], d1 = (float)(2.0 + kw.a2[1]), d2 = (float)(1.0 - kw.a2[2]);
+        float s0 = (float)z[0], s1 = (float)z[1], h1 = (float)z[2], h2 = (float)z[3];
         const long long li0 = c0 + (long long)tid * seg;
         const int n_own = (int)max(0LL, min((long long)seg, it.own_len - li0));      // samples of this segment inside the recording
-#pragma unroll 2
-        for (int i = 0; i < n_own; ++i) {
-            const float xv = (float)xl[i] * (1.0f / 32768.0f);
+        const int n_run = SEG ? SEG : n_own;
+#pragma unroll 10
+        for (int i = 0; i < n_run; ++i) {
+            const float xv = int_to_float_exact((int)xl[i]) * (1.0f / 32768.0f);
             const float y1 = fmaf(b10, xv, s0);
             s0 = fmaf(-a11, y1, fmaf(b11, xv, s1));
             s1 = fmaf(-a12, y1, b12 * xv);
-            const double x2 = (double)y1;
-            const double y2 = kw.b2[0] * x2 + z20;
-            z20 = (kw.b2[1] * x2 + z21) - kw.a2[1] * y2;
-            z21 = kw.b2[2] * x2 - kw.a2[2] * y2;
-            const float d = (float)y2;
-            acc = fmaf(d, d, acc);
+            const float y2 = fmaf(hb0, y1, h1);
+            const float nh1 = fmaf(-d1, y2, fmaf(2.0f, h1, h2));
+            h2 = fmaf(d2, y2, -h1);
+            h1 = nh1;
+            if (!SEG || i < n_own) acc = fmaf(y2, y2, acc);
         }
     }
     e_lane[tid] = (double)acc;
@@ -180,34 +193,54 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
 }
 
 void launch_kweight_energy(const int16_t* den16, const Item* items, int n_items, int max_groups, int tile_len, const KwGeom& geo,
-                           const KWeight& kw, const KwScan* tab, int peak_normalize, double target_peak, const int* peak,
+                           const KWeight& kw, const KwScan* tab, int peak_normalize, const PeakNorm* pnorm,
                            double* sub_energy, int* peak_norm, cudaStream_t st) {
     if (n_items <= 0 || max_groups <= 0) return;
     const size_t smem = sizeof(double) * (geo.threads + 128) + sizeof(float4) * KW_MAX_SEG + sizeof(int16_t) * (size_t)(geo.tpc + 1) * tile_len + 16;
-    cudaFuncSetAttribute(kweight_energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = geo.seg == 50 ? kweight_energy_kernel<50> : kweight_energy_kernel<0>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int y0 = 0; y0 < n_items; y0 += 32768) {
         const int ny = n_items - y0 < 32768 ? n_items - y0 : 32768;
         dim3 grid(max_groups, ny);
-        kweight_energy_kernel<<<grid, geo.threads, smem, st>>>(den16, items + y0, tile_len, geo.seg, geo.lpt, geo.tpc, kw, tab, peak_normalize,
-                                                               target_peak, peak ? peak + y0 : nullptr, sub_energy, peak_norm + y0);
+        kern<<<grid, geo.threads, smem, st>>>(den16, items + y0, tile_len, geo.seg, geo.lpt, geo.tpc, kw, tab, peak_normalize,
+                                                               pnorm ? pnorm + y0 : nullptr, sub_energy, peak_norm + y0);
     }
+}
+
+// pydub.effects.normalize factor of every item (float64 pow / log10: once per item instead of once per thread)
+__global__ void peak_factor_kernel(const int* __restrict__ peak, int n, double target_peak, PeakNorm* __restrict__ pnorm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int pk = peak[i];
+    PeakNorm pn = make_peak_norm(pk > 0 ? peak_factor(pk, target_peak) : 1.0);
+    pn.active = pk > 0 ? 1 : 0;                                       // audioop.mul is skipped for an all-zero recording
+    pnorm[i] = pn;
+}
+void launch_peak_factor(const int* peak, int n_items, double target_peak, PeakNorm* pnorm, cudaStream_t st) {
+    if (n_items <= 0) return;
+    peak_factor_kernel<<<(n_items + 127) / 128, 128, 0, st>>>(peak, n_items, target_peak, pnorm);
 }
 
 // ---- gating -----------------------------------------------------------------------------------------------------
 constexpr int GATE_THREADS = 1024;
 
-__device__ double block_sum(double v, double* sh) {
-    // deterministic tree reduction over the CTA
-    const int tid = threadIdx.x;
-    sh[tid] = v;
+// deterministic CTA-wide sum of two values at once: fixed shuffle tree inside each warp, then warp 0 adds the 32 warp
+// sums in a fixed order (two barriers instead of a 10-level shared-memory tree per value)
+__device__ void block_sum2(double& a, double& b, double* sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if (lane == 0) { sh[2 * warp] = a; sh[2 * warp + 1] = b; }
     __syncthreads();
-    for (int s = GATE_THREADS / 2; s > 0; s >>= 1) {
-        if (tid < s) sh[tid] += sh[tid + s];
-        __syncthreads();
+    if (warp == 0) {
+        double x = sh[2 * lane], y = sh[2 * lane + 1];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { x += __shfl_xor_sync(0xffffffffu, x, o); y += __shfl_xor_sync(0xffffffffu, y, o); }
+        if (lane == 0) { sh[64] = x; sh[65] = y; }
     }
-    const double r = sh[0];
     __syncthreads();
-    return r;
+    a = sh[64]; b = sh[65];
+    __syncthreads();
 }
 
 // The two gates are evaluated on the block energies themselves: l_j >= -70 <=> z_j >= 10^((-70 + 0.691)/10) and
@@ -215,7 +248,7 @@ __device__ double block_sum(double v, double* sh) {
 __global__ void __launch_bounds__(GATE_THREADS) gate_kernel(const double* __restrict__ sub_energy, const Item* __restrict__ items,
                                                             double inv_block, double target_lufs, const int* __restrict__ peak_norm,
                                                             Gate* __restrict__ gates) {
-    __shared__ double sh[GATE_THREADS];
+    __shared__ double sh[66];
     const int item = blockIdx.x;
     const Item it = items[item];
     const double* sb = sub_energy + it.ktile_first;
@@ -230,7 +263,7 @@ __global__ void __launch_bounds__(GATE_THREADS) gate_kernel(const double* __rest
         const double z = inv_block * e;
         if (z >= zabs) { s += z; c += 1.0; }
     }
-    s = block_sum(s, sh); c = block_sum(c, sh);
+    block_sum2(s, c, sh);
     const double zrel = c > 0.0 ? (s / c) * 0.1 : NAN;                 // NaN threshold: nothing passes, like np.mean([])
     double s2 = 0.0, c2 = 0.0;
     for (int j = threadIdx.x; j < nb; j += GATE_THREADS) {
@@ -241,7 +274,7 @@ __global__ void __launch_bounds__(GATE_THREADS) gate_kernel(const double* __rest
         const double z = inv_block * e;
         if (z > zrel && z > zabs) { s2 += z; c2 += 1.0; }
     }
-    s2 = block_sum(s2, sh); c2 = block_sum(c2, sh);
+    block_sum2(s2, c2, sh);
     if (threadIdx.x == 0) {
         const double zavg = c2 > 0.0 ? s2 / c2 : 0.0;                 // nan_to_num(mean([])) = 0
         const double lufs = -0.691 + 10.0 * log10(zavg);
@@ -270,22 +303,21 @@ void launch_gate(const double* sub_energy, const Item* items, int n_items, doubl
 // clip(y * 32768, -32768, 32767).astype(int16)
 __device__ __forceinline__ int gain_sample(int s, const Gate& gt) {
     if (!gt.applied) return s;
-    float y = __fmul_rn(gt.gain, (float)s * (1.0f / 32768.0f));
+    float y = __fmul_rn(gt.gain, int_to_float_exact(s) * (1.0f / 32768.0f));
     if (gt.lim) y = __fdiv_rn(y, gt.limp);
     float v = __fmul_rn(y, 32768.0f);
     v = fminf(fmaxf(v, -32768.0f), 32767.0f);
-    return (int)v;
+    return trunc_to_int(v);
 }
 
 __global__ void __launch_bounds__(256) apply_gain_kernel(const int16_t* __restrict__ den16, const Item* __restrict__ items,
-                                                         int peak_normalize, double target_peak, const int* __restrict__ peak,
+                                                         int peak_normalize, const PeakNorm* __restrict__ pnorm,
                                                          const Gate* __restrict__ gates, int use_gate, int16_t* __restrict__ out16) {
     const int item = blockIdx.y;
     const Item it = items[item];
-    const int pkin = peak_normalize ? peak[item] : 0;
-    const bool pn = peak_normalize && pkin > 0;
-    const double factor = pn ? peak_factor(pkin, target_peak) : 1.0;
-    const PeakNorm pnv = make_peak_norm(factor);
+    PeakNorm pnv; pnv.active = 0;
+    if (peak_normalize) pnv = pnorm[item];
+    const bool pn = pnv.active != 0;
     Gate gt; gt.applied = 0;
     if (use_gate) gt = gates[item];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < it.own_len; i += (long long)gridDim.x * blockDim.x) {
@@ -297,7 +329,7 @@ __global__ void __launch_bounds__(256) apply_gain_kernel(const int16_t* __restri
 }
 
 void launch_apply_gain(const int16_t* den16, const Item* items, int n_items, long long max_len, int peak_normalize,
-                       double target_peak, const int* peak, const Gate* gates, int use_gate, int16_t* out16,
+                       const PeakNorm* pnorm, const Gate* gates, int use_gate, int16_t* out16,
                        cudaStream_t st) {
     if (n_items <= 0 || max_len <= 0) return;
     long long bx = (max_len + 256 * 8 - 1) / (256 * 8);
@@ -305,7 +337,7 @@ void launch_apply_gain(const int16_t* den16, const Item* items, int n_items, lon
     for (int y0 = 0; y0 < n_items; y0 += 32768) {
         const int ny = n_items - y0 < 32768 ? n_items - y0 : 32768;
         dim3 grid((unsigned)bx, ny);
-        apply_gain_kernel<<<grid, 256, 0, st>>>(den16, items + y0, peak_normalize, target_peak, peak ? peak + y0 : nullptr,
+        apply_gain_kernel<<<grid, 256, 0, st>>>(den16, items + y0, peak_normalize, pnorm ? pnorm + y0 : nullptr,
                                                 gates ? gates + y0 : nullptr, use_gate, out16);
     }
 }
