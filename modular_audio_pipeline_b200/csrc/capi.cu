@@ -164,7 +164,7 @@ struct maf_plan {
     NsParams ns{}; void* d_ns = nullptr;
     KwGeom kgeo{}; KwScan kscan{}; void* d_kscan = nullptr; int max_kgroups = 0;
     long long total_tiles = 0;
-    WsBuf S, M, P, Q, Yend, Zend, bits, rowflag, T2, T2hi, nmax, partial, E, ZC, clips, seg, den16, peak, pnorm, peak_norm, mel_max, sub, gates;
+    WsBuf S, M, P, Q, Yend, Zend, bits, rowflag, T2, T2hi, nmax, partial, E, ZC, clips, seg, den16, peak, pnorm, peak_norm, mel_max, mel_tmin, sub, gates;
     long long ws_bytes = 0;
     long long launches = 0;
     // optional per-stage CUDA-event timing (maf_plan_profile): ring of event sets, one per maf_process call
@@ -420,6 +420,7 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
     pl->pnorm = carve(cur, (long long)n_items * sizeof(PeakNorm));
     pl->peak_norm = carve(cur, (long long)n_items * 4);
     pl->mel_max = carve(cur, (long long)n_items * 4);
+    pl->mel_tmin = carve(cur, (long long)n_items * std::max(1, pl->max_mel_tiles) * 4);
     pl->sub = carve(cur, std::max(1, pl->total_ktiles) * 8LL);
     pl->gates = carve(cur, (long long)n_items * sizeof(Gate));
     pl->ws_bytes = align_up(cur, 256);
@@ -627,12 +628,16 @@ static int run_logmel(maf_plan* pl, const int16_t* src, const Item* items, int p
                       float* mel, bool finalize, cudaStream_t st) {
     const int n = pl->n_items;
     fill_int_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws_ptr<int>(ws, pl->mel_max), n, (int)0x80000001);
+    {
+        const int nt = n * std::max(1, pl->max_mel_tiles);
+        fill_int_kernel<<<(nt + 255) / 256, 256, 0, st>>>(ws_ptr<int>(ws, pl->mel_tmin), nt, (int)0x7fffffff);
+    }
     launch_logmel(src, items, n, pl->max_mel_tiles, pl->ctx->c, pick_mel(pl), pl->p.mel_padding, peak_normalize,
-                  ws_ptr<PeakNorm>(ws, pl->pnorm), gates, out16, mel, ws_ptr<int>(ws, pl->mel_max), st);
-    pl->launches += 2;
+                  ws_ptr<PeakNorm>(ws, pl->pnorm), gates, out16, mel, ws_ptr<int>(ws, pl->mel_max), ws_ptr<int>(ws, pl->mel_tmin), st);
+    pl->launches += 3;
     mark(pl, ST_LOGMEL, st);
     if (finalize) {
-        launch_mel_finalize(mel, items, n, pl->p.n_mels, pl->max_mel_frames, ws_ptr<int>(ws, pl->mel_max), st);
+        launch_mel_finalize(mel, items, n, pl->p.n_mels, std::max(1, pl->max_mel_tiles), ws_ptr<int>(ws, pl->mel_max), ws_ptr<int>(ws, pl->mel_tmin), st);
         pl->launches += 1;
     }
     mark(pl, ST_MELFIN, st);
@@ -819,7 +824,8 @@ extern "C" int maf_sharded_logmel(maf_plan* pl, void* ws, const void* gate, int1
 extern "C" int maf_mel_finalize(maf_plan* pl, void* ws, float* mel, void* stream) {
     if (!pl || !ws || !mel) return fail(MAF_ERR_INVALID, "maf_mel_finalize: NULL argument");
     CU(cudaSetDevice(pl->ctx->device));
-    launch_mel_finalize(mel, pl->d_items, pl->n_items, pl->p.n_mels, pl->max_mel_frames, ws_ptr<int>(ws, pl->mel_max), (cudaStream_t)stream);
+    launch_mel_finalize(mel, pl->d_items, pl->n_items, pl->p.n_mels, std::max(1, pl->max_mel_tiles), ws_ptr<int>(ws, pl->mel_max), ws_ptr<int>(ws, pl->mel_tmin),
+                        (cudaStream_t)stream);
     pl->launches += 1;
     CU(cudaGetLastError());
     return MAF_OK;

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
                                                      MelBank mel, int padding, int peak_normalize,
                                                      const PeakNorm* __restrict__ pnorm, const Gate* __restrict__ gates,
                                                      int16_t* __restrict__ out16, float* __restrict__ mel_out,
-                                                     int* __restrict__ mel_max) {
+                                                     int* __restrict__ mel_max, int* __restrict__ tile_min) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* span = reinterpret_cast<float*>(smem_raw);
     c32* zb = reinterpret_cast<c32*>(span + MEL_SPAN);
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
         const int lane = tid & 31, warp = tid >> 5;
         const int lf = lane;
         const bool valid = lf0 + lf < it.mel_frames;
-        float bmax = -INFINITY;
+        float bmax = -INFINITY, bmin = INFINITY;
         float* orow = mel_out + it.mel_off + lf0 + lf;
         for (int q = warp; q < mel.n_mels / 4; q += 8) {
             const int cnt = m_qcount[q];
@@ -182,8 +182,12 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
             const float l2 = __log2f(fmaxf(a2, 1e-10f)) * 0.30102999566398120f, l3 = __log2f(fmaxf(a3, 1e-10f)) * 0.30102999566398120f;
             if (valid) {
                 float* o = orow + (long long)(4 * q) * it.mel_frames;
-                o[0] = l0; o[it.mel_frames] = l1; o[2LL * it.mel_frames] = l2; o[3LL * it.mel_frames] = l3;
+                // written already scaled, (L + 4) / 4; the max - 8 clamp is applied afterwards only to tiles that need it
+                // (division by 4 is exact in binary floating point: multiply by 0.25)
+                o[0] = __fmul_rn(__fadd_rn(l0, 4.0f), 0.25f); o[it.mel_frames] = __fmul_rn(__fadd_rn(l1, 4.0f), 0.25f);
+                o[2LL * it.mel_frames] = __fmul_rn(__fadd_rn(l2, 4.0f), 0.25f); o[3LL * it.mel_frames] = __fmul_rn(__fadd_rn(l3, 4.0f), 0.25f);
                 bmax = fmaxf(fmaxf(bmax, fmaxf(l0, l1)), fmaxf(l2, l3));
+                bmin = fminf(fminf(bmin, fminf(l0, l1)), fminf(l2, l3));
             }
         }
         bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, 16));
@@ -191,13 +195,21 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
         bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, 4));
         bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, 2));
         bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, 1));
-        if (lane == 0 && bmax > -INFINITY) atomicMax(&mel_max[item], float_to_ordered(bmax));
+        bmin = fminf(bmin, __shfl_xor_sync(0xffffffffu, bmin, 16));
+        bmin = fminf(bmin, __shfl_xor_sync(0xffffffffu, bmin, 8));
+        bmin = fminf(bmin, __shfl_xor_sync(0xffffffffu, bmin, 4));
+        bmin = fminf(bmin, __shfl_xor_sync(0xffffffffu, bmin, 2));
+        bmin = fminf(bmin, __shfl_xor_sync(0xffffffffu, bmin, 1));
+        if (lane == 0 && bmax > -INFINITY) {
+            atomicMax(&mel_max[item], float_to_ordered(bmax));
+            atomicMin(&tile_min[(long long)item * gridDim.x + blockIdx.x], float_to_ordered(bmin));
+        }
     }
 }
 
 void launch_logmel(const int16_t* den16, const Item* items, int n_items, int max_tiles, const Consts& c,
                    const MelBank& mel, int padding, int peak_normalize, const PeakNorm* pnorm,
-                   const Gate* gates, int16_t* out16, float* mel_out, int* mel_max, cudaStream_t st) {
+                   const Gate* gates, int16_t* out16, float* mel_out, int* mel_max, int* tile_min, cudaStream_t st) {
     if (n_items <= 0) return;
     cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOGMEL_SMEM);
     if (max_tiles < 1) max_tiles = 1;
@@ -206,33 +218,39 @@ void launch_logmel(const int16_t* den16, const Item* items, int n_items, int max
         dim3 grid(max_tiles, ny);
         logmel_kernel<<<grid, 256, LOGMEL_SMEM, st>>>(den16, items + y0, c, mel, padding, peak_normalize,
                                                       pnorm ? pnorm + y0 : nullptr, gates ? gates + y0 : nullptr, out16,
-                                                      mel_out, mel_max + y0);
+                                                      mel_out, mel_max + y0, tile_min + (long long)y0 * max_tiles);
     }
 }
 
+// whisper.audio.log_mel_spectrogram: log_spec = maximum(log_spec, log_spec.max() - 8.0); (log_spec + 4.0) / 4.0.
+// logmel_kernel has already stored (L + 4) / 4 and the minimum L of every 32-frame tile; division by 4 and adding 4 are
+// monotonic, so clamping the stored value at ((max - 8) + 4) / 4 is the same float32 arithmetic as the reference, and only
+// tiles whose minimum lies below max - 8 (silence, the zero padding) have to be touched again.
 __global__ void __launch_bounds__(256) mel_finalize_kernel(float* __restrict__ mel_out, const Item* __restrict__ items, int n_mels,
-                                                           const int* __restrict__ mel_max) {
+                                                           const int* __restrict__ mel_max, const int* __restrict__ tile_min) {
     const int item = blockIdx.y;
     const Item it = items[item];
-    const long long total = (long long)n_mels * it.mel_frames;
+    const int lf0 = blockIdx.x * MEL_TILE;
+    if (lf0 >= it.mel_frames) return;
     const float floor_v = ordered_to_float(mel_max[item]) - 8.0f;
-    float* p = mel_out + it.mel_off;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const float v = fmaxf(p[i], floor_v);
-        p[i] = __fdiv_rn(__fadd_rn(v, 4.0f), 4.0f);
+    if (ordered_to_float(tile_min[(long long)item * gridDim.x + blockIdx.x]) >= floor_v) return;
+    const float floor_s = __fmul_rn(__fadd_rn(floor_v, 4.0f), 0.25f);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lf0 + lane >= it.mel_frames) return;
+    float* p = mel_out + it.mel_off + lf0 + lane;
+    for (int m = warp; m < n_mels; m += 8) {
+        float* q = p + (long long)m * it.mel_frames;
+        *q = fmaxf(*q, floor_s);
     }
 }
 
-void launch_mel_finalize(float* mel_out, const Item* items, int n_items, int n_mels, int max_frames,
-                         const int* mel_max, cudaStream_t st) {
-    if (n_items <= 0 || max_frames <= 0) return;
-    long long bx = ((long long)n_mels * max_frames + 256 * 4 - 1) / (256 * 4);
-    if (bx > 8192) bx = 8192;
-    if (bx < 1) bx = 1;
+void launch_mel_finalize(float* mel_out, const Item* items, int n_items, int n_mels, int max_tiles,
+                         const int* mel_max, const int* tile_min, cudaStream_t st) {
+    if (n_items <= 0 || max_tiles <= 0) return;
     for (int y0 = 0; y0 < n_items; y0 += 32768) {
         const int ny = n_items - y0 < 32768 ? n_items - y0 : 32768;
-        dim3 grid((unsigned)bx, ny);
-        mel_finalize_kernel<<<grid, 256, 0, st>>>(mel_out, items + y0, n_mels, mel_max + y0);
+        dim3 grid(max_tiles, ny);
+        mel_finalize_kernel<<<grid, 256, 0, st>>>(mel_out, items + y0, n_mels, mel_max + y0, tile_min + (long long)y0 * max_tiles);
     }
 }
 
