@@ -147,6 +147,65 @@ MAF_HD void irfft_merge_pair(c32 xk, c32 xnk, c32 tw1024k, c32& zck, c32& zcnk) 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// 1024-point complex FFT by ONE WARP as 32 x 32: every lane runs two 32-point FFTs in registers with a single
+// shared-memory transpose in between (one store + one load of the data per transform instead of the three round
+// trips of the 8 x 8 x 8 scheme).  The STFT kernels feed it TWO real frames at once (frame A in the real part,
+// frame B in the imaginary part); the split X_A[k] = (Z[k] + conj Z[1024-k]) / 2, X_B[k] = (Z[k] - conj Z[1024-k]) / 2i
+// pairs lane l with lane 32 - l and is done with warp shuffles.
+//   in : v[j] = x[lane + 32 j]        out: v[j] = X[32 j + lane]
+// Scratch: FFT1024_SMEM c32 per warp, pitch 33 (both the row-wise stores and the column-wise 64-bit loads are
+// conflict-free).  Twiddles: tww[j * 32 + lane] = e^{-2 pi i lane j / 1024}.
+// ------------------------------------------------------------------------------------------------------------
+// e^{-2 pi i e / 32}; after unrolling every index is a compile-time constant, so these fold into immediates
+MAF_HD c32 w32(int e) {
+    const float re[32] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654757f, 0.55557023301960229f, 0.38268343236508984f, 0.19509032201612833f,
+                          0.0f, -0.19509032201612819f, -0.38268343236508973f, -0.55557023301960196f, -0.70710678118654746f, -0.83146961230254535f, -0.92387953251128674f, -0.98078528040323043f,
+                          -1.0f, -0.98078528040323043f, -0.92387953251128685f, -0.83146961230254546f, -0.70710678118654768f, -0.55557023301960218f, -0.38268343236509034f, -0.19509032201612866f,
+                          0.0f, 0.1950903220161283f, 0.38268343236509f, 0.55557023301960184f, 0.70710678118654735f, 0.83146961230254524f, 0.92387953251128652f, 0.98078528040323032f};
+    const float im[32] = {-0.0f, -0.19509032201612825f, -0.38268343236508978f, -0.55557023301960218f, -0.70710678118654746f, -0.83146961230254524f, -0.92387953251128674f, -0.98078528040323043f,
+                          -1.0f, -0.98078528040323043f, -0.92387953251128674f, -0.83146961230254546f, -0.70710678118654757f, -0.55557023301960218f, -0.38268343236508989f, -0.19509032201612861f,
+                          -0.0f, 0.19509032201612836f, 0.38268343236508967f, 0.55557023301960196f, 0.70710678118654746f, 0.83146961230254535f, 0.92387953251128652f, 0.98078528040323032f,
+                          1.0f, 0.98078528040323043f, 0.92387953251128663f, 0.83146961230254546f, 0.70710678118654768f, 0.55557023301960229f, 0.38268343236509039f, 0.19509032201612872f};
+    return mk(re[e], im[e]);
+}
+
+// 32-point forward DFT in registers (4 x fft8, twiddle, 8 x fft4), natural order in and out.
+// n = 4 n1 + n2 (n1 < 8, n2 < 4), k = k1 + 8 k2:  X[k1 + 8 k2] = sum_n2 W32^{n2 k1} W4^{n2 k2} sum_n1 x[4 n1 + n2] W8^{n1 k1}
+MAF_HD void fft32(c32 (&v)[32]) {
+    c32 a[4][8];
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) {
+        c32 t[8];
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) t[n1] = v[4 * n1 + n2];
+        fft8(t);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; ++k1) a[n2][k1] = (n2 == 0 || k1 == 0) ? t[k1] : (n2 * k1 == 8 ? mul_mi(t[k1]) : cmul(t[k1], w32(n2 * k1)));
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < 8; ++k1) {
+        c32 b0 = a[0][k1], b1 = a[1][k1], b2 = a[2][k1], b3 = a[3][k1];
+        fft4(b0, b1, b2, b3);
+        v[k1] = b0; v[k1 + 8] = b1; v[k1 + 16] = b2; v[k1 + 24] = b3;
+    }
+}
+
+constexpr int FFT1024_PITCH = 33;
+constexpr int FFT1024_SMEM = 32 * FFT1024_PITCH;
+
+MAF_HD void fft1024w_pass1(c32 (&v)[32], c32* sm, const c32* tww, int lane) {
+    fft32(v);                                                         // over n2 (registers) -> k2
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sm[j * FFT1024_PITCH + lane] = (j == 0) ? v[0] : cmul(v[j], tww[j * 32 + lane]);
+}
+// (warp barrier)
+MAF_HD void fft1024w_pass2(c32 (&v)[32], const c32* sm, int lane) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = sm[lane * FFT1024_PITCH + j];  // lane = k2, j = n1
+    fft32(v);                                                         // over n1 -> k1: v[k1] = X[32 k1 + k2]
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // 200-point complex FFT as 8 x 25.  n = j + 25 m (j < 25, m < 8), k = p + 8 q (p < 8, q < 25):
 //   X[p + 8q] = sum_j W25^{jq} [ W200^{jp} sum_m x[j + 25m] W8^{mp} ]
 // step A: work item (j): 8-point FFT over m, twiddle W200^{jp}, store sm[p * 25 + j]        (25 items / transform)

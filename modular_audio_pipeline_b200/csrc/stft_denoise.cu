@@ -13,6 +13,7 @@
 // The stationary gate "dB > thresh" is evaluated without a logarithm: 20 log10(|X| + eps) > t  <=>
 // |X|^2 > (10^(t/20) - eps)^2 =: T2, and noisereduce's top_db=80 row clamp max(D, rowmax - 80) > t adds
 // "or rowmax^2 > (10^((t+80)/20) - eps)^2 =: T2hi", recorded per (chunk, bin) in `rowflag`.
+#include <algorithm>
 #include "maf_common.cuh"
 
 namespace maf {
@@ -33,188 +34,213 @@ __device__ __forceinline__ void group_fft512(c32 (&v)[8], c32* sm, const c32* tw
 }
 
 // ============================================================================================================
-// K1  forward STFT
+// K1  forward STFT.  A CTA stages the contiguous int16 span of a tile of STFT_TILE frames once (75 % overlap); every warp
+// transforms PAIRS of consecutive frames with the warp-level 1024-point complex FFT of fft_core.h (frame A in the real
+// part, frame B in the imaginary part), separates them with one shuffle exchange between lanes l and 32 - l, and stores
+// two 4 KB rows with 256-byte coalesced stores.  Lane l ends up with bins 32 k1 + l (k1 = 0..15) of both frames, lane 0
+// additionally with bin 512.
+//   stationary    : `|X|^2 > T2` bits straight from __ballot_sync (bit = lane), row flags for the top_db clamp
+//   non-stationary: per (tile, bin) the two weighted sums of |X| from which the scan kernel rebuilds the forward /
+//                   backward one-pole states at every tile boundary (see ns_scan_kernel):
+//     P = sum_s b a^(n-1-s) |X_s|                            zero-state forward response at the end of the tile
+//     Q = sum_s b^2 a^s (1 - a^(2(n-s))) / (1 - a^2) |X_s|   zero-state backward response (of the zero-state forward
+//                                                            one) at the start of the tile;  n = frames in the tile
 // ============================================================================================================
 __device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-constexpr int STFT_SPAN = (STFT_TILE + 3) * HOP;
+constexpr int STFT_WARPS = 8;
+constexpr int STFT_SPAN = (STFT_TILE + 3) * HOP;                          // samples covered by a tile's frames
+constexpr size_t STFT_SMEM = sizeof(c32) * (STFT_WARPS * FFT1024_SMEM + 1024) + 2 * sizeof(int16_t) * STFT_SPAN;
 
-// Non-stationary mode additionally emits, per (STFT_TILE-frame tile, bin), the two weighted sums of |X| from which the scan
-// kernel rebuilds the forward / backward one-pole states at every tile boundary (see ns_scan_kernel):
-//   P = sum_s b a^(n-1-s) |X_s|                      zero-state forward response at the end of the tile
-//   Q = sum_s b^2 a^s (1 - a^(2(n-s))) / (1 - a^2) |X_s|   zero-state backward response (of the zero-state forward one)
-//                                                    at the start of the tile;  n = frames in the tile, s = 0..n-1
-template <bool STATIONARY>
-__global__ void __launch_bounds__(256, 4) stft1024_kernel(const int16_t* __restrict__ pcm, const Item* __restrict__ items,
-                                                       const Chunk* __restrict__ chunks, Consts cs,
-                                                       const float* __restrict__ T2, const float* __restrict__ T2hi,
-                                                       c32* __restrict__ S, uint32_t* __restrict__ bits,
-                                                       uint8_t* __restrict__ rowflag, const NsParams* __restrict__ nsp,
-                                                       float* __restrict__ P, float* __restrict__ Q) {
-    constexpr int SPAN = STFT_SPAN;                   // samples covered by the tile's frames
-    extern __shared__ __align__(16) int16_t span[];   // [SPAN] (dynamic: static + dynamic exceeds the 48 KB default limit)
-    __shared__ float win[NFFT];
-    __shared__ c32 tw1[FFT512_TW1];
-    __shared__ c32 tw2[FFT512_TW2];
-    __shared__ c32 tw1024[257];
-    __shared__ __align__(16) c32 fsm[4][FFT512_SMEM];
-    __shared__ __align__(4) uint8_t flags[STATIONARY ? 4 : 1][528];
-    __shared__ float wpq[2][STATIONARY ? 1 : STFT_TILE];
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
 
-    const Chunk ch = chunks[blockIdx.y];
-    const int f0 = blockIdx.x * STFT_TILE;
-    if (f0 >= ch.n_frames) return;
-    const Item it = items[ch.item];
-    const int tid = threadIdx.x;
-    if (!STATIONARY && tid < STFT_TILE) {
-        const int n = min(STFT_TILE, ch.n_frames - f0);
-        float wp = 0.f, wq = 0.f;
-        if (tid < n) {
-            wp = (float)(nsp->b * nsp->apow[n - 1 - tid]);
-            wq = (float)(nsp->b * nsp->b * nsp->apow[tid] * (1.0 - nsp->apow[2 * (n - tid)]) * nsp->inv_1ma2);
-        }
-        wpq[0][tid] = wp; wpq[1][tid] = wq;
-    }
-
-    for (int i = tid; i < NFFT; i += 256) win[i] = cs.win1024[i];
-    for (int i = tid; i < FFT512_TW1; i += 256) tw1[i] = cs.tw1[i];
-    if (tid < FFT512_TW2) tw2[tid] = cs.tw2[tid];
-    for (int i = tid; i < 257; i += 256) tw1024[i] = cs.tw1024[i];
-
-    // stage the contiguous sample span once (frames overlap 75 %); zero outside the padded chunk and the recording
-    {
-        const long long j0 = (long long)f0 * HOP - NFFT / 2;          // padded-chunk coordinate of span[0]
-        const long long li0 = ch.s_local - PADS + j0;                 // local buffer index of span[0]
-        const int16_t* base = pcm + it.pcm_off;
-        for (int g = tid; g < SPAN / 8; g += 256) {
-            const long long j = j0 + 8 * g, li = li0 + 8 * g;
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (j >= 0 && j + 8 <= ch.L && li >= 0 && li + 8 <= it.buf_len && ((it.pcm_off + li) & 7) == 0) {
-                val = *reinterpret_cast<const uint4*>(base + li);
-            } else {
-                int16_t tmp[8];
+// Stage the contiguous int16 span of tile (chunk c, frames f0 ..) into `span`: 16-byte cp.async where the group lies
+// inside the padded chunk and the recording (asynchronous: no register staging, no stall), plain stores of the zero-
+// filled samples at the edges.
+__device__ __forceinline__ void stft_stage_span(int16_t* span, const int16_t* __restrict__ pcm, const Item& it, const Chunk& ch, int f0, int tid) {
+    const long long j0 = (long long)f0 * HOP - NFFT / 2;              // padded-chunk coordinate of span[0]
+    const long long li0 = ch.s_local - PADS + j0;                     // local buffer index of span[0]
+    const int16_t* base = pcm + it.pcm_off;
+    for (int g = tid; g < STFT_SPAN / 8; g += 32 * STFT_WARPS) {
+        const long long j = j0 + 8 * g, li = li0 + 8 * g;
+        if (j >= 0 && j + 8 <= ch.L && li >= 0 && li + 8 <= it.buf_len && ((it.pcm_off + li) & 7) == 0) {
+            cp_async16(&span[8 * g], base + li);
+        } else {
+            int16_t tmp[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const long long jj = j + e, ll = li + e;
-                    tmp[e] = (jj >= 0 && jj < ch.L && ll >= 0 && ll < it.buf_len) ? base[ll] : (int16_t)0;
-                }
-                val = *reinterpret_cast<uint4*>(tmp);
+            for (int e = 0; e < 8; ++e) {
+                const long long jj = j + e, ll = li + e;
+                tmp[e] = (jj >= 0 && jj < ch.L && ll >= 0 && ll < it.buf_len) ? base[ll] : (int16_t)0;
             }
-            *reinterpret_cast<uint4*>(&span[8 * g]) = val;
+            *reinterpret_cast<uint4*>(&span[8 * g]) = *reinterpret_cast<uint4*>(tmp);
         }
     }
-    __syncthreads();
+}
 
-    const int g = tid >> 6, t = tid & 63;
-    const float* t2 = STATIONARY ? T2 + (long long)ch.item * T_PITCH : nullptr;
-    const float* t2hi = STATIONARY ? T2hi + (long long)ch.item * T_PITCH : nullptr;
-    uint8_t* rf = STATIONARY ? rowflag + (long long)blockIdx.y * M_PITCH : nullptr;
+// Persistent CTAs (two per SM) walk the (chunk, tile) list; the span of the NEXT tile is in flight (cp.async, double
+// buffer) while the warps transform the current one, so the only exposed latency is the first tile's.
+template <bool STATIONARY>
+__global__ void __launch_bounds__(32 * STFT_WARPS, 2) stft1024_kernel(const int16_t* __restrict__ pcm, const Item* __restrict__ items,
+                                                                     const Chunk* __restrict__ chunks, int n_chunks, int tiles_per_chunk,
+                                                                     Consts cs, const float* __restrict__ T2, const float* __restrict__ T2hi,
+                                                                     c32* __restrict__ S, uint32_t* __restrict__ bits,
+                                                                     uint8_t* __restrict__ rowflag, const NsParams* __restrict__ nsp,
+                                                                     float* __restrict__ P, float* __restrict__ Q) {
+    extern __shared__ __align__(16) unsigned char stft_smem[];
+    c32* scratch = reinterpret_cast<c32*>(stft_smem);                     // [STFT_WARPS][FFT1024_SMEM]
+    c32* tww = scratch + STFT_WARPS * FFT1024_SMEM;                       // [1024]
+    int16_t* span0 = reinterpret_cast<int16_t*>(tww + 1024);              // [2][STFT_SPAN]
 
-    // the four 64-thread groups run decoupled from here on: span / tables are read-only, fsm / flags are per group
-    const short2* span2 = reinterpret_cast<const short2*>(span);
-    const float2* win2 = reinterpret_cast<const float2*>(win);
-    float accP[9], accQ[9];                                   // bins t + 64 q -> 2q, 512 - (t + 64 q) -> 2q + 1, 256 -> 8
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    c32* sm = scratch + warp * FFT1024_SMEM;
+    const int pl = (32 - lane) & 31;                                  // lane holding bins 1024 - k of this lane's bins k
+    for (int i = tid; i < 1024; i += 32 * STFT_WARPS) tww[i] = cs.tww[i];
+    // periodic Hann / 1024 at n = lane + 32 j:  h - h cos(2 pi lane / 1024 + 2 pi j / 32) = h + wc cos(2 pi j / 32) + ws sin(2 pi j / 32)
+    float wc, ws;
+    {
+        float sl, cl;
+        sincospif((float)lane * (1.0f / 512.0f), &sl, &cl);
+        wc = -cl * (0.5f / 1024.0f); ws = sl * (0.5f / 1024.0f);
+    }
+
+    const long long total = (long long)n_chunks * tiles_per_chunk;
+    auto tile_valid = [&](long long t, Chunk& ch, int& f0) {
+        ch = chunks[t / tiles_per_chunk];
+        f0 = (int)(t % tiles_per_chunk) * STFT_TILE;
+        return f0 < ch.n_frames;
+    };
+    // first valid tile of this CTA
+    long long t = blockIdx.x;
+    Chunk ch; int f0 = 0;
+    while (t < total && !tile_valid(t, ch, f0)) t += gridDim.x;
+    if (t >= total) return;
+    int buf = 0;
+    stft_stage_span(span0, pcm, items[ch.item], ch, f0, tid);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    while (t < total) {
+        // next valid tile: start its span load into the other buffer
+        long long tn = t + gridDim.x;
+        Chunk chn; int f0n = 0;
+        while (tn < total && !tile_valid(tn, chn, f0n)) tn += gridDim.x;
+        if (tn < total) stft_stage_span(span0 + (buf ^ 1) * STFT_SPAN, pcm, items[chn.item], chn, f0n, tid);
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();                                              // current span landed; everyone is done with the previous tile's scratch
+
+        const int16_t* span = span0 + buf * STFT_SPAN;
+        const int c = (int)(t / tiles_per_chunk), tile = (int)(t % tiles_per_chunk);
+        const int n_tile = min(STFT_TILE, ch.n_frames - f0);
+        const float* t2 = STATIONARY ? T2 + (long long)ch.item * T_PITCH : nullptr;
+        const float* t2hi = STATIONARY ? T2hi + (long long)ch.item * T_PITCH : nullptr;
+        uint8_t* rf = STATIONARY ? rowflag + (long long)c * M_PITCH : nullptr;
+        float accP[17], accQ[17];                                     // bins 32 k1 + lane -> k1, bin 512 (lane 0) -> 16
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { accP[i] = 0.f; accQ[i] = 0.f; }
-    for (int r = 0; r < STFT_TILE / 4; ++r) {
-        const int lf = r * 4 + g;
-        const int f = f0 + lf;
-        const bool active = f < ch.n_frames;
-        const float wp = STATIONARY ? 0.f : wpq[0][STATIONARY ? 0 : lf], wq = STATIONARY ? 0.f : wpq[1][STATIONARY ? 0 : lf];
-        c32 v[8];
+        for (int i = 0; i < 17; ++i) { accP[i] = 0.f; accQ[i] = 0.f; }
+
+        for (int pr = warp; pr < STFT_TILE / 2; pr += STFT_WARPS) {
+            const int lfA = 2 * pr, fA = f0 + lfA;
+            if (fA >= ch.n_frames) break;                             // warp-uniform
+            const bool actB = fA + 1 < ch.n_frames;
+            c32 v[32];
+            {
+                // frame B is frame A shifted by 256 samples = 8 strides of 32: 40 loads serve both
+                const int16_t* sp = span + lfA * HOP + lane;
+                float s[40];
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int n = t + 64 * m;
-            const short2 sv = span2[lf * (HOP / 2) + n];
-            const float2 w = win2[n];
-            v[m] = mk((float)sv.x * w.x, (float)sv.y * w.y);
-        }
-        group_fft512(v, fsm[g], tw1, tw2, t, g);
-        group_bar(g);
+                for (int m = 0; m < 40; ++m) s[m] = int_to_float_exact((int)sp[32 * m]);
 #pragma unroll
-        for (int d = 0; d < 8; ++d) fsm[g][t + 64 * d] = v[d];
-        group_bar(g);
-        if (active) {
-            c32* row = S + (ch.row0 + f) * S_PITCH;
-            const c32* z = fsm[g];
+                for (int j = 0; j < 32; ++j) {
+                    const float w = fmaf(wc, w32(j).x, fmaf(ws, -w32(j).y, 0.5f / 1024.0f));
+                    v[j] = mk(s[j] * w, actB ? s[j + 8] * w : 0.f);
+                }
+            }
+            fft1024w_pass1(v, sm, tww, lane);
+            __syncwarp();
+            fft1024w_pass2(v, sm, lane);
+            __syncwarp();
+            // v[k1] = Z[32 k1 + lane], Z = X_A + i X_B (the window carries the 1/2):  X_A = Z[k] + conj Z[1024-k],  X_B = -i (Z[k] - conj Z[1024-k])
+            c32* rowA = S + (ch.row0 + fA) * S_PITCH;
+            c32* rowB = rowA + S_PITCH;
+            float wpA = 0.f, wqA = 0.f, wpB = 0.f, wqB = 0.f;
+            if (!STATIONARY) {
+                wpA = (float)(nsp->b * nsp->apow[n_tile - 1 - lfA]);
+                wqA = (float)(nsp->b * nsp->b * nsp->apow[lfA] * (1.0 - nsp->apow[2 * (n_tile - lfA)]) * nsp->inv_1ma2);
+                if (actB) {
+                    wpB = (float)(nsp->b * nsp->apow[n_tile - 2 - lfA]);
+                    wqB = (float)(nsp->b * nsp->b * nsp->apow[lfA + 1] * (1.0 - nsp->apow[2 * (n_tile - lfA - 1)]) * nsp->inv_1ma2);
+                }
+            }
+            uint32_t wordA = 0, wordB = 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int k = t + 64 * q;
-                if (k == 0) {
-                    const c32 z0 = z[0], zm = z[256];
-                    const float x0 = z0.x + z0.y, xn = z0.x - z0.y;
-                    row[0] = mk(x0, xn);
-                    const c32 xm = cconj(zm);
-                    row[256] = xm;
-                    if (STATIONARY) {
-                        const float p0 = x0 * x0, pn = xn * xn, pm = xm.x * xm.x + xm.y * xm.y;
-                        flags[g][0] = p0 > t2[0]; flags[g][512] = pn > t2[512]; flags[g][256] = pm > t2[256];
-                        if (p0 > t2hi[0]) rf[0] = 1;
-                        if (pn > t2hi[512]) rf[512] = 1;
-                        if (pm > t2hi[256]) rf[256] = 1;
-                    } else {
-                        const float a0 = fabsf(x0), an = fabsf(xn), am = fast_sqrt(xm.x * xm.x + xm.y * xm.y);
-                        accP[0] += wp * a0; accQ[0] += wq * a0; accP[1] += wp * an; accQ[1] += wq * an;
-                        accP[8] += wp * am; accQ[8] += wq * am;
+            for (int k1 = 0; k1 < 16; ++k1) {
+                const int k = 32 * k1 + lane;
+                c32 zp;
+                zp.x = __shfl_sync(0xffffffffu, v[31 - k1].x, pl);
+                zp.y = __shfl_sync(0xffffffffu, v[31 - k1].y, pl);
+                if (lane == 0) zp = v[(32 - k1) & 31];                // 1024 - 32 k1 = 32 (32 - k1): lane 0 pairs with itself
+                const c32 z = v[k1];
+                c32 xa = mk(z.x + zp.x, z.y - zp.y), xb = mk(z.y + zp.y, zp.x - z.x);
+                float magA2, magB2, a512 = 0.f, b512 = 0.f;
+                if (k1 == 0 && lane == 0) {
+                    // bins 0 and 512 are real and share slot 0: (re X_0, re X_512)
+                    a512 = 2.f * v[16].x; b512 = 2.f * v[16].y;
+                    xa = mk(xa.x, a512); xb = mk(xb.x, b512);
+                    magA2 = xa.x * xa.x; magB2 = xb.x * xb.x;
+                } else {
+                    magA2 = xa.x * xa.x + xa.y * xa.y; magB2 = xb.x * xb.x + xb.y * xb.y;
+                }
+                rowA[k] = xa;
+                if (actB) rowB[k] = xb;
+                if (STATIONARY) {
+                    const float th = t2[k], thh = t2hi[k];
+                    const uint32_t ba = __ballot_sync(0xffffffffu, magA2 > th), bb = __ballot_sync(0xffffffffu, actB && magB2 > th);
+                    if (lane == k1) { wordA = ba; wordB = bb; }
+                    if (magA2 > thh || (actB && magB2 > thh)) rf[k] = 1;
+                    if (k1 == 0) {
+                        const float th5 = t2[512], thh5 = t2hi[512];
+                        const uint32_t ca = __ballot_sync(0xffffffffu, lane == 0 && a512 * a512 > th5);
+                        const uint32_t cb = __ballot_sync(0xffffffffu, lane == 0 && actB && b512 * b512 > th5);
+                        if (lane == 16) { wordA = ca & 1u; wordB = cb & 1u; }
+                        if (lane == 0 && (a512 * a512 > thh5 || (actB && b512 * b512 > thh5))) rf[512] = 1;
                     }
                 } else {
-                    c32 xk, xnk;
-                    rfft_split_pair(z[k], z[512 - k], tw1024[k], xk, xnk);
-                    row[k] = xk;
-                    row[512 - k] = xnk;
-                    if (STATIONARY) {
-                        const float pk = xk.x * xk.x + xk.y * xk.y, pnk = xnk.x * xnk.x + xnk.y * xnk.y;
-                        flags[g][k] = pk > t2[k]; flags[g][512 - k] = pnk > t2[512 - k];
-                        if (pk > t2hi[k]) rf[k] = 1;
-                        if (pnk > t2hi[512 - k]) rf[512 - k] = 1;
-                    } else {
-                        const float ak = fast_sqrt(xk.x * xk.x + xk.y * xk.y), ank = fast_sqrt(xnk.x * xnk.x + xnk.y * xnk.y);
-                        accP[2 * q] += wp * ak; accQ[2 * q] += wq * ak; accP[2 * q + 1] += wp * ank; accQ[2 * q + 1] += wq * ank;
+                    const float ma = fast_sqrt(magA2), mb = fast_sqrt(magB2);
+                    accP[k1] = fmaf(wpB, mb, fmaf(wpA, ma, accP[k1]));
+                    accQ[k1] = fmaf(wqB, mb, fmaf(wqA, ma, accQ[k1]));
+                    if (k1 == 0) {
+                        accP[16] = fmaf(wpB, fabsf(b512), fmaf(wpA, fabsf(a512), accP[16]));
+                        accQ[16] = fmaf(wqB, fabsf(b512), fmaf(wqA, fabsf(a512), accQ[16]));
                     }
                 }
             }
-        }
-        if (STATIONARY) {
-            group_bar(g);
-            if (active && t < 17) {
-                const uint32_t* fw = reinterpret_cast<const uint32_t*>(&flags[g][32 * t]);
-                uint32_t word = 0;
-                const int nb = (t == 16) ? 1 : 32;
-                for (int b = 0; b < nb; b += 4) {
-                    const uint32_t w4 = fw[b >> 2];                      // four 0/1 bytes, lowest bin in the low byte
-                    const uint32_t nib = (w4 & 1u) | ((w4 >> 7) & 2u) | ((w4 >> 14) & 4u) | ((w4 >> 21) & 8u);
-                    word |= nib << b;
-                }
-                if (t == 16) word &= 1u;
-                bits[(ch.row0 + f) * B_PITCH + t] = word;
+            if (STATIONARY && lane < 17) {
+                bits[(ch.row0 + fA) * B_PITCH + lane] = wordA;
+                if (actB) bits[(ch.row0 + fA + 1) * B_PITCH + lane] = wordB;
             }
         }
-        group_bar(g);
-    }
-    if (!STATIONARY) {
-        // combine the four groups' partial sums in a fixed order (group g's scratch is free after its last barrier)
-        float* gp = reinterpret_cast<float*>(fsm[g]);
+        if (!STATIONARY) {
+            // combine the warps' partial sums in a fixed order (a warp's scratch is its own until the barrier)
+            float* gp = reinterpret_cast<float*>(sm);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int k = t + 64 * q;
-            if (k == 0) {
-                gp[0] = accP[0]; gp[512] = accP[1]; gp[256] = accP[8];
-                gp[T_PITCH] = accQ[0]; gp[T_PITCH + 512] = accQ[1]; gp[T_PITCH + 256] = accQ[8];
-            } else {
-                gp[k] = accP[2 * q]; gp[512 - k] = accP[2 * q + 1];
-                gp[T_PITCH + k] = accQ[2 * q]; gp[T_PITCH + 512 - k] = accQ[2 * q + 1];
+            for (int k1 = 0; k1 < 16; ++k1) { gp[32 * k1 + lane] = accP[k1]; gp[T_PITCH + 32 * k1 + lane] = accQ[k1]; }
+            if (lane == 0) { gp[512] = accP[16]; gp[T_PITCH + 512] = accQ[16]; }
+            __syncthreads();
+            const long long trow = (ch.tile0 + tile) * T_PITCH;
+            for (int k = tid; k < NBIN; k += 32 * STFT_WARPS) {
+                float p = 0.f, q = 0.f;
+#pragma unroll
+                for (int w = 0; w < STFT_WARPS; ++w) {
+                    const float* g = reinterpret_cast<const float*>(scratch + w * FFT1024_SMEM);
+                    p += g[k]; q += g[T_PITCH + k];
+                }
+                P[trow + k] = p; Q[trow + k] = q;
             }
         }
-        __syncthreads();
-        const long long trow = (ch.tile0 + blockIdx.x) * T_PITCH;
-        for (int k = tid; k < NBIN; k += 256) {
-            const float* g0p = reinterpret_cast<const float*>(fsm[0]);
-            const float* g1p = reinterpret_cast<const float*>(fsm[1]);
-            const float* g2p = reinterpret_cast<const float*>(fsm[2]);
-            const float* g3p = reinterpret_cast<const float*>(fsm[3]);
-            P[trow + k] = (g0p[k] + g1p[k]) + (g2p[k] + g3p[k]);
-            Q[trow + k] = (g0p[T_PITCH + k] + g1p[T_PITCH + k]) + (g2p[T_PITCH + k] + g3p[T_PITCH + k]);
-        }
+        if (STATIONARY) __syncthreads();                              // every warp is done with this span before it is refilled
+        t = tn; ch = chn; f0 = f0n; buf ^= 1;
     }
 }
 
@@ -223,18 +249,16 @@ void launch_stft(const int16_t* pcm, const Item* items, const Chunk* chunks, int
                  uint8_t* rowflag, const NsParams* ns, float* P, float* Q, cudaStream_t st) {
     if (n_chunks <= 0) return;
     const int tiles = (max_frames + STFT_TILE - 1) / STFT_TILE;
-    constexpr int dyn = STFT_SPAN * (int)sizeof(int16_t);
-    cudaFuncSetAttribute(stft1024_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-    cudaFuncSetAttribute(stft1024_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-    for (int y0 = 0; y0 < n_chunks; y0 += 32768) {
-        const int ny = n_chunks - y0 < 32768 ? n_chunks - y0 : 32768;
-        dim3 grid(tiles, ny);
-        if (stationary)
-            stft1024_kernel<true><<<grid, 256, dyn, st>>>(pcm, items, chunks + y0, c, T2, T2hi, S, bits,
-                                                        rowflag + (long long)y0 * M_PITCH, nullptr, nullptr, nullptr);
-        else
-            stft1024_kernel<false><<<grid, 256, dyn, st>>>(pcm, items, chunks + y0, c, nullptr, nullptr, S, nullptr, nullptr, ns, P, Q);
-    }
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    const long long total = (long long)n_chunks * tiles;
+    const int grid = (int)std::min<long long>(total, 2LL * n_sm);
+    cudaFuncSetAttribute(stft1024_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STFT_SMEM);
+    cudaFuncSetAttribute(stft1024_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STFT_SMEM);
+    if (stationary)
+        stft1024_kernel<true><<<grid, 32 * STFT_WARPS, STFT_SMEM, st>>>(pcm, items, chunks, n_chunks, tiles, c, T2, T2hi, S, bits, rowflag, nullptr, nullptr, nullptr);
+    else
+        stft1024_kernel<false><<<grid, 32 * STFT_WARPS, STFT_SMEM, st>>>(pcm, items, chunks, n_chunks, tiles, c, nullptr, nullptr, S, nullptr, nullptr, ns, P, Q);
 }
 
 // ============================================================================================================

@@ -68,6 +68,35 @@ int main() {
         }
         printf("irfft1024 round-trip max err %.3e\n", ierr); if (ierr > 1e-5) ++fails;
     }
+    // ---- fft32 vs direct, warp-level fft1024 (32 x 32) vs direct, two-real-frames split / merge
+    {
+        c32 v[32]; std::vector<cd> x(32);
+        for (int n = 0; n < 32; ++n) { v[n] = mk((float)frand(), (float)frand()); x[n] = cd(v[n].x, v[n].y); }
+        fft32(v);
+        double err = 0;
+        for (int k = 0; k < 32; ++k) { cd s = 0; for (int n = 0; n < 32; ++n) s += x[n] * std::polar(1.0, -2 * PI * n * k / 32.0); err = fmax(err, std::abs(s - cd(v[k].x, v[k].y))); }
+        printf("fft32    max err %.3e\n", err); if (err > 1e-5) ++fails;
+    }
+    {
+        std::vector<c32> tww(1024), sm(FFT1024_SMEM);
+        for (int j = 0; j < 32; ++j) for (int l = 0; l < 32; ++l) tww[j * 32 + l] = mk((float)cos(2 * PI * l * j / 1024), (float)-sin(2 * PI * l * j / 1024));
+        std::vector<float> xa(1024), xb(1024);
+        for (int n = 0; n < 1024; ++n) { xa[n] = (float)frand(); xb[n] = (float)frand(); }
+        c32 regs[32][32];
+        for (int l = 0; l < 32; ++l) { for (int j = 0; j < 32; ++j) regs[l][j] = mk(xa[l + 32 * j], xb[l + 32 * j]); fft1024w_pass1(regs[l], sm.data(), tww.data(), l); }
+        for (int l = 0; l < 32; ++l) fft1024w_pass2(regs[l], sm.data(), l);
+        std::vector<cd> Z(1024);
+        for (int l = 0; l < 32; ++l) for (int j = 0; j < 32; ++j) Z[32 * j + l] = cd(regs[l][j].x, regs[l][j].y);
+        double err = 0, erra = 0;
+        for (int k = 0; k <= 512; ++k) {
+            cd sa = 0, sb = 0;
+            for (int n = 0; n < 1024; ++n) { cd w = std::polar(1.0, -2 * PI * n * k / 1024.0); sa += (double)xa[n] * w; sb += (double)xb[n] * w; }
+            err = fmax(err, std::abs(sa + cd(0, 1) * sb - Z[k]));
+            const cd zp = std::conj(Z[(1024 - k) % 1024]);
+            erra = fmax(erra, std::abs((Z[k] + zp) * 0.5 - sa)); erra = fmax(erra, std::abs((Z[k] - zp) * cd(0, -0.5) - sb));
+        }
+        printf("fft1024w max err %.3e, two-frame split max err %.3e\n", err, erra); if (err > 4e-4 || erra > 4e-4) ++fails;
+    }
     // ---- fft200 + rfft400
     {
         std::vector<float> x(400); for (auto& v : x) v = (float)frand();
