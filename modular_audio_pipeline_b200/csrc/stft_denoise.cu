@@ -98,6 +98,11 @@ __global__ void __launch_bounds__(32 * STFT_WARPS, 2) stft1024_kernel(const int1
     c32* sm = scratch + warp * FFT1024_SMEM;
     const int pl = (32 - lane) & 31;                                  // lane holding bins 1024 - k of this lane's bins k
     for (int i = tid; i < 1024; i += 32 * STFT_WARPS) tww[i] = cs.tww[i];
+    __shared__ float wtab[2][STATIONARY ? 1 : STFT_TILE];             // scan weights of a full tile (n = STFT_TILE)
+    if (!STATIONARY && tid < STFT_TILE) {
+        wtab[0][tid] = (float)(nsp->b * nsp->apow[STFT_TILE - 1 - tid]);
+        wtab[1][tid] = (float)(nsp->b * nsp->b * nsp->apow[tid] * (1.0 - nsp->apow[2 * (STFT_TILE - tid)]) * nsp->inv_1ma2);
+    }
     // periodic Hann / 1024 at n = lane + 32 j:  h - h cos(2 pi lane / 1024 + 2 pi j / 32) = h + wc cos(2 pi j / 32) + ws sin(2 pi j / 32)
     float wc, ws;
     {
@@ -165,7 +170,10 @@ __global__ void __launch_bounds__(32 * STFT_WARPS, 2) stft1024_kernel(const int1
             c32* rowA = S + (ch.row0 + fA) * S_PITCH;
             c32* rowB = rowA + S_PITCH;
             float wpA = 0.f, wqA = 0.f, wpB = 0.f, wqB = 0.f;
-            if (!STATIONARY) {
+            if (!STATIONARY && n_tile == STFT_TILE) {
+                wpA = wtab[0][STATIONARY ? 0 : lfA]; wqA = wtab[1][STATIONARY ? 0 : lfA];
+                wpB = wtab[0][STATIONARY ? 0 : lfA + 1]; wqB = wtab[1][STATIONARY ? 0 : lfA + 1];
+            } else if (!STATIONARY) {
                 wpA = (float)(nsp->b * nsp->apow[n_tile - 1 - lfA]);
                 wqA = (float)(nsp->b * nsp->b * nsp->apow[lfA] * (1.0 - nsp->apow[2 * (n_tile - lfA)]) * nsp->inv_1ma2);
                 if (actB) {
@@ -821,33 +829,47 @@ __global__ void __launch_bounds__(256) istft_kernel(const c32* __restrict__ S, c
     __syncthreads();
 
     const int fbase = g0 - 1;                                       // local frame 0
+    // Group g walks local frames 8 g .. 8 g + 7.  The masked spectrum of the NEXT frame is fetched into registers while the
+    // current one is transformed (the global-load latency used to sit exposed in front of every frame).
+    c32 pxk[4], pxn[4];                                             // S[k], S[512 - k], k = t + 64 q  (q = 0, t = 0: S[0], S[256])
+    float pmk[4], pmn[4], pm512 = 0.f;                              // M[k], M[512 - k]                 (q = 0, t = 0: M[0], M[256]; M[512])
+    auto fetch = [&](int lf) {
+        const int f = fbase + lf;
+        if (f >= 0 && f < ch.n_frames) {
+            const c32* row = S + (ch.row0 + f) * S_PITCH;
+            const float* mrow = M + (ch.row0 + f) * M_PITCH;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = t + 64 * q;
+                pxk[q] = row[k]; pmk[q] = mrow[k];
+                const int kn = k == 0 ? 256 : 512 - k;
+                pxn[q] = row[kn]; pmn[q] = mrow[kn];
+            }
+            if (t == 0) pm512 = mrow[512];
+        }
+    };
+    fetch((ISTFT_FR / 4) * g);
     for (int r = 0; r < ISTFT_FR / 4; ++r) {
         const int lf = r + (ISTFT_FR / 4) * g;
         const int f = fbase + lf;
         const bool active = f >= 0 && f < ch.n_frames;
         c32* z = fsm + g * FFT512_SMEM;
         if (active) {
-            const c32* row = S + (ch.row0 + f) * S_PITCH;
-            const float* mrow = M + (ch.row0 + f) * M_PITCH;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int k = t + 64 * q;
                 if (k == 0) {
-                    const c32 x0 = row[0];
-                    const float a = x0.x * mrow[0], b = x0.y * mrow[512];
+                    const float a = pxk[0].x * pmk[0], b = pxk[0].y * pm512;
                     z[0] = mk(a + b, -(a - b));                     // 2 conj(Z0)
-                    const c32 xm = row[256];
-                    const float mm = mrow[256];
-                    z[256] = mk(2.f * xm.x * mm, 2.f * xm.y * mm);  // 2 conj(Z256) = 2 X256
+                    z[256] = mk(2.f * pxn[0].x * pmn[0], 2.f * pxn[0].y * pmn[0]);   // 2 conj(Z256) = 2 X256
                 } else {
-                    const c32 xk = row[k], xnk = row[512 - k];
-                    const float mk_ = mrow[k], mnk = mrow[512 - k];
                     c32 zk, znk;
-                    irfft_merge_pair(mk(xk.x * mk_, xk.y * mk_), mk(xnk.x * mnk, xnk.y * mnk), tw1024[k], zk, znk);
+                    irfft_merge_pair(mk(pxk[q].x * pmk[q], pxk[q].y * pmk[q]), mk(pxn[q].x * pmn[q], pxn[q].y * pmn[q]), tw1024[k], zk, znk);
                     z[k] = zk; z[512 - k] = znk;
                 }
             }
         }
+        if (r + 1 < ISTFT_FR / 4) fetch(lf + 1);
         group_bar(g);
         c32 v[8];
 #pragma unroll
@@ -867,8 +889,11 @@ __global__ void __launch_bounds__(256) istft_kernel(const c32* __restrict__ S, c
                 o2[n] = acc;
             }
         }
-        __syncthreads();            // the overlap-add buffer is shared by all four groups: one CTA-wide barrier per round
+        // Frames of one group overlap their successors (group barrier).  Across groups only rounds 0..2 of group g and
+        // rounds 5..7 of group g - 1 touch the same samples: one CTA-wide barrier between round 3 and round 4 orders them.
+        if (r == 3) __syncthreads(); else group_bar(g);
     }
+    __syncthreads();
     // emit: segment g covers padded-chunk samples [256 g, 256 g + 256) = ola[768 + 256 (g - g0) ...]
     int pk = 0;
     const long long obase = (to_out ? it.out_off : it.den_off) + ch.out_off;
