@@ -49,6 +49,27 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     if (lf0 >= it.mel_frames) return;
     const int tid = threadIdx.x;
 
+    // geometry of the tile's sample span; on the interior fast path the 16-byte sample loads are issued first so that their
+    // latency overlaps the table prologue
+    const int16_t* x = den16 + it.den_off;
+    const long long i0 = ((long long)it.mel_f0 + lf0) * W_HOP - W_NFFT / 2;
+    const bool last_tile = lf0 + MEL_TILE >= it.mel_frames;
+    const long long own_lo = i0 + W_NFFT / 2;
+    const long long own_hi = last_tile ? it.g0 + it.own_len : own_lo + (long long)MEL_TILE * W_HOP;
+    const long long l0 = i0 - it.g0;                                // item-relative index of span[0]
+    const bool interior = i0 >= 0 && i0 + MEL_SPAN <= it.n_global && l0 >= -(long long)it.lo_avail &&
+                          l0 + MEL_SPAN <= it.own_len + it.hi_avail && ((it.den_off + l0) & 7) == 0 && !last_tile &&
+                          (!out16 || (((it.out_off + l0) & 7) == 0 && l0 + W_NFFT / 2 >= 0 && l0 + W_NFFT / 2 + MEL_TILE * W_HOP <= it.own_len));
+    constexpr int PRE = (MEL_SPAN / 8 + 255) / 256;                 // 16-byte groups per thread
+    uint4 pre[PRE];
+    if (interior) {
+#pragma unroll
+        for (int u = 0; u < PRE; ++u) {
+            const int gq = tid + 256 * u;
+            if (gq < MEL_SPAN / 8) pre[u] = *reinterpret_cast<const uint4*>(x + l0 + 8 * gq);
+        }
+    }
+
     for (int i = tid; i < W_NFFT; i += 256) win[i] = cs.win400[i];
     for (int i = tid; i < 200; i += 256) twA[i] = cs.twA[i];
     if (tid < mel.n_mels / 4) { m_qstart[tid] = mel.qstart[tid]; m_qcount[tid] = mel.qcount[tid]; m_qoff[tid] = mel.qoff[tid]; }
@@ -60,7 +81,6 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     const bool pn = pnv.active != 0;
     Gate gt; gt.applied = 0;
     if (gates) gt = gates[item];
-    const int16_t* x = den16 + it.den_off;
     const long long np_global = it.n_global + padding;            // length of the zero-padded recording
     __syncthreads();
 
@@ -68,18 +88,13 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     // recording.  The tile also writes the final PCM of the 32 hops it is centred on (the last tile up to the item's
     // end: with padding 0 the tail N mod 160 plus the last hop still lies inside its span).
     {
-        const long long i0 = ((long long)it.mel_f0 + lf0) * W_HOP - W_NFFT / 2;
-        const bool last_tile = lf0 + MEL_TILE >= it.mel_frames;
-        const long long own_lo = i0 + W_NFFT / 2;
-        const long long own_hi = last_tile ? it.g0 + it.own_len : own_lo + (long long)MEL_TILE * W_HOP;
-        const long long l0 = i0 - it.g0;                            // item-relative index of span[0]
-        const bool interior = i0 >= 0 && i0 + MEL_SPAN <= it.n_global && l0 >= -(long long)it.lo_avail &&
-                              l0 + MEL_SPAN <= it.own_len + it.hi_avail && ((it.den_off + l0) & 7) == 0 && !last_tile &&
-                              (!out16 || (((it.out_off + l0) & 7) == 0 && l0 + W_NFFT / 2 >= 0 && l0 + W_NFFT / 2 + MEL_TILE * W_HOP <= it.own_len));
         if (interior) {
             // fast path: no reflection, no padding, 16-byte loads and stores (i0, own_lo and the hop are multiples of 8)
-            for (int gq = tid; gq < MEL_SPAN / 8; gq += 256) {
-                const uint4 v = *reinterpret_cast<const uint4*>(x + l0 + 8 * gq);
+#pragma unroll
+            for (int u = 0; u < PRE; ++u) {
+                const int gq = tid + 256 * u;
+                if (gq >= MEL_SPAN / 8) break;
+                const uint4 v = pre[u];
                 int sv[8];
                 sv[0] = (short)(v.x & 0xffff); sv[1] = (short)(v.x >> 16); sv[2] = (short)(v.y & 0xffff); sv[3] = (short)(v.y >> 16);
                 sv[4] = (short)(v.z & 0xffff); sv[5] = (short)(v.z >> 16); sv[6] = (short)(v.w & 0xffff); sv[7] = (short)(v.w >> 16);

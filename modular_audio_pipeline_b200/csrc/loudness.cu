@@ -47,7 +47,9 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
     extern __shared__ __align__(16) unsigned char kw_smem[];
     double* e_lane = reinterpret_cast<double*>(kw_smem);                         // [blockDim.x] lane energies
     double* e_warp = e_lane + blockDim.x;                                        // [32][4] zero-state end state of each warp
-    float4* hs = reinterpret_cast<float4*>(e_warp + 32 * 4);                     // [KW_MAX_SEG] state impulse responses
+    double* mats = e_warp + 32 * 4;                                              // [6][16] Mstep[0..4], Mwarp
+    double* mlane = mats + 6 * 16;                                               // [16][32] Mlane transposed: element-major, lane-minor
+    float4* hs = reinterpret_cast<float4*>(mlane + 16 * 32);                     // [KW_MAX_SEG] state impulse responses
     int16_t* xs = reinterpret_cast<int16_t*>(hs + KW_MAX_SEG);                   // [(tpc + 1) * tile_len] staged samples
     const int seg = SEG ? SEG : seg_rt;
 
@@ -61,6 +63,9 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
     const long long c0 = (first_tile - 1) * tile_len;                            // item-relative index of the first staged sample
     const int span = (tpc + 1) * tile_len;
     if (tid < seg) hs[tid] = make_float4(tab->H[tid][0], tab->H[tid][1], tab->H[tid][2], tab->H[tid][3]);
+    // scan matrices into shared memory (the scan steps are a dependent chain: global-load latency would sit in every link)
+    for (int i = tid; i < 6 * 16; i += blockDim.x) mats[i] = i < 80 ? tab->Mstep[i >> 4][i & 15] : tab->Mwarp[i - 80];
+    for (int i = tid; i < 16 * 32; i += blockDim.x) mlane[i] = tab->Mlane[i & 31][i >> 5];
 
     PeakNorm pnv; pnv.active = 0;
     if (peak_normalize) pnv = pnorm[item];
@@ -128,7 +133,7 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
         double o[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) o[r] = __shfl_up_sync(0xffffffffu, e[r], d);
-        if (lane >= d) mat4_apply_add(tab->Mstep[i], o, e);
+        if (lane >= d) mat4_apply_add(mats + 16 * i, o, e);
     }
     if (lane == 31) { e_warp[4 * warp] = e[0]; e_warp[4 * warp + 1] = e[1]; e_warp[4 * warp + 2] = e[2]; e_warp[4 * warp + 3] = e[3]; }
     __syncthreads();
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
     double sw[4] = {0.0, 0.0, 0.0, 0.0};
     for (int w = 0; w < warp; ++w) {
         double nx[4] = {e_warp[4 * w], e_warp[4 * w + 1], e_warp[4 * w + 2], e_warp[4 * w + 3]};
-        mat4_apply_add(tab->Mwarp, sw, nx);
+        mat4_apply_add(mats + 80, sw, nx);
 #pragma unroll
         for (int r = 0; r < 4; ++r) sw[r] = nx[r];
     }
@@ -144,7 +149,12 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
     double z[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) { const double up = __shfl_up_sync(0xffffffffu, e[r], 1); z[r] = lane > 0 ? up : 0.0; }
-    mat4_apply_add(tab->Mlane[lane], sw, z);
+    {
+        double ml[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ml[i] = mlane[32 * i + lane];
+        mat4_apply_add(ml, sw, z);
+    }
     // pass 2 (samples past the end of the recording are zeros in shared memory: they add nothing), all float32:
     //   shelf      y1 = b0 x + s0 ; s0 = b1 x - a1 y1 + s1 ; s1 = b2 x - a2 y1
     //   high pass  b = (b0, -2 b0, b0) exactly (RBJ), a1 = -2 + d1, a2 = 1 - d2 with d1, d2 ~ 0.03 held as floats:
@@ -196,7 +206,7 @@ void launch_kweight_energy(const int16_t* den16, const Item* items, int n_items,
                            const KWeight& kw, const KwScan* tab, int peak_normalize, const PeakNorm* pnorm,
                            double* sub_energy, int* peak_norm, cudaStream_t st) {
     if (n_items <= 0 || max_groups <= 0) return;
-    const size_t smem = sizeof(double) * (geo.threads + 128) + sizeof(float4) * KW_MAX_SEG + sizeof(int16_t) * (size_t)(geo.tpc + 1) * tile_len + 16;
+    const size_t smem = sizeof(double) * (geo.threads + 128 + 6 * 16 + 16 * 32) + sizeof(float4) * KW_MAX_SEG + sizeof(int16_t) * (size_t)(geo.tpc + 1) * tile_len + 16;
     auto kern = geo.seg == 50 ? kweight_energy_kernel<50> : kweight_energy_kernel<0>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int y0 = 0; y0 < n_items; y0 += 32768) {

@@ -593,8 +593,18 @@ __device__ __forceinline__ void ns_walk(const c32* __restrict__ sp, int k, int b
         for (int q = 0; q < NB; ++q) {
             const int rr = base + NS_TILE - 1 - (b0 + q);
             if (b0 + q < W) dst[q] = (INTERIOR || (rr >= 0 && rr < F)) ? sp[(long long)rr * S_PITCH] : mk(0.f, 0.f);
+            // pull the rows of three batches ahead into L2 (the walk streams S from DRAM exactly once)
+            const int rp = rr - 3 * NB;
+            if (b0 + q + 3 * NB < W && (INTERIOR || (rp >= 0 && rp < F))) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + (long long)rp * S_PITCH));
         }
     };
+    if (INTERIOR || base + NS_TILE - 1 - 3 * NB >= 0) {
+#pragma unroll
+        for (int q = 0; q < 3 * NB; ++q) {
+            const int rr = min(base + NS_TILE - 1, F - 1) - q;
+            if (rr >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + (long long)rr * S_PITCH));
+        }
+    }
     load(cur, 0);
 #pragma unroll
     for (int b0 = 0; b0 < W; b0 += NB) {
