@@ -11,15 +11,6 @@
 
 namespace maf {
 
-__device__ __forceinline__ int gain_sample_m(int s, const Gate& gt) {
-    if (!gt.applied) return s;
-    float y = __fmul_rn(gt.gain, int_to_float_exact(s) * (1.0f / 32768.0f));
-    if (gt.lim) y = __fdiv_rn(y, gt.limp);
-    float v = __fmul_rn(y, 32768.0f);
-    v = fminf(fmaxf(v, -32768.0f), 32767.0f);
-    return trunc_to_int(v);
-}
-
 constexpr int MEL_SPAN = (MEL_TILE - 1) * W_HOP + W_NFFT;            // 5360 samples per tile
 constexpr int Z_PITCH = 200;
 constexpr int P_PITCH = 201;
@@ -101,9 +92,9 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
                 float a[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    if (pn) sv[e] = peak_norm_sample_fast(sv[e], pnv);
-                    sv[e] = gain_sample_m(sv[e], gt);
-                    a[e] = int_to_float_exact(sv[e]) * (1.0f / 32768.0f);
+                    float qf;
+                    sv[e] = norm_gain_sample(sv[e], pn, pnv, gt, qf);
+                    a[e] = qf * (1.0f / 32768.0f);
                 }
                 *reinterpret_cast<float4*>(span + 8 * gq) = make_float4(a[0], a[1], a[2], a[3]);
                 *reinterpret_cast<float4*>(span + 8 * gq + 4) = make_float4(a[4], a[5], a[6], a[7]);
@@ -126,9 +117,9 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
                     const long long l = r - it.g0;                    // item-relative index into the denoised samples
                     if (l >= -(long long)it.lo_avail && l < it.own_len + it.hi_avail) {
                         int sv = x[l];
-                        if (pn) sv = peak_norm_sample_fast(sv, pnv);
-                        const int q = gain_sample_m(sv, gt);
-                        a = int_to_float_exact(q) * (1.0f / 32768.0f);
+                        float qf;
+                        const int q = norm_gain_sample(sv, pn, pnv, gt, qf);
+                        a = qf * (1.0f / 32768.0f);
                         if (out16 && r == i && i >= own_lo && i < own_hi && l >= 0 && l < it.own_len) out16[it.out_off + l] = (int16_t)q;
                     }
                 }

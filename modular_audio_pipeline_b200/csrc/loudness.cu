@@ -313,9 +313,8 @@ void launch_gate(const double* sub_energy, const Item* items, int n_items, doubl
 // clip(y * 32768, -32768, 32767).astype(int16)
 __device__ __forceinline__ int gain_sample(int s, const Gate& gt) {
     if (!gt.applied) return s;
-    float y = __fmul_rn(gt.gain, int_to_float_exact(s) * (1.0f / 32768.0f));
-    if (gt.lim) y = __fdiv_rn(y, gt.limp);
-    float v = __fmul_rn(y, 32768.0f);
+    float v = __fmul_rn(gt.gain, int_to_float_exact(s));      // == gain * (s / 32768) * 32768: power-of-two scaling commutes with rounding
+    if (gt.lim) v = __fdiv_rn(v, gt.limp);
     v = fminf(fmaxf(v, -32768.0f), 32767.0f);
     return trunc_to_int(v);
 }

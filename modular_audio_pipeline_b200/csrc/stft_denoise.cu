@@ -857,7 +857,19 @@ __global__ void __launch_bounds__(256) istft_kernel(const c32* __restrict__ S, c
             }
             if (t == 0) pm512 = mrow[512];
         }
+        // the rows two frames further on go to L2 meanwhile: one 128-byte line per thread (32 of S, 17 of M)
+        const int fp = f + 2;
+        if (lf + 2 < (ISTFT_FR / 4) * (g + 1) && fp >= 0 && fp < ch.n_frames) {
+            const char* ps = reinterpret_cast<const char*>(S + (ch.row0 + fp) * S_PITCH);
+            const char* pm = reinterpret_cast<const char*>(M + (ch.row0 + fp) * M_PITCH);
+            if (t < 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + 128 * t));
+            else if (t < 49) asm volatile("prefetch.global.L2 [%0];" ::"l"(pm + 128 * (t - 32)));
+        }
     };
+    if (t < 32) {                                                   // the group's first two frames
+        const int f1 = fbase + (ISTFT_FR / 4) * g + 1;
+        if (f1 >= 0 && f1 < ch.n_frames) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(S + (ch.row0 + f1) * S_PITCH) + 128 * t));
+    }
     fetch((ISTFT_FR / 4) * g);
     for (int r = 0; r < ISTFT_FR / 4; ++r) {
         const int lf = r + (ISTFT_FR / 4) * g;
