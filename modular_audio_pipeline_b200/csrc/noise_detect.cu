@@ -81,9 +81,76 @@ __global__ void __launch_bounds__(128) frame_stats_kernel(const int16_t* __restr
     zc[it.sframe_off + f] = c;
 }
 
+// Fast path for the 16 kHz geometry (frame 400, hop 160): one WARP per frame, samples staged in shared memory.
+// numpy's pairwise sum of 400 float32 squares is ((leaf(0,96) + leaf(96,104)) + (leaf(200,96) + leaf(296,104))) where a leaf
+// keeps 8 strided accumulators r[j] += x[8 i + j]^2 and folds them as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)): that is 32
+// independent sequential chains -- one per lane -- followed by exactly the xor-1, 2, 4 (inside a leaf) and xor-8, 16
+// (across leaves) butterfly, so the warp-parallel sum is bit-identical to the serial one (float addition commutes).
+constexpr int FS_FRAMES = 64;                                    // frames per CTA
+constexpr int FS_SPAN = (FS_FRAMES - 1) * 160 + 400;             // 10480 samples
+
+__global__ void __launch_bounds__(256) frame_stats400_kernel(const int16_t* __restrict__ pcm, const Item* __restrict__ items,
+                                                            float* __restrict__ energies, int* __restrict__ zc) {
+    __shared__ __align__(16) int16_t span[FS_SPAN + 8];
+    const Item it = items[blockIdx.y];
+    const int f0 = blockIdx.x * FS_FRAMES;
+    if (f0 >= it.n_sframes) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nfr = min(FS_FRAMES, it.n_sframes - f0);
+    const int need = (nfr - 1) * 160 + 400;
+    const long long g0 = it.pcm_off + it.origin + (long long)f0 * 160;          // first sample of the tile in the pcm array
+    const int16_t* p = pcm + g0;
+    if ((g0 & 7) == 0) {
+        for (int g = tid; g < (need + 7) / 8; g += 256) {
+            if (8 * g + 8 <= need) *reinterpret_cast<uint4*>(&span[8 * g]) = *reinterpret_cast<const uint4*>(p + 8 * g);
+            else for (int e = 8 * g; e < need; ++e) span[e] = p[e];
+        }
+    } else {
+        for (int e = tid; e < need; e += 256) span[e] = p[e];
+    }
+    __syncthreads();
+    // lane -> (leaf, accumulator): leaf offsets 0 / 96 / 200 / 296, lengths 96 / 104 / 96 / 104
+    const int leaf = lane >> 3, j = lane & 7;
+    const int loff = leaf == 0 ? 0 : leaf == 1 ? 96 : leaf == 2 ? 200 : 296;
+    const int lcnt = (leaf & 1) ? 13 : 12;
+    for (int lf = warp; lf < nfr; lf += 8) {
+        const int16_t* x = span + lf * 160;
+        float v0 = int_to_float_exact((int)x[loff + j]);
+        float r = __fmul_rn(v0, v0);
+#pragma unroll
+        for (int i = 1; i < 13; ++i) {
+            if (i < lcnt) { const float v = int_to_float_exact((int)x[loff + j + 8 * i]); r = __fadd_rn(r, __fmul_rn(v, v)); }
+        }
+        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 8));
+        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 16));
+        // sign changes between consecutive samples: lane owns pairs (i - 1, i), i = 1 + 13 lane .. 13 lane + 13
+        int c = 0;
+        const int i0 = 1 + 13 * lane;
+        int prev = x[i0 - 1 < 400 ? i0 - 1 : 399] < 0;
+#pragma unroll
+        for (int q = 0; q < 13; ++q) {
+            const int i = i0 + q;
+            if (i < 400) { const int cur = x[i] < 0; c += (cur != prev); prev = cur; }
+        }
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0) {
+            energies[it.sframe_off + f0 + lf] = __fsqrt_rn(__fdiv_rn(r, 400.0f));
+            zc[it.sframe_off + f0 + lf] = c;
+        }
+    }
+}
+
 void launch_frame_stats(const int16_t* pcm, const Item* items, int n_items, int max_frames, int frame_len, int hop,
                         float* energies, int* zc, cudaStream_t st) {
     if (max_frames <= 0 || n_items <= 0) return;
+    if (frame_len == 400 && hop == 160) {
+        dim3 grid((max_frames + FS_FRAMES - 1) / FS_FRAMES, n_items);
+        frame_stats400_kernel<<<grid, 256, 0, st>>>(pcm, items, energies, zc);
+        return;
+    }
     dim3 grid((max_frames + 127) / 128, n_items);
     frame_stats_kernel<<<grid, 128, 0, st>>>(pcm, items, frame_len, hop, energies, zc);
 }

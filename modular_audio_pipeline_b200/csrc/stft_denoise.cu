@@ -726,77 +726,108 @@ void launch_ns_mask(const c32* S, const Chunk* chunks, int n_chunks, int max_fra
 
 // ============================================================================================================
 // K2  separable triangular smoothing of the stationary gate (scipy.signal.fftconvolve(mask, outer(vf, vt)/sum, 'same'),
-// zero padded): raw = bit | rowflag ? 1 : 1 - prop (blend, then smooth).
-// Phase 1 applies the time taps while expanding the raw bit rows (17 words per frame, L2 resident), writing rows into
-// shared memory with MAX_NF zeros on both sides; phase 2 applies the frequency taps from shared memory, 8 outputs per
-// thread in registers.
+// zero padded): raw = bit | rowflag ? 1 : 1 - prop (blend, then smooth).  Same structure as the non-stationary mask
+// kernel: a CTA owns 32 output frames, one thread per bin walks the 32 + 2 nt raw rows (one warp-uniform 4-byte load of
+// the frame's bit word per row, eight rows in flight), applies the time taps in a register window and leaves the rows in
+// shared memory for the frequency taps.
 // ============================================================================================================
-__global__ void __launch_bounds__(256) smooth_mask_kernel(const uint32_t* __restrict__ bits, const uint8_t* __restrict__ rowflag,
-                                                          const Chunk* __restrict__ chunks, float prop, SmoothTaps taps,
-                                                          float* __restrict__ M) {
-    __shared__ __align__(16) float rows[MASK_TILE][SM_ROW];
-    __shared__ uint32_t rfbits[17];
+template <int NT>
+__global__ void __launch_bounds__(NSM_THREADS, 2) smooth_mask_kernel(const uint32_t* __restrict__ bits, const uint8_t* __restrict__ rowflag,
+                                                                     const Chunk* __restrict__ chunks, float prop, SmoothTaps taps,
+                                                                     float* __restrict__ M) {
+    extern __shared__ __align__(16) float rows[];                 // [NS_TILE][SM_ROW]
+    constexpr int W = NS_TILE + 2 * NT;
     const Chunk ch = chunks[blockIdx.y];
-    const int f0 = blockIdx.x * MASK_TILE;
-    if (f0 >= ch.n_frames) return;
+    const int F = ch.n_frames;
+    const int base = NS_TILE * blockIdx.x;                        // outputs [base, base + 32), raw rows [base - NT, base + 32 + NT)
+    if (base >= F) return;
     const int tid = threadIdx.x;
-    const int nt = taps.nt, nf = taps.nf;
-    for (int i = tid; i < MASK_TILE * SM_ROW; i += 256) (&rows[0][0])[i] = 0.f;
-    if (tid < 17) {
-        const uint8_t* rf = rowflag + (long long)blockIdx.y * M_PITCH;
-        uint32_t w = 0;
-        for (int b = 0; b < 32; ++b) { const int k = 32 * tid + b; if (k < NBIN && rf[k]) w |= 1u << b; }
-        rfbits[tid] = w;
+    for (int i = tid; i < NS_TILE * (SM_ROW - NBIN); i += NSM_THREADS) {
+        const int r = i / (SM_ROW - NBIN), c = i - r * (SM_ROW - NBIN);
+        rows[r * SM_ROW + (c < MAX_NF ? c : c + NBIN)] = 0.f;
     }
-    __syncthreads();
-    {
+    if (tid < NBIN) {
+        const int k = tid;
         const float lo = 1.0f - prop;
-        for (int w = tid; w < MASK_TILE * 17; w += 256) {
-            const int lf = w / 17, wi = w % 17;
-            const int f = f0 + lf;
-            if (f >= ch.n_frames) continue;
-            float acc[32];
+        const bool rf = rowflag[(long long)blockIdx.y * M_PITCH + k] != 0;
+        const uint32_t* bp = bits + ch.row0 * B_PITCH + (k >> 5);
+        const int sh = k & 31;
+        float vt[2 * NT + 1], w[2 * NT + 1];
 #pragma unroll
-            for (int b = 0; b < 32; ++b) acc[b] = 0.f;
-            const uint32_t rfw = rfbits[wi];
-            for (int j = -nt; j <= nt; ++j) {
-                const int ff = f + j;
-                if (ff < 0 || ff >= ch.n_frames) continue;
-                const uint32_t word = bits[(ch.row0 + ff) * B_PITCH + wi] | rfw;
-                const float wt = taps.vt[j + nt];
+        for (int i = 0; i < 2 * NT + 1; ++i) { vt[i] = taps.vt[i]; w[i] = 0.f; }
 #pragma unroll
-                for (int b = 0; b < 32; ++b) acc[b] += wt * (((word >> b) & 1u) ? 1.0f : lo);
+        for (int b0 = 0; b0 < W; b0 += 8) {
+            uint32_t wd[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int rr = base - NT + b0 + q;
+                wd[q] = (b0 + q < W && rr >= 0 && rr < F) ? __ldg(bp + (long long)rr * B_PITCH) : 0u;
             }
-            const int nb = (wi == 16) ? 1 : 32;
 #pragma unroll
-            for (int b = 0; b < 32; ++b) if (b < nb) rows[lf][MAX_NF + 32 * wi + b] = acc[b];
+            for (int q = 0; q < 8; ++q) {
+                const int i = b0 + q;
+                if (i < W) {
+                    const int rr = base - NT + i;
+                    const float R = (rr >= 0 && rr < F) ? ((((wd[q] >> sh) & 1u) | (rf ? 1u : 0u)) ? 1.0f : lo) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 2 * NT; ++j) w[j] = w[j + 1];
+                    w[2 * NT] = R;                                // w[j] = raw mask of frame rr - 2 NT + j
+                    if (i >= 2 * NT) {
+                        const int lr = i - 2 * NT;                // output frame rr - NT = base + lr
+                        float acc = vt[0] * w[0];
+#pragma unroll
+                        for (int j = 1; j < 2 * NT + 1; ++j) acc = fmaf(vt[j], w[j], acc);
+                        rows[lr * SM_ROW + MAX_NF + k] = acc;
+                    }
+                }
+            }
         }
     }
     __syncthreads();
-    // phase 2: frequency taps, 8 consecutive outputs per work item
-    for (int w = tid; w < MASK_TILE * 65; w += 256) {
-        const int lf = w / 65, seg = w - lf * 65;
-        const int f = f0 + lf;
-        if (f >= ch.n_frames) continue;
+    const int nf = taps.nf;
+    for (int wi = tid; wi < NS_TILE * 65; wi += NSM_THREADS) {
+        const int lr = wi / 65, seg = wi - lr * 65;
+        const int f = base + lr;
+        if (f >= F) continue;
         const int k0 = 8 * seg;
         float out[8];
-        freq_taps8(&rows[lf][MAX_NF + k0], nf, taps.vf, out);
+        freq_taps8(&rows[lr * SM_ROW + MAX_NF + k0], nf, taps.vf, out);
         float* dst = M + (ch.row0 + f) * M_PITCH + k0;
-#pragma unroll
-        for (int o = 0; o < 8; ++o) {
-            if (k0 + o < NBIN) dst[o] = out[o];
+        if (k0 + 8 <= NBIN) {
+            *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(out[4], out[5], out[6], out[7]);
+        } else {
+            dst[0] = out[0];                                      // bin 512
         }
     }
+}
+
+template <int NT>
+static void launch_sm(dim3 grid, cudaStream_t st, const uint32_t* bits, const uint8_t* rowflag, const Chunk* chunks, float prop,
+                      const SmoothTaps& taps, float* M) {
+    cudaFuncSetAttribute(smooth_mask_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NSM_SMEM);
+    smooth_mask_kernel<NT><<<grid, NSM_THREADS, NSM_SMEM, st>>>(bits, rowflag, chunks, prop, taps, M);
 }
 
 void launch_smooth_mask(const uint32_t* bits, const uint8_t* rowflag, const Chunk* chunks, int n_chunks,
                         int max_frames, float prop, const SmoothTaps& taps, float* M, cudaStream_t st) {
     if (n_chunks <= 0) return;
-    const int tiles = (max_frames + MASK_TILE - 1) / MASK_TILE;
+    const int tiles = (max_frames + NS_TILE - 1) / NS_TILE;
     for (int y0 = 0; y0 < n_chunks; y0 += 32768) {
         const int ny = n_chunks - y0 < 32768 ? n_chunks - y0 : 32768;
         dim3 grid(tiles, ny);
-        smooth_mask_kernel<<<grid, 256, 0, st>>>(bits, rowflag + (long long)y0 * M_PITCH, chunks + y0, prop, taps, M);
+        const uint8_t* rf = rowflag + (long long)y0 * M_PITCH;
+        switch (taps.nt) {
+            case 1: launch_sm<1>(grid, st, bits, rf, chunks + y0, prop, taps, M); break;
+            case 2: launch_sm<2>(grid, st, bits, rf, chunks + y0, prop, taps, M); break;
+            case 3: launch_sm<3>(grid, st, bits, rf, chunks + y0, prop, taps, M); break;
+            case 4: launch_sm<4>(grid, st, bits, rf, chunks + y0, prop, taps, M); break;
+            case 5: launch_sm<5>(grid, st, bits, rf, chunks + y0, prop, taps, M); break;
+            case 6: launch_sm<6>(grid, st, bits, rf, chunks + y0, prop, taps, M); break;
+            case 7: launch_sm<7>(grid, st, bits, rf, chunks + y0, prop, taps, M); break;
+            case 8: launch_sm<8>(grid, st, bits, rf, chunks + y0, prop, taps, M); break;
+            default: launch_sm<9>(grid, st, bits, rf, chunks + y0, prop, taps, M); break;
+        }
     }
 }
 
