@@ -17,8 +17,16 @@ constexpr int P_PITCH = 201;
 constexpr size_t LOGMEL_SMEM = sizeof(float) * MEL_SPAN + sizeof(c32) * MEL_TILE * Z_PITCH + sizeof(float) * MEL_TILE * P_PITCH +
                                sizeof(float) * W_NFFT + sizeof(c32) * 200 + sizeof(c32) * 208 + sizeof(int) * 3 * 32 + sizeof(float4) * MEL_WQ_MAX;
 
-__global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__ den16, const Item* __restrict__ items, Consts cs,
-                                                     MelBank mel, int padding, int peak_normalize,
+struct MelTile {            // geometry of one (item, 32-frame tile) unit
+    int item, lf0;
+    long long i0, l0, own_lo, own_hi;
+    bool last_tile, interior;
+};
+
+// Persistent CTAs (two per SM) walk the (item, tile) list: the tables are loaded once per CTA, and the raw samples of
+// the NEXT tile are fetched into registers before the current tile's FFT phases, so no global-load latency is exposed.
+__global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__ den16, const Item* __restrict__ items, int n_items,
+                                                     int max_tiles, Consts cs, MelBank mel, int padding, int peak_normalize,
                                                      const PeakNorm* __restrict__ pnorm, const Gate* __restrict__ gates,
                                                      int16_t* __restrict__ out16, float* __restrict__ mel_out,
                                                      int* __restrict__ mel_max, int* __restrict__ tile_min) {
@@ -33,33 +41,41 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     int* m_qstart = reinterpret_cast<int*>(m_wq + MEL_WQ_MAX);
     int* m_qcount = m_qstart + 32;
     int* m_qoff = m_qcount + 32;
-
-    const int item = blockIdx.y;
-    const Item it = items[item];
-    const int lf0 = blockIdx.x * MEL_TILE;                       // first frame of the tile, item-relative
-    if (lf0 >= it.mel_frames) return;
     const int tid = threadIdx.x;
 
-    // geometry of the tile's sample span; on the interior fast path the 16-byte sample loads are issued first so that their
-    // latency overlaps the table prologue
-    const int16_t* x = den16 + it.den_off;
-    const long long i0 = ((long long)it.mel_f0 + lf0) * W_HOP - W_NFFT / 2;
-    const bool last_tile = lf0 + MEL_TILE >= it.mel_frames;
-    const long long own_lo = i0 + W_NFFT / 2;
-    const long long own_hi = last_tile ? it.g0 + it.own_len : own_lo + (long long)MEL_TILE * W_HOP;
-    const long long l0 = i0 - it.g0;                                // item-relative index of span[0]
-    const bool interior = i0 >= 0 && i0 + MEL_SPAN <= it.n_global && l0 >= -(long long)it.lo_avail &&
-                          l0 + MEL_SPAN <= it.own_len + it.hi_avail && ((it.den_off + l0) & 7) == 0 && !last_tile &&
-                          (!out16 || (((it.out_off + l0) & 7) == 0 && l0 + W_NFFT / 2 >= 0 && l0 + W_NFFT / 2 + MEL_TILE * W_HOP <= it.own_len));
+    const long long total = (long long)n_items * max_tiles;
+    auto geom = [&](long long t, MelTile& g) {
+        g.item = (int)(t / max_tiles);
+        g.lf0 = (int)(t % max_tiles) * MEL_TILE;
+        const Item& it = items[g.item];
+        if (g.lf0 >= it.mel_frames) return false;
+        g.i0 = ((long long)it.mel_f0 + g.lf0) * W_HOP - W_NFFT / 2;
+        g.last_tile = g.lf0 + MEL_TILE >= it.mel_frames;
+        g.own_lo = g.i0 + W_NFFT / 2;
+        g.own_hi = g.last_tile ? it.g0 + it.own_len : g.own_lo + (long long)MEL_TILE * W_HOP;
+        g.l0 = g.i0 - it.g0;                                        // item-relative index of span[0]
+        g.interior = g.i0 >= 0 && g.i0 + MEL_SPAN <= it.n_global && g.l0 >= -(long long)it.lo_avail &&
+                     g.l0 + MEL_SPAN <= it.own_len + it.hi_avail && ((it.den_off + g.l0) & 7) == 0 && !g.last_tile &&
+                     (!out16 || (((it.out_off + g.l0) & 7) == 0 && g.l0 + W_NFFT / 2 >= 0 && g.l0 + W_NFFT / 2 + MEL_TILE * W_HOP <= it.own_len));
+        return true;
+    };
     constexpr int PRE = (MEL_SPAN / 8 + 255) / 256;                 // 16-byte groups per thread
     uint4 pre[PRE];
-    if (interior) {
+    auto fetch = [&](const MelTile& g) {                            // interior fast path only: raw samples -> registers
+        if (!g.interior) return;
+        const int16_t* x = den16 + items[g.item].den_off + g.l0;
 #pragma unroll
         for (int u = 0; u < PRE; ++u) {
             const int gq = tid + 256 * u;
-            if (gq < MEL_SPAN / 8) pre[u] = *reinterpret_cast<const uint4*>(x + l0 + 8 * gq);
+            if (gq < MEL_SPAN / 8) pre[u] = *reinterpret_cast<const uint4*>(x + 8 * gq);
         }
-    }
+    };
+
+    long long t = blockIdx.x;
+    MelTile cur, nxt;
+    while (t < total && !geom(t, cur)) t += gridDim.x;
+    if (t >= total) return;
+    fetch(cur);
 
     for (int i = tid; i < W_NFFT; i += 256) win[i] = cs.win400[i];
     for (int i = tid; i < 200; i += 256) twA[i] = cs.twA[i];
@@ -67,19 +83,25 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     for (int i = tid; i < mel.n_wq; i += 256) m_wq[i] = mel.wq[i];
     for (int i = tid; i < 201; i += 256) tw400[i] = cs.tw400[i];
 
+  while (t < total) {
+    const int item = cur.item;
+    const Item it = items[item];
+    const int lf0 = cur.lf0;
     PeakNorm pnv; pnv.active = 0;
     if (peak_normalize) pnv = pnorm[item];
     const bool pn = pnv.active != 0;
     Gate gt; gt.applied = 0;
     if (gates) gt = gates[item];
+    const int16_t* x = den16 + it.den_off;
     const long long np_global = it.n_global + padding;            // length of the zero-padded recording
-    __syncthreads();
+    const long long i0 = cur.i0, l0 = cur.l0, own_lo = cur.own_lo, own_hi = cur.own_hi;
+    __syncthreads();                                              // tables ready / previous tile's shared memory free
 
     // Stage the tile's samples: global index i = 160 f - 200 + e, reflected at the true ends of the zero-padded
     // recording.  The tile also writes the final PCM of the 32 hops it is centred on (the last tile up to the item's
     // end: with padding 0 the tail N mod 160 plus the last hop still lies inside its span).
     {
-        if (interior) {
+        if (cur.interior) {
             // fast path: no reflection, no padding, 16-byte loads and stores (i0, own_lo and the hop are multiples of 8)
 #pragma unroll
             for (int u = 0; u < PRE; ++u) {
@@ -127,6 +149,10 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
             }
         }
     }
+    // next unit of this CTA: its raw samples travel while this tile is transformed
+    long long tn = t + gridDim.x;
+    while (tn < total && !geom(tn, nxt)) tn += gridDim.x;
+    if (tn < total) fetch(nxt);
     __syncthreads();
 
     // stage A: (frame, j) -> 8-point FFT over m of z[j + 25 m], twiddle, store
@@ -208,9 +234,11 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
         bmin = fminf(bmin, __shfl_xor_sync(0xffffffffu, bmin, 1));
         if (lane == 0 && bmax > -INFINITY) {
             atomicMax(&mel_max[item], float_to_ordered(bmax));
-            atomicMin(&tile_min[(long long)item * gridDim.x + blockIdx.x], float_to_ordered(bmin));
+            atomicMin(&tile_min[(long long)item * max_tiles + lf0 / MEL_TILE], float_to_ordered(bmin));
         }
     }
+    t = tn; cur = nxt;
+  }
 }
 
 void launch_logmel(const int16_t* den16, const Item* items, int n_items, int max_tiles, const Consts& c,
@@ -219,13 +247,12 @@ void launch_logmel(const int16_t* den16, const Item* items, int n_items, int max
     if (n_items <= 0) return;
     cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOGMEL_SMEM);
     if (max_tiles < 1) max_tiles = 1;
-    for (int y0 = 0; y0 < n_items; y0 += 32768) {
-        const int ny = n_items - y0 < 32768 ? n_items - y0 : 32768;
-        dim3 grid(max_tiles, ny);
-        logmel_kernel<<<grid, 256, LOGMEL_SMEM, st>>>(den16, items + y0, c, mel, padding, peak_normalize,
-                                                      pnorm ? pnorm + y0 : nullptr, gates ? gates + y0 : nullptr, out16,
-                                                      mel_out, mel_max + y0, tile_min + (long long)y0 * max_tiles);
-    }
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    const long long total = (long long)n_items * max_tiles;
+    const int grid = (int)(total < 2LL * n_sm ? total : 2LL * n_sm);
+    logmel_kernel<<<grid, 256, LOGMEL_SMEM, st>>>(den16, items, n_items, max_tiles, c, mel, padding, peak_normalize, pnorm, gates, out16,
+                                                  mel_out, mel_max, tile_min);
 }
 
 // whisper.audio.log_mel_spectrogram: log_spec = maximum(log_spec, log_spec.max() - 8.0); (log_spec + 4.0) / 4.0.
