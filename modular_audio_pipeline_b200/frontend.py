@@ -274,9 +274,12 @@ class HostPipeline:
     (final int16 PCM, float32 log-mel, float64 LUFS) in the plan's layouts.
     """
 
-    def __init__(self, fe: FrontEnd, lengths: Sequence[int], depth: int = 2, **plan_kw):
+    def __init__(self, fe: FrontEnd, lengths: Sequence[int], depth: int = 2, mel_to_host: bool = True, **plan_kw):
         self.fe = fe
         self.depth = depth
+        # mel_to_host=False keeps the log-mel on the device (``d_mel[slot]``) for the hand-off into a Whisper encoder on the
+        # same GPU (transcriber.py adapters); only the final PCM and the LUFS travel back over PCIe
+        self.mel_to_host = mel_to_host
         self.plans = [fe.plan(lengths, **plan_kw) for _ in range(depth)]
         p0 = self.plans[0]
         dev = fe.device
@@ -300,7 +303,7 @@ class HostPipeline:
     @property
     def d2h_bytes(self) -> int:
         p = self.plans[0]
-        return 2 * p.total_out + 4 * p.total_mel + 8 * p.n_items
+        return 2 * p.total_out + (4 * p.total_mel if self.mel_to_host else 0) + 8 * p.n_items
 
     def submit(self) -> int:
         """Process the batch currently in ``h_in[slot]`` (slot = submission count mod depth).  Returns the slot."""
@@ -312,7 +315,7 @@ class HostPipeline:
             self.d_in[slot].copy_(self.h_in[slot], non_blocking=True)
             res = plan.process(self.d_in[slot], out_pcm=self.d_out[slot], mel=self.d_mel[slot] if plan.params.n_mels else None)
             self.h_out[slot].copy_(self.d_out[slot], non_blocking=True)
-            if plan.params.n_mels:
+            if plan.params.n_mels and self.mel_to_host:
                 self.h_mel[slot].copy_(self.d_mel[slot], non_blocking=True)
             self.h_lufs[slot].copy_(res.lufs, non_blocking=True)
             self.done[slot].record(st)
