@@ -327,7 +327,8 @@ class HostPipeline:
     def results(self, slot: int):
         self.done[slot].synchronize()
         p = self.plans[slot]
-        return p.split_out(self.h_out[slot]), (p.split_mel(self.h_mel[slot]) if p.params.n_mels else []), self.h_lufs[slot]
+        mel_src = self.h_mel[slot] if self.mel_to_host else self.d_mel[slot]       # device tensors when the mel is handed over on the GPU
+        return p.split_out(self.h_out[slot]), (p.split_mel(mel_src) if p.params.n_mels else []), self.h_lufs[slot]
 
     def drain(self) -> None:
         for e in self.done:

@@ -264,6 +264,25 @@ def test_host_pipeline_overlap_matches_device(frontend):
     pipe.drain()
 
 
+def test_host_pipeline_device_handoff(frontend):
+    """mel_to_host=False: PCM and LUFS come back in pinned host memory, the log-mel stays a CUDA tensor."""
+    from modular_audio_pipeline_b200 import HostPipeline
+    clips = [gen(10, 40), gen(7.5, 41)]
+    lengths = [c.numel() for c in clips]
+    pipe = HostPipeline(frontend, lengths, depth=3, mel_to_host=False, n_mels=128, mel_padding=160)
+    plan = frontend.plan(lengths, n_mels=128, mel_padding=160)
+    want = plan.process(plan.pack(clips))
+    slot = pipe.next_slot()
+    pipe.plans[slot].pack(clips, out=pipe.h_in[slot])
+    pipe.submit()
+    out, mel, lufs = pipe.results(slot)
+    assert pipe.d2h_bytes == 2 * plan.total_out + 8 * len(clips)
+    for i in range(2):
+        assert mel[i].is_cuda and torch.equal(mel[i], want.log_mel[i])
+        assert not out[i].is_cuda and torch.equal(out[i], want.pcm[i].cpu())
+    assert torch.equal(lufs, want.lufs.cpu())
+
+
 # ---- other sample rates: the kernels' generic paths (time taps nt = 1 / 9, frequency taps nf = 32 / 5, loudness
 # ---- segmentation for 800- / 4800-sample sub-blocks, serial frame statistics) ---------------------------------
 @pytest.mark.parametrize("sr,seconds", [(8000, 40.0), (48000, 20.0), (22050, 15.0)])
