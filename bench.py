@@ -146,19 +146,54 @@ def stage_bytes(plan, lengths, stationary, n_mels, padding):
     return b
 
 
-def cpu_reference_rate(wl, sample_seconds, seed=1, repeats=1):
-    """Audio-s/s of the CPU oracle (restated reference path) on `sample_seconds` of the workload's audio."""
+def _cpu_worker(conn, wl, sample_seconds, seed):
+    """One host thread of the CPU baseline: owns one recording, runs the oracle front-end on it on request."""
+    import torch as _torch
+    _torch.set_num_threads(1)
     from modular_audio_pipeline_b200.synth import speech_noise
     from oracle import reference_path as O
     desc, seconds, per_gpu, stationary, n_mels, padding, meeting = WORKLOADS[wl]
     pcm = speech_noise(min(sample_seconds, seconds), seed, meeting=meeting).numpy()
-    best = None
-    for _ in range(repeats):
+    conn.send(len(pcm) / SR)
+    while conn.recv() == "go":
         t0 = time.perf_counter()
         O.front_end(pcm, SR, stationary, n_mels, padding)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return len(pcm) / SR / best, len(pcm) / SR, best
+        conn.send(time.perf_counter() - t0)
+
+
+class CpuPool:
+    """The CPU arm: the oracle (restated reference path; `kind: "port"`) on ALL host threads the process may use -- one
+    single-threaded worker process per core, each with its own recording of the workload's kind; a step = every worker
+    processes its recording once, concurrently."""
+
+    def __init__(self, wl, sample_seconds, n_workers=None):
+        import multiprocessing as mp
+        ctx = mp.get_context("spawn")                      # the parent may hold a CUDA context: never fork it
+        self.n = n_workers or max(1, len(os.sched_getaffinity(0)))
+        self.conns, self.procs = [], []
+        for i in range(self.n):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_cpu_worker, args=(b, wl, sample_seconds, 1000 + i), daemon=True)
+            p.start()
+            self.conns.append(a); self.procs.append(p)
+        self.audio_s = sum(c.recv() for c in self.conns)   # workers report the seconds they hold once they are ready
+
+    def step(self):
+        t0 = time.perf_counter()
+        for c in self.conns:
+            c.send("go")
+        for c in self.conns:
+            c.recv()
+        return time.perf_counter() - t0
+
+    def close(self):
+        for c in self.conns:
+            try:
+                c.send("stop")
+            except Exception:
+                pass
+        for p in self.procs:
+            p.join(timeout=10)
 
 
 def run_reference(args):
@@ -167,21 +202,22 @@ def run_reference(args):
         return
     desc, seconds, per_gpu, stationary, n_mels, padding, meeting = WORKLOADS[args.workload]
     sample = min(seconds, args.cpu_sample)
+    pool = CpuPool(args.workload, sample)
     times = []
     for i in range(args.warmup + args.steps):
-        rate, secs, dt = cpu_reference_rate(args.workload, sample, seed=1)
+        dt = pool.step()
         if i >= args.warmup:
             times.append(dt)
+    pool.close()
     ms = 1e3 * float(np.mean(times))
-    value = sample / (ms / 1e3)
-    cores = len(os.sched_getaffinity(0))
+    value = pool.audio_s / (ms / 1e3)
     line = {"impl": "reference", "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "sample": f"first {sample:.0f} s of one recording per step"},
-            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample:.0f} s of the workload audio, oracle/reference_path.front_end, "
-                                       f"torch threads {torch.get_num_threads()}"},
+            "config": {"workload": desc, "sample": f"{pool.n} recordings of {sample:.0f} s per step, one per host thread"},
+            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": pool.n, "kind": "port",
+                             "sample": f"{pool.n} x {sample:.0f} s of the workload audio per step through oracle/reference_path.front_end, "
+                                       f"one single-threaded process per host thread"},
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -193,7 +229,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample", type=float, default=600.0, help="seconds of audio the CPU baseline processes")
+    ap.add_argument("--cpu-sample", type=float, default=120.0, help="seconds of audio EACH host thread of the CPU baseline processes per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -342,11 +378,15 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        sample = min(seconds * per_gpu, args.cpu_sample)
-        rate, secs, dt = cpu_reference_rate(args.workload, sample)
-        cpu = {"value": rate, "unit": "audio-s/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
-               "sample": f"first {secs:.0f} s of the same workload through oracle/reference_path.front_end ({dt:.2f} s wall, "
-                         f"torch threads {torch.get_num_threads()}, os.cpu_count {os.cpu_count()})"}
+        sample = min(seconds, args.cpu_sample)
+        pool = CpuPool(args.workload, sample)
+        pool.step()                                        # warm-up (page-in, FFT plans)
+        dts = [pool.step() for _ in range(2)]
+        pool.close()
+        dt = min(dts)
+        cpu = {"value": pool.audio_s / dt, "unit": "audio-s/s", "cores": pool.n, "kind": "port",
+               "sample": f"{pool.n} x {sample:.0f} s of the same workload through oracle/reference_path.front_end, one single-threaded "
+                         f"process per host thread ({dt:.2f} s wall per step, os.cpu_count {os.cpu_count()})"}
 
     if rank == 0:
         line = {"metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
