@@ -148,6 +148,14 @@ int maf_ms_energy(maf_ctx* ctx, const int16_t* pcm_dev, int64_t n, int32_t sampl
 int maf_silence_flags(maf_ctx* ctx, const uint64_t* bucket_dev, int64_t n, int32_t sample_rate, int64_t n_starts, int32_t window_ms,
                       double thresh, uint8_t* flags_dev, void* stream);
 
+/* ---- front door of AudioPreprocessor.normalize_audio for 16-bit input that is not yet mono at the target rate
+ * (preprocessor.py:227-233: pydub normalize(seg).set_frame_rate(sr).set_channels(1) -> audioop.max / mul / ratecv /
+ * tomono, in this order).  pcm_dev holds n_frames_in interleaved frames of `channels` (1 or 2) int16 samples;
+ * out_dev receives maf_front_door_out_len() mono samples at out_rate.  peak_normalize = 0 skips the normalise. */
+int64_t maf_front_door_out_len(int64_t n_frames_in, int32_t in_rate, int32_t out_rate);
+int maf_front_door(maf_ctx* ctx, const int16_t* pcm_dev, int64_t n_frames_in, int32_t channels, int32_t in_rate, int32_t out_rate,
+                   int32_t peak_normalize, int16_t* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

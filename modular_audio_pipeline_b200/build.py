@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmaf_b200.so")
-SOURCES = ["noise_detect.cu", "stft_denoise.cu", "loudness.cu", "logmel.cu", "silence.cu", "capi.cu"]
+SOURCES = ["noise_detect.cu", "stft_denoise.cu", "loudness.cu", "logmel.cu", "silence.cu", "front_door.cu", "capi.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

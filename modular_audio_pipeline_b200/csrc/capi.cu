@@ -854,3 +854,26 @@ extern "C" int maf_silence_flags(maf_ctx* ctx, const uint64_t* bucket, int64_t n
     CU(cudaGetLastError());
     return MAF_OK;
 }
+
+// ---- front door ------------------------------------------------------------------------------------------------
+static long long gcd_ll(long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return a; }
+
+extern "C" int64_t maf_front_door_out_len(int64_t n_frames_in, int32_t in_rate, int32_t out_rate) {
+    if (n_frames_in <= 0 || in_rate <= 0 || out_rate <= 0) return 0;
+    if (in_rate == out_rate) return n_frames_in;
+    const long long g = gcd_ll(in_rate, out_rate);
+    return ((n_frames_in - 1) * (out_rate / g)) / (in_rate / g) + 1;
+}
+
+extern "C" int maf_front_door(maf_ctx* ctx, const int16_t* pcm, int64_t n_frames_in, int32_t channels, int32_t in_rate, int32_t out_rate,
+                              int32_t peak_normalize, int16_t* out, void* stream) {
+    if (!ctx || !pcm || !out || n_frames_in <= 0) return fail(MAF_ERR_INVALID, "maf_front_door: bad argument");
+    if (channels != 1 && channels != 2) return fail(MAF_ERR_UNSUPPORTED, "maf_front_door: 1 or 2 channels");
+    if (in_rate <= 0 || out_rate <= 0) return fail(MAF_ERR_INVALID, "maf_front_door: bad rate");
+    CU(cudaSetDevice(ctx->device));
+    const long long g = gcd_ll(in_rate, out_rate);
+    launch_front_door(pcm, n_frames_in, channels, in_rate / g, out_rate / g, (int*)ctx->scratch, 32768.0 * pow(10.0, -0.1 / 20.0),
+                      peak_normalize, out, maf_front_door_out_len(n_frames_in, in_rate, out_rate), (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return MAF_OK;
+}

@@ -56,6 +56,25 @@ class FrontEnd:
         self._h = h
         self._plans = weakref.WeakSet()
 
+    def front_door(self, pcm: torch.Tensor, channels: int, in_rate: int, out_rate: int, normalize: bool = True) -> torch.Tensor:
+        """normalize_audio's conversions for 16-bit input that is not yet mono at the target rate (preprocessor.py:227-233:
+        pydub normalize -> set_frame_rate -> set_channels(1), i.e. audioop.max / mul / ratecv / tomono): interleaved int16
+        CUDA tensor in, mono int16 CUDA tensor at ``out_rate`` out."""
+        if pcm.dtype != torch.int16 or not pcm.is_cuda or not pcm.is_contiguous():
+            raise MafError("front_door: contiguous int16 CUDA tensor expected")
+        if channels not in (1, 2) or pcm.numel() % channels:
+            raise MafError("front_door: 1 or 2 interleaved channels expected")
+        n_in = pcm.numel() // channels
+        n_out = int(self._lib.maf_front_door_out_len(n_in, int(in_rate), int(out_rate)))
+        out = torch.empty(max(n_out, 1), dtype=torch.int16, device=self.device)
+        if n_in > 0:
+            with torch.cuda.device(self.device):
+                rc = self._lib.maf_front_door(self._h, pcm.data_ptr(), n_in, int(channels), int(in_rate), int(out_rate), int(bool(normalize)),
+                                              out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+            if rc:
+                raise MafError(self._lib.maf_last_error().decode())
+        return out[:n_out]
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             for p in list(self._plans):          # plans point into the context: release them first

@@ -162,9 +162,10 @@ class GpuAudioPreprocessor:
     def normalize_audio(self, input_wav: str) -> str:
         """preprocessor.py:216-242: pydub peak normalise (-0.1 dBFS), then mono / 16-bit at the target rate.
 
-        16-bit input at the target rate is the pipeline's contract (media_handler.py:219-223); multi-channel input is
-        downmixed with audioop.tomono semantics after the normalise, like pydub's call order.  Other sample rates or
-        widths are outside this path's scope and raise AudioProcessingError."""
+        16-bit mono input at the target rate (the pipeline's contract, media_handler.py:219-223) takes the plan's peak
+        normalise; stereo input and / or another sample rate go through the front-door kernel, which reproduces pydub's
+        call order over audioop: max / mul on the interleaved samples, ratecv, tomono.  Other sample widths and more than
+        two channels raise AudioProcessingError."""
         try:
             hit = self._resident.get(input_wav)
             if hit is not None and os.path.exists(input_wav) and os.path.getmtime(input_wav) == hit[2]:
@@ -174,13 +175,14 @@ class GpuAudioPreprocessor:
                 if width != 2:
                     raise ValueError(f"unsupported sample width {width} (16-bit PCM expected)")
                 x = torch.frombuffer(bytearray(raw), dtype=torch.int16).to(self.frontend.device)
-            if sr != self.sample_rate:
-                raise ValueError(f"sample rate {sr} != target {self.sample_rate}: resampling is not part of this path")
-            plan = self.frontend.plan([x.numel()], sample_rate=sr, n_mels=0)
-            y = plan.peak_normalize(plan.pack([x]))[0].clone()
-            plan.close()
-            if ch > 1:   # audioop.tomono(0.5, 0.5): floor of the mean, per frame
-                y = torch.floor(y.view(-1, ch).to(torch.float64).mean(dim=1)).to(torch.int16)
+            if sr != self.sample_rate or ch > 1:
+                if ch > 2:
+                    raise ValueError(f"{ch} channels: only mono / stereo input is supported")
+                y = self.frontend.front_door(x.contiguous(), ch, sr, self.sample_rate, normalize=True)
+            else:
+                plan = self.frontend.plan([x.numel()], sample_rate=sr, n_mels=0)
+                y = plan.peak_normalize(plan.pack([x]))[0].clone()
+                plan.close()
         except Exception as e:
             raise AudioProcessingError("Audio normalization failed", details=str(e))
         out_path = os.path.join(self.temp_dir, f"{Path(input_wav).stem}_norm.wav")

@@ -404,6 +404,59 @@ def front_end(pcm: np.ndarray, sr: int = 16000, stationary: bool = True, n_mels:
             "loud_i16": loud16, "lufs": lufs, "applied": applied, "log_mel": mel}
 
 
+
+# ------------------------------------------------------------------------------------------------------------------
+# Front door: what normalize_audio does to a WAV that is not yet 16-bit mono at the target
+# rate -- preprocessor.py:227-233: normalize(seg).set_frame_rate(sr).set_channels(1).set_sample_width(2), i.e. pydub over
+# stdlib audioop, in this order: audioop.max / audioop.mul on the interleaved samples, audioop.ratecv(data, 2, channels,
+# in_rate, out_rate, None) (weights 1, 0), audioop.tomono(data, 2, 0.5, 0.5).  Restated from CPython's Modules/audioop.c:
+#   ratecv  rates divided by their gcd; d starts at -outrate; every input frame adds outrate; while d >= 0 an output frame
+#           (int)((prev * d + cur * (outrate - d)) / outrate) is emitted (double arithmetic on the samples scaled to 32 bit,
+#           truncation toward zero, high 16 bits kept) and d -= inrate.  Closed form: output m reads input n = ceil(m in / out)
+#           with d = n out - m in, so there are floor((N - 1) out / in) + 1 outputs.
+#   tomono  floor(fbound(l * 0.5 + r * 0.5)).
+# ------------------------------------------------------------------------------------------------------------------
+def ratecv(pcm: np.ndarray, channels: int, in_rate: int, out_rate: int) -> np.ndarray:
+    """audioop.ratecv(pcm.tobytes(), 2, channels, in_rate, out_rate, None)[0] for int16 interleaved input."""
+    import math
+    x = np.asarray(pcm, dtype=np.int16).reshape(-1, channels)
+    g = math.gcd(in_rate, out_rate)
+    inr, outr = in_rate // g, out_rate // g
+    n_in = x.shape[0]
+    if n_in == 0:
+        return np.zeros(0, dtype=np.int16)
+    n_out = ((n_in - 1) * outr) // inr + 1
+    m = np.arange(n_out, dtype=np.int64)
+    n = -((-m * inr) // outr)                                   # ceil(m inr / outr)
+    d = (n * outr - m * inr).astype(np.float64)[:, None]
+    cur = x[n].astype(np.int64) << 16
+    prev = np.where((n > 0)[:, None], x[np.maximum(n - 1, 0)].astype(np.int64) << 16, 0)
+    val = (prev.astype(np.float64) * d + cur.astype(np.float64) * (float(outr) - d)) / float(outr)
+    out = np.trunc(val).astype(np.int64) >> 16                   # (int) cast, then the high 16 bits
+    return out.astype(np.int16).reshape(-1)
+
+
+def tomono(pcm: np.ndarray, channels: int) -> np.ndarray:
+    """pydub set_channels(1): audioop.tomono(data, 2, 0.5, 0.5) for stereo (floor of the mean); mono passes through."""
+    x = np.asarray(pcm, dtype=np.int16).reshape(-1, channels)
+    if channels == 1:
+        return x[:, 0].copy()
+    if channels != 2:
+        raise ValueError("only mono / stereo input is restated")
+    v = x[:, 0].astype(np.float64) * 0.5 + x[:, 1].astype(np.float64) * 0.5
+    return np.floor(np.clip(v, -32768.0, 32767.0)).astype(np.int16)
+
+
+def front_door(pcm: np.ndarray, channels: int, in_rate: int, out_rate: int, normalize: bool = True) -> np.ndarray:
+    """normalize_audio on arbitrary 16-bit input: peak normalise (interleaved), ratecv, tomono -> int16 mono at out_rate."""
+    x = np.asarray(pcm, dtype=np.int16).reshape(-1)
+    if normalize:
+        x = peak_normalize(x)
+    if in_rate != out_rate:
+        x = ratecv(x, channels, in_rate, out_rate)
+    return tomono(x, channels)
+
+
 # --------------------------------------------------------------------------------------------------------------
 # Next-row 1: remove_silence -- preprocessor.py:290-375 over pydub.silence / AudioSegment.append, restated on the
 # REAL stdlib audioop primitives pydub calls (audioop.rms / mul / add), per-millisecond loop exactly like pydub.

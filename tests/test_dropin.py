@@ -163,6 +163,26 @@ def test_explicit_noise_sample_and_quiet_passthrough(tmp_path, frontend):
 
 
 @pytest.mark.gpu
+def test_normalize_audio_front_door_48k_stereo(tmp_path, frontend):
+    """normalize_audio on a 48 kHz stereo WAV (BASELINE config 5 input): pydub's normalize -> set_frame_rate(16000) ->
+    set_channels(1) chain over audioop, bit for bit (the oracle restatement is pinned against stdlib audioop)."""
+    from modular_audio_pipeline_b200.preprocessor import GpuAudioPreprocessor
+    left = speech_noise(6.0, 21, sr=48000).numpy()
+    right = np.roll(speech_noise(6.0, 22, sr=48000, sigma=0.05).numpy(), 777)
+    inter = np.stack([left, right], axis=1).reshape(-1)
+    _write_wav(tmp_path / "st48.wav", inter, sr=48000, channels=2)
+    pre = GpuAudioPreprocessor(SR, str(tmp_path / "tmp"))
+    out, sr, ch = _read_wav(pre.normalize_audio(str(tmp_path / "st48.wav")))
+    assert (sr, ch) == (SR, 1)
+    assert np.array_equal(out, O.front_door(inter, 2, 48000, SR))
+    # and the rest of the chain runs on the result
+    loud, _, _ = _read_wav(pre.normalize_loudness(pre.normalize_audio(str(tmp_path / "st48.wav"))))
+    want16, _, _ = O.normalize_loudness(O.front_door(inter, 2, 48000, SR), SR)
+    d = np.abs(loud.astype(np.int32) - want16.astype(np.int32))
+    assert d.max() <= 1 and np.mean(d != 0) <= 5e-3
+
+
+@pytest.mark.gpu
 def test_transcriber_adapter_with_fake_models(frontend):
     from modular_audio_pipeline_b200.transcriber import GpuFrontEndTranscriber, GpuLogMelFrontEnd
     x = speech_noise(3, 1)

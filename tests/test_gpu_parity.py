@@ -315,3 +315,18 @@ def test_loudness_parity_other_rates(frontend, sr, seconds):
     # truncation of ~0.2 % of them by one LSB
     d = np.abs(out[0].cpu().numpy().astype(np.int32) - want16.astype(np.int32))
     assert d.max() <= 1 and np.mean(d != 0) <= 5e-3
+
+
+# ---- front door of normalize_audio: peak normalise -> ratecv -> tomono, bit-exact vs the oracle -----
+@pytest.mark.parametrize("channels", [1, 2])
+@pytest.mark.parametrize("in_rate,out_rate", [(48000, 16000), (44100, 16000), (22050, 16000), (8000, 16000), (16000, 16000)])
+def test_front_door_bit_exact(frontend, channels, in_rate, out_rate):
+    rng = np.random.default_rng(channels * 100003 + in_rate)
+    n = 3 * in_rate + 17
+    x = (rng.standard_normal(n * channels) * 6000).clip(-32768, 32767).astype(np.int16)
+    want = O.front_door(x, channels, in_rate, out_rate)
+    got = frontend.front_door(torch.from_numpy(x).to(frontend.device), channels, in_rate, out_rate)
+    assert got.shape[0] == want.shape[0]
+    assert np.array_equal(got.cpu().numpy(), want)
+    raw = frontend.front_door(torch.from_numpy(x).to(frontend.device), channels, in_rate, out_rate, normalize=False)
+    assert np.array_equal(raw.cpu().numpy(), O.front_door(x, channels, in_rate, out_rate, normalize=False))

@@ -114,3 +114,27 @@ def test_loudness_glue_semantics():
     with pytest.raises(ValueError):
         O.integrated_loudness(np.zeros(100, dtype=np.float32), SR)
     assert list(O.to_int16_trunc(np.array([1.7, -1.7, 40000.0], dtype=np.float32))) == [1, -1, -25536]
+
+
+def test_front_door_restatement_matches_stdlib_audioop():
+    """ratecv / tomono / the normalize_audio chain (preprocessor.py:227-233) against the REAL audioop pydub calls."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        audioop = pytest.importorskip("audioop")
+    rng = np.random.default_rng(0)
+    for ch in (1, 2):
+        for a, b in [(48000, 16000), (44100, 16000), (22050, 16000), (8000, 16000), (32000, 16000), (11025, 16000)]:
+            for n in (1, 2, 5, 1000, 48001):
+                x = rng.integers(-32768, 32768, size=n * ch).astype(np.int16)
+                want = np.frombuffer(audioop.ratecv(x.tobytes(), 2, ch, a, b, None)[0], dtype=np.int16)
+                assert np.array_equal(want, O.ratecv(x, ch, a, b)), (ch, a, b, n)
+    x = rng.integers(-20000, 20000, size=2 * 30011).astype(np.int16)
+    assert np.array_equal(np.frombuffer(audioop.tomono(x.tobytes(), 2, 0.5, 0.5), dtype=np.int16), O.tomono(x, 2))
+    # the whole chain as pydub runs it: max -> mul -> ratecv -> tomono
+    peak = audioop.max(x.tobytes(), 2)
+    f = O.peak_normalize_factor(peak)
+    y = audioop.mul(x.tobytes(), 2, f)
+    y = audioop.ratecv(y, 2, 2, 48000, 16000, None)[0]
+    y = np.frombuffer(audioop.tomono(y, 2, 0.5, 0.5), dtype=np.int16)
+    assert np.array_equal(y, O.front_door(x, 2, 48000, 16000))
