@@ -187,10 +187,23 @@ __device__ void radix_select2(const float* __restrict__ v, int n, int k, unsigne
             if (run) atomicAdd(&hist[cur], run);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned acc = 0; int d = 0;
-            for (; d < 256; ++d) { if (acc + hist[d] > (unsigned)kk) break; acc += hist[d]; }
-            scratch[0] = d; scratch[1] = acc;
+        if (threadIdx.x < 32) {
+            // first digit whose cumulative count exceeds kk: every lane sums 8 bins, warp scan, the crossing lane finishes
+            const int lane = threadIdx.x;
+            unsigned h[8], tot = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { h[j] = hist[8 * lane + j]; tot += h[j]; }
+            unsigned incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const unsigned excl = incl - tot;
+            const unsigned hit = __ballot_sync(0xffffffffu, incl > (unsigned)kk);
+            if (hit == 0) { if (lane == 31) { scratch[0] = 256; scratch[1] = incl; } }
+            else if (lane == __ffs(hit) - 1) {
+                unsigned acc = excl; int j = 0;
+                for (; j < 8; ++j) { if (acc + h[j] > (unsigned)kk) break; acc += h[j]; }
+                scratch[0] = 8 * lane + j; scratch[1] = acc;
+            }
         }
         __syncthreads();
         prefix |= scratch[0] << shift; mask |= 255u << shift; kk -= (int)scratch[1];
@@ -244,18 +257,32 @@ __global__ void __launch_bounds__(SEL_THREADS) select_clip_kernel(const float* _
             __syncthreads();
             for (int i = threadIdx.x; i < F; i += blockDim.x) atomicAdd(&hist[min(Z[i], 2047)], 1u);
             __syncthreads();
-            if (threadIdx.x == 0) {
-                double vi = __dmul_rn((double)(F - 1), 0.5);
-                double lo = floor(vi);
-                int k = (int)lo, k1 = min(k + 1, F - 1);
-                int ca = -1, cb = -1; unsigned acc = 0;
-                for (int d = 0; d < 2048; ++d) {
-                    acc += hist[d];
-                    if (ca < 0 && acc > (unsigned)k) ca = d;
-                    if (cb < 0 && acc > (unsigned)k1) { cb = d; break; }
+            if (threadIdx.x < 32) {
+                // order statistics k and k + 1 of the counts: lanes sum 64 bins each, warp scan, the crossing lanes finish
+                const int lane = threadIdx.x;
+                const double vi = __dmul_rn((double)(F - 1), 0.5);
+                const double lo = floor(vi);
+                const int k = (int)lo, k1 = min(k + 1, F - 1);
+                unsigned tot = 0;
+                for (int j = 0; j < 64; ++j) tot += hist[64 * lane + j];
+                unsigned incl = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                const unsigned excl = incl - tot;
+                int ca = -1, cb = -1;
+                if (excl <= (unsigned)k && incl > (unsigned)k) {
+                    unsigned acc = excl;
+                    for (int j = 0; j < 64; ++j) { acc += hist[64 * lane + j]; if (acc > (unsigned)k) { ca = 64 * lane + j; break; } }
                 }
-                double a = __ddiv_rn((double)ca, (double)frame_len), b = __ddiv_rn((double)cb, (double)frame_len);
-                thr[1] = __dmul_rn(np_lerp(a, b, __dsub_rn(vi, lo)), 0.5);
+                if (excl <= (unsigned)k1 && incl > (unsigned)k1) {
+                    unsigned acc = excl;
+                    for (int j = 0; j < 64; ++j) { acc += hist[64 * lane + j]; if (acc > (unsigned)k1) { cb = 64 * lane + j; break; } }
+                }
+                ca = __reduce_max_sync(0xffffffffu, ca); cb = __reduce_max_sync(0xffffffffu, cb);
+                if (lane == 0) {
+                    double a = __ddiv_rn((double)ca, (double)frame_len), b = __ddiv_rn((double)cb, (double)frame_len);
+                    thr[1] = __dmul_rn(np_lerp(a, b, __dsub_rn(vi, lo)), 0.5);
+                }
             }
         }
         __syncthreads();

@@ -402,10 +402,16 @@ __global__ void noise_finalize_kernel(const Clip* __restrict__ clips, const doub
     if (k >= NBIN) return;
     const int n = clips[item].n_frames;
     double s1 = 0.0, s2 = 0.0;
-    for (int p = 0; p < n_parts; ++p) {
-        const double* pr = partial + ((long long)item * n_parts + p) * (2 * T_PITCH);
-        s1 += pr[k]; s2 += pr[T_PITCH + k];
+    const double* pr0 = partial + (long long)item * n_parts * (2 * T_PITCH) + k;
+    int p = 0;
+    for (; p + 8 <= n_parts; p += 8) {                 // loads first (independent), fixed summation order kept
+        double a[8], b[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { a[u] = pr0[(long long)(p + u) * (2 * T_PITCH)]; b[u] = pr0[(long long)(p + u) * (2 * T_PITCH) + T_PITCH]; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { s1 += a[u]; s2 += b[u]; }
     }
+    for (; p < n_parts; ++p) { s1 += pr0[(long long)p * (2 * T_PITCH)]; s2 += pr0[(long long)p * (2 * T_PITCH) + T_PITCH]; }
     const double mean = s1 / n;
     double var = s2 / n - mean * mean;
     if (var < 0.0) var = 0.0;

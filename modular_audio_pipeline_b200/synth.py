@@ -40,3 +40,26 @@ def speech_noise(seconds: float, seed: int = 0, sr: int = 16000, sigma: float = 
         x = 0.5 * (sig + noise)
         out[s:e] = torch.clamp(torch.round(x * 32768.0), -32768, 32767).to(torch.int16)
     return out
+
+
+def music_bed_stereo(seconds: float, seed: int = 0, sr: int = 48000, device: str | torch.device = "cpu") -> torch.Tensor:
+    """BASELINE config 5 input: interleaved stereo int16 at ``sr`` -- the speech generator in the left
+    channel, a "music bed" of three detuned sawtooth chords (amplitude 0.2) plus white noise (sigma 0.05) in both."""
+    n = int(round(seconds * sr))
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(7654321 + seed)
+    t = torch.arange(n, device=dev, dtype=torch.float64) / sr
+    bed = torch.zeros_like(t)
+    for root in (110.0, 164.81, 220.5):                         # three chords, each voice slightly detuned
+        for det in (0.997, 1.0, 1.004):
+            ph = (root * det * t) % 1.0
+            bed += (2.0 * ph - 1.0)
+    bed = 0.2 * bed / 9.0
+    speech = speech_noise(seconds, seed, sr=sr, device=dev).to(torch.float64) / 32768.0
+    out = torch.empty(n, 2, dtype=torch.int16, device=dev)
+    for c in range(2):
+        noise = torch.randn(n, generator=gen, device=dev, dtype=torch.float64) * 0.05
+        x = bed + noise + (speech if c == 0 else 0.0)
+        out[:, c] = torch.clamp(torch.round(0.5 * x * 32768.0), -32768, 32767).to(torch.int16)
+    return out.reshape(-1)
