@@ -106,11 +106,10 @@ extern "C" int maf_create(int device, maf_ctx** out) {
     for (int e = 0; e <= 512; ++e) t1024[e] = mk((float)cos(2 * PI * e / 1024), (float)-sin(2 * PI * e / 1024));
     for (int p = 0; p < 8; ++p) for (int j = 0; j < 25; ++j) t200[p * 25 + j] = mk((float)cos(2 * PI * (j * p) / 200), (float)-sin(2 * PI * (j * p) / 200));
     for (int e = 0; e <= 200; ++e) t400[e] = mk((float)cos(2 * PI * e / 400), (float)-sin(2 * PI * e / 400));
-    std::vector<c32> tww(1024); std::vector<float> winh(NFFT);
+    std::vector<c32> tww(1024);
     for (int j = 0; j < 32; ++j) for (int l = 0; l < 32; ++l) tww[j * 32 + l] = mk((float)cos(2 * PI * (l * j) / 1024), (float)-sin(2 * PI * (l * j) / 1024));
-    for (int i = 0; i < NFFT; ++i) winh[i] = (float)((0.5 - 0.5 * cos(2.0 * PI * i / NFFT)) / 1024.0);
     MelHost m80 = build_mel(80), m128 = build_mel(128);
-    size_t o_tww = put(tww.data(), tww.size() * 8), o_winh = put(winh.data(), winh.size() * 4);
+    size_t o_tww = put(tww.data(), tww.size() * 8);
     size_t o_win = put(win.data(), win.size() * 4), o_winv = put(winv.data(), winv.size() * 4), o_win4 = put(win4.data(), win4.size() * 4);
     size_t o_t512 = put(t512.data(), t512.size() * 8), o_t2 = put(t2.data(), t2.size() * 8), o_t1024 = put(t1024.data(), t1024.size() * 8);
     size_t o_t200 = put(t200.data(), t200.size() * 8), o_t400 = put(t400.data(), t400.size() * 8);
@@ -128,7 +127,7 @@ extern "C" int maf_create(int device, maf_ctx** out) {
     ctx->c.win1024 = (const float*)(b + o_win); ctx->c.winv1024 = (const float*)(b + o_winv); ctx->c.win400 = (const float*)(b + o_win4);
     ctx->c.tw1 = (const c32*)(b + o_t512); ctx->c.tw2 = (const c32*)(b + o_t2); ctx->c.tw1024 = (const c32*)(b + o_t1024);
     ctx->c.twA = (const c32*)(b + o_t200); ctx->c.tw400 = (const c32*)(b + o_t400);
-    ctx->c.tww = (const c32*)(b + o_tww); ctx->c.win1024h = (const float*)(b + o_winh);
+    ctx->c.tww = (const c32*)(b + o_tww);
     ctx->mel80 = MelBank{80, (int)m80.wq.size() / 4, (const int*)(b + o80[0]), (const int*)(b + o80[1]), (const int*)(b + o80[2]), (const float4*)(b + o80[3])};
     ctx->mel128 = MelBank{128, (int)m128.wq.size() / 4, (const int*)(b + o128[0]), (const int*)(b + o128[1]), (const int*)(b + o128[2]), (const float4*)(b + o128[3])};
     *out = ctx;
