@@ -7,7 +7,7 @@ __all__ = ["FrontEnd", "Plan", "GpuAudioPreprocessor", "GpuLogMelFrontEnd", "__v
 
 
 def __getattr__(name):
-    if name in ("FrontEnd", "Plan", "FrontEndResult", "HostPipeline", "MafError"):
+    if name in ("FrontEnd", "Plan", "FrontEndResult", "HostPipeline", "MafError", "capture_graph"):
         from . import frontend
         return getattr(frontend, name)
     if name == "GpuAudioPreprocessor":

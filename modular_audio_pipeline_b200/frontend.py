@@ -285,6 +285,23 @@ class Plan:
         return self.split_mel(mel)
 
 
+def capture_graph(fn, device=None):
+    """Capture the asynchronous work ``fn()`` issues (copies, front door, ``Plan.process`` ...) into ONE CUDA graph and
+    return ``(graph, fn's return value)``; ``graph.replay()`` re-issues the whole launch sequence with a single call.  Meant
+    for launch-bound small batches (BASELINE config 5: one 30 s chunk is ~20 kernels of a few microseconds each).  Every
+    tensor ``fn`` touches must stay alive and keep its address; tensors ``fn`` allocates live in the graph's memory pool."""
+    side = torch.cuda.Stream(device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(side):
+        fn()                                               # warm-up outside capture (lazy module load, function attributes)
+    torch.cuda.current_stream(device).wait_stream(side)
+    torch.cuda.synchronize(device)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ret = fn()
+    return graph, ret
+
+
 class HostPipeline:
     """Host-buffer entry with copy / compute overlap: ``depth`` plans (each with its own device buffers and stream) are
     used round-robin, so the H2D copy and the kernels of batch i+1 run while batch i's results travel back over PCIe.
@@ -354,4 +371,4 @@ class HostPipeline:
             e.synchronize()
 
 
-__all__ = ["FrontEnd", "Plan", "FrontEndResult", "HostPipeline", "MafError", "ItemDesc"]
+__all__ = ["FrontEnd", "Plan", "FrontEndResult", "HostPipeline", "MafError", "ItemDesc", "capture_graph"]
