@@ -330,3 +330,67 @@ def test_front_door_bit_exact(frontend, channels, in_rate, out_rate):
     assert np.array_equal(got.cpu().numpy(), want)
     raw = frontend.front_door(torch.from_numpy(x).to(frontend.device), channels, in_rate, out_rate, normalize=False)
     assert np.array_equal(raw.cpu().numpy(), O.front_door(x, channels, in_rate, out_rate, normalize=False))
+
+
+# ---- full size: BASELINE config 2 (1 h, non-stationary, 128-mel, 30 s pad), the workload bench.py times ----------------
+@pytest.mark.timeout(900)
+def test_full_size_cfg2_against_oracle_and_properties(frontend):
+    """The headline workload itself: all 96 chunks / 7776 tiles of a 1 h recording.  Stage-wise parity of the denoise and
+    the loudness against the oracle (which needs ~20 s of CPU for the hour), the log-mel against the oracle on the GPU's own
+    final PCM, plus size-independent properties: halving the input lowers the loudness by 20 log10(2) LU, and the
+    fused entry equals the stages chained."""
+    pcm = gen(3600.0, 1, meeting=True)
+    n = pcm.numel()
+    plan = frontend.plan([n], stationary=False, n_mels=128, mel_padding=480000)
+    packed = plan.pack([pcm])
+    out16, outf, _ = plan.denoise(packed, want_float=True)
+    red, den16, _ = O.denoise_int16(pcm.numpy(), SR, stationary=False)
+    s = snr_db(red, outf[0].cpu().numpy())
+    assert s >= 80.0, f"SNR {s:.1f} dB"
+    diff = np.abs(out16[0].cpu().numpy().astype(np.int32) - den16.astype(np.int32))
+    assert diff.max() <= 1 and np.mean(diff != 0) <= 1e-3
+    # fused entry on the same input
+    res = plan.process(packed)
+    final = res.pcm[0].cpu().numpy()
+    # loudness of the GPU's own peak-normalised signal vs the oracle on the same samples
+    norm = O.peak_normalize(out16[0].cpu().numpy())
+    want16, want_lufs, applied = O.normalize_loudness(norm, SR)
+    assert applied and abs(res.lufs.item() - want_lufs) <= 1e-4
+    d = np.abs(final.astype(np.int32) - want16.astype(np.int32))
+    assert d.max() <= 1 and np.mean(d != 0) <= 5e-3
+    # log-mel of the final PCM
+    want_mel = O.log_mel_spectrogram(final.astype(np.float32) / 32768.0, 128, 480000)
+    assert res.log_mel[0].shape == want_mel.shape == (128, (n + 480000) // 160)
+    assert np.abs(res.log_mel[0].cpu().numpy() - want_mel).max() <= 1e-4
+    # property: half the amplitude -> loudness lower by 20 log10(2) (up to the int16 rounding of the halved samples)
+    half = (pcm.to(torch.int32) // 2).to(torch.int16)
+    p2 = frontend.plan([n], n_mels=0)
+    _, l1 = p2.loudness(p2.pack([pcm]))
+    _, l2 = p2.loudness(p2.pack([half]))
+    assert abs((l1.item() - l2.item()) - 20 * np.log10(2.0)) <= 2e-3
+
+
+@pytest.mark.timeout(900)
+def test_full_size_cfg3_batch_equals_singles(frontend):
+    """BASELINE config 3 at full size: 1024 x 30 s clips in ONE plan (stationary, 80-mel).  Every item of the batch must
+    equal, bit for bit, the same clip processed alone (items are independent: no statistic may leak between files), and a
+    few of them are checked against the oracle."""
+    base = [gen(30.0, 100 + i) for i in range(16)]
+    clips = [base[i % 16] for i in range(1024)]
+    lengths = [c.numel() for c in clips]
+    plan = frontend.plan(lengths, stationary=True, n_mels=80, mel_padding=0)
+    res = plan.process(plan.pack(clips))
+    singles = []
+    for i in range(16):
+        p1 = frontend.plan([lengths[i]], stationary=True, n_mels=80, mel_padding=0)
+        r1 = p1.process(p1.pack([base[i]]))
+        singles.append((r1.pcm[0].clone(), r1.log_mel[0].clone(), r1.lufs.clone(), r1.noise_clip.clone()))
+        p1.close()
+    for i in range(1024):
+        pcm1, mel1, lufs1, clip1 = singles[i % 16]
+        assert torch.equal(res.pcm[i], pcm1) and torch.equal(res.log_mel[i], mel1), f"item {i}"
+        assert res.lufs[i].item() == lufs1.item() and torch.equal(res.noise_clip[i], clip1[0])
+    for i in (0, 5, 11):
+        ref = O.front_end(base[i].numpy(), SR, True, 80, 0)
+        assert tuple(res.noise_clip[i].cpu().numpy()) == tuple(ref["noise_clip"])
+        assert abs(res.lufs[i].item() - ref["lufs"]) <= 0.01
