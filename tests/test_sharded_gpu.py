@@ -46,9 +46,11 @@ def _free_port():
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("stationary,n_mels,padding", [(True, 80, 0), (False, 128, 480000)])
-def test_two_ranks_equal_one_gpu(frontend, stationary, n_mels, padding):
-    pcm = speech_noise(1500000 / SR, 8, meeting=not stationary).numpy()      # 3 chunks: ranks own 2 + 1
+@pytest.mark.parametrize("stationary,n_mels,padding,n_samples", [(True, 80, 0, 1500000), (False, 128, 480000, 1500000),
+                                                                  (False, 80, 480000, 12345678)])
+def test_two_ranks_equal_one_gpu(frontend, stationary, n_mels, padding, n_samples):
+    # 3 chunks (ranks own 2 + 1), and a 12.9 min recording: 21 chunks, ranks own 11 + 10, ragged last chunk
+    pcm = speech_noise(n_samples / SR, 8, meeting=not stationary).numpy()
     world = 2
     mgr = mp.Manager()
     results = mgr.dict()
