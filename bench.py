@@ -32,6 +32,8 @@ WORKLOADS = {
     "cfg1": ("cfg1: 60 s 16 kHz mono, stationary denoise + LUFS + 80-mel (30 s pad)", 60.0, 1, True, 80, 480000, False),
     "cfg2": ("cfg2: 1 h 16 kHz mono meeting, non-stationary denoise + LUFS + 128-mel (30 s pad)", 3600.0, 1, False, 128, 480000, True),
     "cfg3": ("cfg3: 1024 x 30 s clips, stationary denoise + LUFS + 80-mel, file-sharded", 30.0, 1024, True, 80, 0, False),
+    # not a BASELINE config: the reference's own Protocol method (stationary gate) on the 1 h recording of config 2
+    "cfg2s": ("cfg2s: 1 h 16 kHz mono meeting, STATIONARY denoise (auto-detected noise clip) + LUFS + 80-mel (30 s pad)", 3600.0, 1, True, 80, 480000, True),
 }
 CFG5 = "cfg5: 30 s chunk of 48 kHz stereo (speech + music bed + heavy noise) -> front door (peak normalise, 48k->16k, downmix) -> stationary denoise + LUFS + 80-mel; latency per chunk"
 
@@ -202,8 +204,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    if args.workload == "cfg5":
-        args.workload = "cfg3"          # the CPU arm has no 48 kHz front door leg: same 30 s stationary clips as config 3
+    if args.workload in ("cfg4", "cfg5"):
+        args.workload = "cfg3"          # the CPU arm has no sharded / 48 kHz front door leg: 30 s stationary clips as in config 3
     desc, seconds, per_gpu, stationary, n_mels, padding, meeting = WORKLOADS[args.workload]
     sample = min(seconds, args.cpu_sample)
     pool = CpuPool(args.workload, sample)
@@ -289,13 +291,71 @@ def run_cfg5(args):
     print(json.dumps(line), flush=True)
 
 
+def run_cfg4(args):
+    """BASELINE config 4: ONE long recording (1 h per rank: 8 h on 8 GPUs) time-sharded across the ranks with 30 000-sample
+    denoise halos and the six latency-class NCCL collectives of sharded.py (stationary denoise, LUFS, 80-mel)."""
+    import torch.distributed as dist
+    from modular_audio_pipeline_b200 import FrontEnd
+    from modular_audio_pipeline_b200.sharded import Comm, CudaShardBackend, ShardGeometry, run_sharded
+    from modular_audio_pipeline_b200.synth import speech_noise
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    own_init = world > 1
+    if own_init:
+        dist.init_process_group("nccl", device_id=dev)
+    else:                                                     # the collectives still run (group of one)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+    hour = 3600 * SR
+    geo = ShardGeometry(hour * world, rank, world)
+    sl = geo.local_slice()
+    # every rank synthesises the samples it holds (own range + halos); the seams need not be continuous for timing
+    local_pcm = speech_noise((sl.stop - sl.start) / SR, 2 + rank, device=dev)[: sl.stop - sl.start]
+    fe = FrontEnd(dev)
+    backend = CudaShardBackend(fe, geo, local_pcm, stationary=True, n_mels=80, mel_padding=480000)
+    comm = Comm(None)
+    for _ in range(max(args.warmup, 3)):
+        run_sharded(backend, geo, stationary=True, comm=comm)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = backend.plan.launches
+    ev0.record()
+    for _ in range(args.steps):
+        out, mel, lufs = run_sharded(backend, geo, stationary=True, comm=comm)
+    ev1.record()
+    torch.cuda.synchronize()
+    sampler.stop_flag.set()
+    dist.barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    audio_s = 3600.0 * world
+    if rank == 0:
+        line = {"metric": "audio_seconds_per_second", "value": audio_s / (ms_step / 1e3), "unit": "audio-s/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"cfg4: one {world} h recording time-sharded over {world} GPU(s) (whole 600 000-sample chunks, 30 000-sample "
+                                       "halos), stationary denoise + LUFS + 80-mel; NCCL: all-gather frame stats, SUM clip, MAX peak, "
+                                       "all-gather edges / sub-block energies, MAX mel",
+                           "seconds_per_rank": 3600.0, "l2": "working set exceeds the 126 MB L2", "parallelism": f"time-sharded x{world}"},
+                "lufs": float(lufs.cpu().item()), "gpu_launches": backend.plan.launches - launches0, "clocks": sampler.summary()}
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg5"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg4", "cfg5"])
     ap.add_argument("--cpu-sample", type=float, default=120.0, help="seconds of audio EACH host thread of the CPU baseline processes per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
@@ -305,6 +365,9 @@ def main():
         return
     if args.workload == "cfg5":
         run_cfg5(args)
+        return
+    if args.workload == "cfg4":
+        run_cfg4(args)
         return
 
     import torch.distributed as dist

@@ -30,7 +30,7 @@ struct MelHost { std::vector<int> start, count, woff; std::vector<float> w; std:
 struct maf_ctx {
     int device = 0;
     void* blob = nullptr;                // one allocation holding every constant table
-    void* scratch = nullptr;             // 1 KB of device scratch for the single-recording helpers
+    void* scratch = nullptr;             // 1 KB + SEL_SCRATCH_BYTES of device scratch for the single-recording helpers
     Consts c{};
     MelBank mel80{}, mel128{};
 };
@@ -122,7 +122,7 @@ extern "C" int maf_create(int device, maf_ctx** out) {
     if (e != cudaSuccess) { delete ctx; return fail(MAF_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
     e = cudaMemcpy(ctx->blob, host.data(), host.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(ctx->blob); delete ctx; return fail(MAF_ERR_CUDA, std::string("cudaMemcpy: ") + cudaGetErrorString(e)); }
-    if (cudaMalloc(&ctx->scratch, 1024) != cudaSuccess) { cudaFree(ctx->blob); delete ctx; return fail(MAF_ERR_CUDA, "cudaMalloc scratch"); }
+    if (cudaMalloc(&ctx->scratch, 1024 + SEL_SCRATCH_BYTES) != cudaSuccess) { cudaFree(ctx->blob); delete ctx; return fail(MAF_ERR_CUDA, "cudaMalloc scratch"); }
     unsigned char* b = (unsigned char*)ctx->blob;
     ctx->c.win1024 = (const float*)(b + o_win); ctx->c.winv1024 = (const float*)(b + o_winv); ctx->c.win400 = (const float*)(b + o_win4);
     ctx->c.tw1 = (const c32*)(b + o_t512); ctx->c.tw2 = (const c32*)(b + o_t2); ctx->c.tw1024 = (const c32*)(b + o_t1024);
@@ -168,7 +168,7 @@ struct maf_plan {
     NsParams ns{}; void* d_ns = nullptr;
     KwGeom kgeo{}; KwScan kscan{}; void* d_kscan = nullptr; int max_kgroups = 0;
     long long total_tiles = 0;
-    WsBuf S, M, P, Q, Yend, Zend, bits, rowflag, T2, T2hi, nmax, partial, E, ZC, clips, seg, den16, peak, pnorm, peak_norm, mel_max, mel_tmin, sub, gates;
+    WsBuf S, M, P, Q, Yend, Zend, bits, rowflag, T2, T2hi, nmax, partial, E, ZC, clips, seg, den16, peak, pnorm, peak_norm, mel_max, mel_tmin, sub, gates, selws;
     long long ws_bytes = 0;
     long long launches = 0;
     // optional per-stage CUDA-event timing (maf_plan_profile): ring of event sets, one per maf_process call
@@ -427,6 +427,7 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
     pl->mel_tmin = carve(cur, (long long)n_items * std::max(1, pl->max_mel_tiles) * 4);
     pl->sub = carve(cur, std::max(1, pl->total_ktiles) * 8LL);
     pl->gates = carve(cur, (long long)n_items * sizeof(Gate));
+    pl->selws = carve(cur, SEL_SCRATCH_BYTES);
     pl->ws_bytes = align_up(cur, 256);
     // device tables
     std::vector<Item> io = pl->items;
@@ -566,9 +567,25 @@ static int run_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pc
             if (pl->sharded) return fail(MAF_ERR_INVALID, "sharded plans need external noise clips (run maf_frame_stats / maf_select_clip first)");
             launch_frame_stats(pcm, pl->d_items, n, pl->max_sframes, pl->frame_len, pl->frame_hop, ws_ptr<float>(ws, pl->E), ws_ptr<int>(ws, pl->ZC), st);
             const int fallback = (int)(p.sample_rate * (double)p.noise_sample_duration_s);
-            launch_select_clip(ws_ptr<float>(ws, pl->E), ws_ptr<int>(ws, pl->ZC), pl->d_foff, pl->d_fcount, pl->d_items, n, pl->frame_len,
-                               pl->frame_hop, p.sample_rate, fallback, clips, ws_ptr<int>(ws, pl->seg), st);
-            pl->launches += 2;
+            if (pl->max_sframes > SEL_GRID_MIN_FRAMES && n <= 64) {
+                // long recordings: grid-wide co-operative selection per item (a single CTA would need ~1 ms per hour of audio)
+                for (int i = 0; i < n; ++i) {
+                    const Item& hi = pl->items[i];
+                    if (hi.n_sframes > SEL_GRID_MIN_FRAMES)
+                        launch_select_clip_grid(ws_ptr<float>(ws, pl->E) + hi.sframe_off, ws_ptr<int>(ws, pl->ZC) + hi.sframe_off, hi.n_sframes, hi,
+                                                pl->frame_len, pl->frame_hop, p.sample_rate, fallback, ws_ptr<void>(ws, pl->selws), clips + i,
+                                                ws_ptr<int>(ws, pl->seg) + 2 * i, st);
+                    else
+                        launch_select_clip(ws_ptr<float>(ws, pl->E), ws_ptr<int>(ws, pl->ZC), pl->d_foff + i, pl->d_fcount + i, pl->d_items + i, 1,
+                                           pl->frame_len, pl->frame_hop, p.sample_rate, fallback, clips + i, ws_ptr<int>(ws, pl->seg) + 2 * i, st);
+                    pl->launches += 1;
+                }
+                pl->launches += 1;
+            } else {
+                launch_select_clip(ws_ptr<float>(ws, pl->E), ws_ptr<int>(ws, pl->ZC), pl->d_foff, pl->d_fcount, pl->d_items, n, pl->frame_len,
+                                   pl->frame_hop, p.sample_rate, fallback, clips, ws_ptr<int>(ws, pl->seg), st);
+                pl->launches += 2;
+            }
         } else {
             if (pl->sharded) return fail(MAF_ERR_INVALID, "sharded plans need external noise clips");
             use_clips = pl->d_clips_fixed;
@@ -785,8 +802,12 @@ extern "C" int maf_select_clip(maf_ctx* ctx, const float* energy, const int32_t*
     unsigned char* d = (unsigned char*)ctx->scratch;
     CU(cudaMemcpyAsync(d, &h, sizeof(h), cudaMemcpyHostToDevice, st));
     const int frame_len = (int)(sr * 0.025), hop = (int)(sr * 0.010);
-    launch_select_clip(energy, zc, (const long long*)(d + offsetof(decltype(h), foff)), (const int*)(d + offsetof(decltype(h), fcount)),
-                       (const Item*)d, 1, frame_len, hop, sr, (int)(sr * (double)dur), (Clip*)(d + offsetof(decltype(h), clip)), seg, st);
+    if (n_frames > SEL_GRID_MIN_FRAMES)
+        launch_select_clip_grid(energy, zc, (int)n_frames, h.it, frame_len, hop, sr, (int)(sr * (double)dur), d + 1024,
+                                (Clip*)(d + offsetof(decltype(h), clip)), seg, st);
+    else
+        launch_select_clip(energy, zc, (const long long*)(d + offsetof(decltype(h), foff)), (const int*)(d + offsetof(decltype(h), fcount)),
+                           (const Item*)d, 1, frame_len, hop, sr, (int)(sr * (double)dur), (Clip*)(d + offsetof(decltype(h), clip)), seg, st);
     CU(cudaGetLastError());
     return MAF_OK;
 }

@@ -8,6 +8,7 @@
 //                      median ZCR from a histogram, numpy 'linear' interpolation in float64, the
 //                      (E < eT) & (ZCR > 0.5 zT) mask, and the longest run of >= 100 ms that is closed by a
 //                      non-noise frame (an open run at the end is dropped, like the reference's loop).
+#include <cooperative_groups.h>
 #include "maf_common.cuh"
 
 namespace maf {
@@ -346,12 +347,234 @@ __global__ void __launch_bounds__(SEL_THREADS) select_clip_kernel(const float* _
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Long recordings (hundreds of thousands of frames: one hour has 360 000): the same selection, but by a whole GRID that
+// co-operates through cooperative-groups grid barriers -- histograms in global memory, every CTA scanning its share of the
+// frames, one warp of CTA 0 taking the (tiny) decisions.  One CTA needs ~0.8 ms for an hour and would dominate the
+// stationary path; the grid needs ~20 barriers.  Results are bit-identical to select_clip_kernel (same order statistics,
+// same float64 interpolation, same run rule); the run summaries are combined with an associative merge.
+// ------------------------------------------------------------------------------------------------------------------
+struct SelShared {                 // global scratch of one selection (SEL_SCRATCH_BYTES)
+    unsigned hist[2048];
+    unsigned prefix, mask, digit, acc, cnt_le, min_gt;
+    int kk, pad_;
+    double eT, zT;
+    RunSummary sums[1024];         // one per CTA
+};
+
+// merge of the summaries of two adjacent frame ranges (L before R); lenL / lenR are their lengths, startR = first frame of R
+__device__ __forceinline__ RunSummary merge_runs(const RunSummary& L, int lenL, const RunSummary& R, int lenR, int startR) {
+    RunSummary o;
+    if (lenL <= 0) return R;
+    if (lenR <= 0) return L;
+    o.all = L.all && R.all;
+    o.lead = L.all ? lenL + R.lead : L.lead;
+    o.trail = R.all ? lenR + L.trail : R.trail;
+    o.best_len = L.best_len; o.best_start = L.best_start;
+    if (!L.all && !R.all) {                                     // the run across the seam is closed on both sides
+        const int mid = L.trail + R.lead;
+        if (mid > o.best_len) { o.best_len = mid; o.best_start = startR - L.trail; }
+    }
+    if (R.best_len > o.best_len) { o.best_len = R.best_len; o.best_start = R.best_start; }
+    if (o.all) { o.best_len = 0; o.best_start = 0; }
+    return o;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) select_clip_grid_kernel(const float* __restrict__ E, const int* __restrict__ Z, int F,
+                                                                        Item it, int frame_len, int hop, int sr, int fallback_len,
+                                                                        SelShared* __restrict__ g, Clip* __restrict__ clip_out,
+                                                                        int* __restrict__ seg_out) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    __shared__ unsigned hist[2048];
+    __shared__ RunSummary sums[SEL_THREADS];
+    const int tid = threadIdx.x;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + tid, gsize = (long long)gridDim.x * blockDim.x;
+    const bool leader = blockIdx.x == 0;
+    // ---- energy: k-th and (k+1)-th smallest by radix select on the float bits (4 x 8 bits)
+    const double vi_e = __dmul_rn((double)(F - 1), 0.2);
+    const double lo_e = floor(vi_e);
+    const int k_e = (int)lo_e;
+    if (leader) {
+        for (int i = tid; i < 256; i += blockDim.x) g->hist[i] = 0;
+        if (tid == 0) { g->prefix = 0; g->mask = 0; g->kk = k_e; g->cnt_le = 0; g->min_gt = 0x7f800000u; }
+    }
+    grid.sync();
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        const unsigned prefix = g->prefix, mask = g->mask;
+        for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        {
+            int cur = -1; unsigned run = 0;
+            for (long long i = gtid; i < F; i += gsize) {
+                const unsigned u = __float_as_uint(E[i]);
+                if ((u & mask) != prefix) continue;
+                const int d = (u >> shift) & 255;
+                if (d == cur) { ++run; continue; }
+                if (run) atomicAdd(&hist[cur], run);
+                cur = d; run = 1;
+            }
+            if (run) atomicAdd(&hist[cur], run);
+        }
+        __syncthreads();
+        for (int i = tid; i < 256; i += blockDim.x) if (hist[i]) atomicAdd(&g->hist[i], hist[i]);
+        grid.sync();
+        if (leader && tid < 32) {
+            const int lane = tid, kk = g->kk;
+            unsigned h[8], tot = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { h[j] = g->hist[8 * lane + j]; tot += h[j]; }
+            unsigned incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const unsigned excl = incl - tot;
+            const unsigned hit = __ballot_sync(0xffffffffu, incl > (unsigned)kk);
+            if (hit && lane == __ffs(hit) - 1) {
+                unsigned acc = excl; int j = 0;
+                for (; j < 8; ++j) { if (acc + h[j] > (unsigned)kk) break; acc += h[j]; }
+                g->prefix = prefix | ((unsigned)(8 * lane + j) << shift); g->mask = mask | (255u << shift); g->kk = kk - (int)acc;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g->hist[8 * lane + j] = 0;                 // ready for the next pass
+        }
+        grid.sync();
+    }
+    {   // count of elements <= v_k and the smallest element above it
+        const unsigned vk = g->prefix;
+        unsigned cnt = 0, mn = 0x7f800000u;
+        for (long long i = gtid; i < F; i += gsize) { const unsigned u = __float_as_uint(E[i]); if (u <= vk) ++cnt; else mn = min(mn, u); }
+        cnt = __reduce_add_sync(0xffffffffu, cnt); mn = __reduce_min_sync(0xffffffffu, mn);
+        if ((tid & 31) == 0) { if (cnt) atomicAdd(&g->cnt_le, cnt); atomicMin(&g->min_gt, mn); }
+    }
+    // ---- ZCR histogram (counts < frame_len <= 2047)
+    if (leader) for (int i = tid; i < 2048; i += blockDim.x) g->hist[i] = 0;
+    grid.sync();
+    for (int i = tid; i < 2048; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (long long i = gtid; i < F; i += gsize) atomicAdd(&hist[min(Z[i], 2047)], 1u);
+    __syncthreads();
+    for (int i = tid; i < 2048; i += blockDim.x) if (hist[i]) atomicAdd(&g->hist[i], hist[i]);
+    grid.sync();
+    if (leader && tid < 32) {
+        const int lane = tid;
+        if (lane == 0) {
+            const float a = __uint_as_float(g->prefix);
+            float b = (g->cnt_le > (unsigned)(k_e + 1)) ? a : __uint_as_float(g->min_gt);
+            if (k_e + 1 > F - 1) b = a;
+            g->eT = np_lerp((double)a, (double)b, __dsub_rn(vi_e, lo_e));
+        }
+        const double vi = __dmul_rn((double)(F - 1), 0.5);
+        const double lo = floor(vi);
+        const int k = (int)lo, k1 = min(k + 1, F - 1);
+        unsigned tot = 0;
+        for (int j = 0; j < 64; ++j) tot += g->hist[64 * lane + j];
+        unsigned incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const unsigned excl = incl - tot;
+        int ca = -1, cb = -1;
+        if (excl <= (unsigned)k && incl > (unsigned)k) {
+            unsigned acc = excl;
+            for (int j = 0; j < 64; ++j) { acc += g->hist[64 * lane + j]; if (acc > (unsigned)k) { ca = 64 * lane + j; break; } }
+        }
+        if (excl <= (unsigned)k1 && incl > (unsigned)k1) {
+            unsigned acc = excl;
+            for (int j = 0; j < 64; ++j) { acc += g->hist[64 * lane + j]; if (acc > (unsigned)k1) { cb = 64 * lane + j; break; } }
+        }
+        ca = __reduce_max_sync(0xffffffffu, ca); cb = __reduce_max_sync(0xffffffffu, cb);
+        if (lane == 0) {
+            const double a = __ddiv_rn((double)ca, (double)frame_len), b = __ddiv_rn((double)cb, (double)frame_len);
+            g->zT = __dmul_rn(np_lerp(a, b, __dsub_rn(vi, lo)), 0.5);
+        }
+    }
+    grid.sync();
+    // ---- runs: CTA c owns frames [c per_cta, (c+1) per_cta), thread t a contiguous part of them
+    const double eT = g->eT, zT = g->zT;
+    const int per_cta = (F + gridDim.x - 1) / gridDim.x;
+    const int per = (per_cta + SEL_THREADS - 1) / SEL_THREADS;
+    const int c0 = min(F, blockIdx.x * per_cta), c1 = min(F, c0 + per_cta);
+    {
+        const int s0 = min(c1, c0 + tid * per), s1 = min(c1, s0 + per);
+        RunSummary rs; rs.all = 1; rs.lead = 0; rs.trail = 0; rs.best_len = 0; rs.best_start = 0;
+        int run_start = -1; bool seen_false = false;
+        for (int i = s0; i < s1; ++i) {
+            const bool nz = ((double)E[i] < eT) && (__ddiv_rn((double)Z[i], (double)frame_len) > zT);
+            if (nz) {
+                if (run_start < 0) run_start = i;
+            } else {
+                if (run_start >= 0) {
+                    if (!seen_false && run_start == s0) rs.lead = i - s0;
+                    else if (i - run_start > rs.best_len) { rs.best_len = i - run_start; rs.best_start = run_start; }
+                    run_start = -1;
+                }
+                seen_false = true; rs.all = 0;
+            }
+        }
+        if (rs.all) { rs.lead = s1 - s0; rs.trail = s1 - s0; }
+        else rs.trail = (run_start >= 0) ? s1 - run_start : 0;
+        sums[tid] = rs;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        RunSummary acc = sums[0];
+        int len = min(c1, c0 + per) - c0;
+        for (int t = 1; t < SEL_THREADS; ++t) {
+            const int s0 = min(c1, c0 + t * per), s1 = min(c1, s0 + per);
+            if (s1 <= s0) break;
+            acc = merge_runs(acc, len, sums[t], s1 - s0, s0);
+            len += s1 - s0;
+        }
+        g->sums[blockIdx.x] = acc;
+    }
+    grid.sync();
+    if (leader && tid == 0) {
+        RunSummary acc = g->sums[0];
+        int len = min(F, per_cta);
+        for (int c = 1; c < (int)gridDim.x; ++c) {
+            const int a0 = min(F, c * per_cta), a1 = min(F, a0 + per_cta);
+            if (a1 <= a0) break;
+            acc = merge_runs(acc, len, g->sums[c], a1 - a0, a0);
+            len += a1 - a0;
+        }
+        // candidates in order of their start: the leading run (closed unless everything is noise), then the best interior run;
+        // an open run at the end is dropped like in the reference's loop
+        int bl = 0, bs = 0;
+        if (!acc.all && acc.lead > bl) { bl = acc.lead; bs = 0; }
+        if (acc.best_len > bl) { bl = acc.best_len; bs = acc.best_start; }
+        const bool found = bl > 0 && __ddiv_rn((double)((long long)bl * hop), (double)sr) >= 0.1;
+        long long gs, ge;
+        if (found) { gs = (long long)bs * hop; ge = (long long)(bs + bl) * hop; }
+        else { gs = 0; ge = min((long long)fallback_len, it.n_global); }
+        Clip c;
+        c.start = it.pcm_off + gs - it.g0 + it.origin;
+        long long len2 = ge - gs; if (len2 > CHUNK) len2 = CHUNK;
+        c.len = (int)len2; c.n_frames = (int)(len2 / HOP) + 1;
+        *clip_out = c;
+        if (seg_out) { seg_out[0] = (int)gs; seg_out[1] = (int)ge; }
+    }
+}
+
+static_assert(sizeof(SelShared) <= SEL_SCRATCH_BYTES, "selection scratch too small");
+
 void launch_select_clip(const float* energies, const int* zc, const long long* foff, const int* fcount,
                         const Item* items, int n_items, int frame_len, int hop, int sr, int fallback_len,
                         Clip* clips, int* seg_out, cudaStream_t st) {
     if (n_items <= 0) return;
     select_clip_kernel<<<n_items, SEL_THREADS, 0, st>>>(energies, zc, foff, fcount, items, frame_len, hop, sr,
                                                        fallback_len, clips, seg_out);
+}
+
+// one long recording: host-side item description, `scratch` = SEL_SCRATCH_BYTES of device memory owned by the caller
+void launch_select_clip_grid(const float* E, const int* Z, int F, const Item& it, int frame_len, int hop, int sr, int fallback_len,
+                             void* scratch, Clip* clip_out, int* seg_out, cudaStream_t st) {
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    int grid = n_sm < 1024 ? n_sm : 1024;
+    SelShared* g = (SelShared*)scratch;
+    Item itc = it;
+    void* args[] = {(void*)&E, (void*)&Z, (void*)&F, (void*)&itc, (void*)&frame_len, (void*)&hop, (void*)&sr, (void*)&fallback_len,
+                    (void*)&g, (void*)&clip_out, (void*)&seg_out};
+    cudaLaunchCooperativeKernel((const void*)select_clip_grid_kernel, dim3(grid), dim3(SEL_THREADS), args, 0, st);
 }
 
 }  // namespace maf

@@ -36,8 +36,9 @@ def test_frame_stats_bit_exact(frontend, seconds, seed):
     assert np.array_equal(z.cpu().numpy() / 400.0, zo)
 
 
-@pytest.mark.parametrize("seconds,seed", [(30, 3), (60, 0), (97.3, 5), (12, 9)])
+@pytest.mark.parametrize("seconds,seed", [(30, 3), (60, 0), (97.3, 5), (12, 9), (700.3, 6), (1800.0, 7), (3600.0, 1)])
 def test_noise_clip_indices(frontend, seconds, seed):
+    # recordings above 32768 frames (328 s) take the grid-wide co-operative selection kernel
     pcm = gen(seconds, seed)
     plan = frontend.plan([pcm.numel()], n_mels=0)
     _, _, clip = plan.denoise(plan.pack([pcm]))
