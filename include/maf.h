@@ -139,6 +139,13 @@ int maf_mel_finalize(maf_plan* plan, void* workspace_dev, float* mel_dev, void* 
 int maf_plan_buffer(const maf_plan* plan, const char* name, int64_t* offset_bytes, int64_t* size_bytes);
 int64_t maf_plan_den_offset(const maf_plan* plan, int32_t item);   /* int16 index of own sample 0 inside "den16" */
 
+/* Sharded noise clip without a host round trip (seg_dev = the {start, end} maf_select_clip wrote, in global samples):
+ * maf_sharded_clip_contrib fills clip_dev[600000] (int32) with the samples of the range this shard owns and zeros
+ * elsewhere -- the all-reduce(SUM) over the ranks is the clip; maf_set_noise_clips_dev is maf_set_noise_clips for the
+ * one item of a sharded plan with the length taken from seg_dev on the device (clip at offset 0 of noise_pcm_dev). */
+int maf_sharded_clip_contrib(maf_plan* plan, const int16_t* pcm_dev, const int32_t* seg_dev, int32_t* clip_dev, void* stream);
+int maf_set_noise_clips_dev(maf_plan* plan, const int32_t* seg_dev, void* stream);
+
 /* ---- silence detection for AudioPreprocessor.remove_silence / detect_silence_segments (preprocessor.py:290-405 ->
  * pydub.silence.detect_silence over audioop.rms).  maf_ms_energy: exact integer sum of squares per millisecond
  * bucket [int(i r), int((i+1) r)), r = rate / 1000, and of the whole recording (seg.rms -> seg.dBFS).

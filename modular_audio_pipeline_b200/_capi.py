@@ -70,6 +70,8 @@ SYMBOLS = {
     "maf_plan_den_offset": (C.c_int64, [_P, C.c_int32]),
     "maf_ms_energy": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int64, _P, _P, _P]),
     "maf_silence_flags": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_double, _P, _P]),
+    "maf_sharded_clip_contrib": (C.c_int, [_P, _P, _P, _P, _P]),
+    "maf_set_noise_clips_dev": (C.c_int, [_P, _P, _P]),
     "maf_front_door_out_len": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
     "maf_front_door": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
 }

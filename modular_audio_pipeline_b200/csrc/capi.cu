@@ -812,6 +812,40 @@ extern "C" int maf_select_clip(maf_ctx* ctx, const float* energy, const int32_t*
     return MAF_OK;
 }
 
+// Sharded noise clip without a host round trip: the selected range stays on the device (seg = {start, end} in global samples).
+__global__ void clip_contrib_kernel(const int16_t* __restrict__ pcm, Item it, const int* __restrict__ seg, int* __restrict__ clip) {
+    const long long gs = seg[0];
+    long long len = (long long)seg[1] - gs; if (len > CHUNK) len = CHUNK;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < CHUNK; i += gridDim.x * blockDim.x) {
+        const long long g = gs + i;
+        int v = 0;
+        if (i < len && g >= it.g0 && g < it.g0 + it.own_len) v = pcm[it.pcm_off + it.origin + (g - it.g0)];
+        clip[i] = v;
+    }
+}
+__global__ void set_clip_dev_kernel(const int* __restrict__ seg, Clip* __restrict__ clips) {
+    long long len = (long long)seg[1] - seg[0]; if (len > CHUNK) len = CHUNK; if (len < 0) len = 0;
+    Clip c; c.start = 0; c.len = (int)len; c.n_frames = (int)(len / HOP) + 1;
+    clips[0] = c;
+}
+
+extern "C" int maf_sharded_clip_contrib(maf_plan* pl, const int16_t* pcm, const int32_t* seg, int32_t* clip, void* stream) {
+    if (!pl || !pcm || !seg || !clip || pl->n_items != 1) return fail(MAF_ERR_INVALID, "maf_sharded_clip_contrib: bad argument");
+    CU(cudaSetDevice(pl->ctx->device));
+    clip_contrib_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(pcm, pl->items[0], seg, clip);
+    CU(cudaGetLastError());
+    return MAF_OK;
+}
+
+extern "C" int maf_set_noise_clips_dev(maf_plan* pl, const int32_t* seg, void* stream) {
+    if (!pl || !seg || pl->n_items != 1) return fail(MAF_ERR_INVALID, "maf_set_noise_clips_dev: bad argument");
+    CU(cudaSetDevice(pl->ctx->device));
+    set_clip_dev_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(seg, pl->d_clips_fixed);
+    pl->have_noise_clips = true;
+    CU(cudaGetLastError());
+    return MAF_OK;
+}
+
 extern "C" int maf_sharded_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pcm, void* ws, void* stream) {
     if (!pl || !pcm || !ws) return fail(MAF_ERR_INVALID, "maf_sharded_denoise: NULL argument");
     CU(cudaSetDevice(pl->ctx->device));

@@ -137,15 +137,22 @@ def run_sharded(backend, geo: ShardGeometry, group=None, stationary: bool = True
         e, z = backend.frame_stats()
         e_all = _gather_var(e, geo.frame_counts, comm)
         z_all = _gather_var(z, geo.frame_counts, comm)
-        gs, ge = backend.select_clip(e_all, z_all)                 # global sample range (host ints, one sync)
-        clip_len = min(ge - gs, CHUNK)
-        # 2. every rank contributes the clip samples it owns; the sum is the clip
-        clip = torch.zeros(clip_len, dtype=torch.int32, device=e.device)
-        lo, hi = max(gs, geo.own_start), min(gs + clip_len, geo.own_end)
-        if hi > lo:
-            clip[lo - gs: hi - gs] = backend.own_samples(lo - geo.own_start, hi - geo.own_start).to(torch.int32)
-        comm.all_reduce(clip, dist.ReduceOp.SUM)
-        backend.set_noise(clip.to(torch.int16))
+        if hasattr(backend, "clip_contrib"):
+            # device path: the selected range never visits the host (no stream sync in the whole step)
+            seg = backend.select_clip_dev(e_all, z_all)
+            clip = backend.clip_contrib(seg)                       # int32 [CHUNK]: own samples of the range, zeros elsewhere
+            comm.all_reduce(clip, dist.ReduceOp.SUM)
+            backend.set_noise_dev(clip.to(torch.int16), seg)
+        else:
+            gs, ge = backend.select_clip(e_all, z_all)             # global sample range (host ints, one sync)
+            clip_len = min(ge - gs, CHUNK)
+            # 2. every rank contributes the clip samples it owns; the sum is the clip
+            clip = torch.zeros(clip_len, dtype=torch.int32, device=e.device)
+            lo, hi = max(gs, geo.own_start), min(gs + clip_len, geo.own_end)
+            if hi > lo:
+                clip[lo - gs: hi - gs] = backend.own_samples(lo - geo.own_start, hi - geo.own_start).to(torch.int32)
+            comm.all_reduce(clip, dist.ReduceOp.SUM)
+            backend.set_noise(clip.to(torch.int16))
     # 3. denoise the own chunks; global peak
     backend.denoise()
     comm.all_reduce(backend.peak(), dist.ReduceOp.MAX)
@@ -201,13 +208,26 @@ class CudaShardBackend:
     def frame_stats(self):
         return self.plan.frame_stats(self.pcm)
 
-    def select_clip(self, e_all, z_all):
+    def select_clip_dev(self, e_all, z_all):
         seg = torch.zeros(2, dtype=torch.int32, device=self.fe.device)
         lib = self.fe._lib
+        self._e_all, self._z_all = e_all, z_all                 # keep alive until the kernel has run
         self._call(lib.maf_select_clip, self.fe._h, e_all.data_ptr(), z_all.data_ptr(), e_all.numel(), self.geo.n_global,
                    self.geo.sample_rate, self.dur, seg.data_ptr(), self._st())
-        s = seg.cpu()
+        return seg
+
+    def select_clip(self, e_all, z_all):
+        s = self.select_clip_dev(e_all, z_all).cpu()
         return int(s[0]), int(s[1])
+
+    def clip_contrib(self, seg: torch.Tensor) -> torch.Tensor:
+        clip = torch.empty(CHUNK, dtype=torch.int32, device=self.fe.device)
+        self._call(self.fe._lib.maf_sharded_clip_contrib, self.plan._h, self.pcm.data_ptr(), seg.data_ptr(), clip.data_ptr(), self._st())
+        return clip
+
+    def set_noise_dev(self, clip: torch.Tensor, seg: torch.Tensor):
+        self.noise, self._seg = clip.contiguous(), seg
+        self._call(self.fe._lib.maf_set_noise_clips_dev, self.plan._h, seg.data_ptr(), self._st())
 
     def own_samples(self, a: int, b: int) -> torch.Tensor:
         o = self.plan.layout[0].pcm_off + self.geo.origin
