@@ -22,6 +22,20 @@ import time
 import numpy as np
 import torch
 
+# Rank 0 prints exactly ONE line on stdout, the JSON.  Native libraries write there too (NCCL prints its version banner with
+# printf on communicator creation), so file descriptor 1 is pointed at stderr and the JSON goes out through a private
+# duplicate of the real stdout.
+_JSON_OUT = os.fdopen(os.dup(1), "w") if __name__ == "__main__" else sys.stdout
+if __name__ == "__main__":
+    sys.stdout.flush()
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -225,7 +239,7 @@ def run_reference(args):
                              "sample": f"{pool.n} x {sample:.0f} s of the workload audio per step through oracle/reference_path.front_end, "
                                        f"one single-threaded process per host thread"},
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_cfg5(args):
@@ -288,7 +302,7 @@ def run_cfg5(args):
                            "eager_p50": float(lat_eager[len(lat_eager) // 2]), "eager_p99": float(lat_eager[min(len(lat_eager) - 1, int(0.99 * len(lat_eager)))]),
                            "what": "pinned host 48 kHz stereo chunk in -> H2D -> front door -> denoise -> peak normalise -> loudness -> log-mel -> D2H of PCM + LUFS, synchronous"},
             "h2d_bytes_per_step": h_in.numel() * 2, "d2h_bytes_per_step": plan.total_out * 2 + 8, "gpu_launches": launches_per_chunk * runs}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_cfg4(args):
@@ -345,7 +359,7 @@ def run_cfg4(args):
                                        "all-gather edges / sub-block energies, MAX mel",
                            "seconds_per_rank": 3600.0, "l2": "working set exceeds the 126 MB L2", "parallelism": f"time-sharded x{world}"},
                 "lufs": float(lufs.cpu().item()), "gpu_launches": backend.plan.launches - launches0, "clocks": sampler.summary()}
-        print(json.dumps(line), flush=True)
+        emit(line)
     dist.destroy_process_group()
 
 
@@ -530,7 +544,7 @@ def main():
                            "parallelism": f"file-sharded x{world}"},
                 "x_realtime": value, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
                 "clocks": sampler.summary()}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
