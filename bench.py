@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """bench.py -- audio-seconds per second of the denoise + LUFS + log-mel front-end (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg1|cfg2|cfg2s|cfg3|cfg4|cfg5]
+
+Workloads: cfg2 (default, the headline: BASELINE.json configs[1]); cfg1 / cfg3 / cfg4 / cfg5 are the other BASELINE configs
+(cfg4 = one long recording time-sharded over the ranks with NCCL collectives, cfg5 = latency of one 30 s chunk of 48 kHz
+stereo through the front door, replayed as a CUDA graph); cfg2s = the stationary gate on cfg2's recording.
 
 One "step" = one pass of the whole hot path (noise detect / threshold, STFT, mask, iSTFT, peak normalise, loudness,
 log-mel) over one batch of synthetic recordings resident in HBM.  N = 1 runs BASELINE.json configs[1]: one 1 h
