@@ -43,10 +43,10 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     int* m_qoff = m_qcount + 32;
     const int tid = threadIdx.x;
 
-    const long long total = (long long)n_items * max_tiles;
-    auto geom = [&](long long t, MelTile& g) {
-        g.item = (int)(t / max_tiles);
-        g.lf0 = (int)(t % max_tiles) * MEL_TILE;
+    const unsigned total = (unsigned)n_items * (unsigned)max_tiles;            // < 2^31 (checked by the launcher): 32-bit index math
+    auto geom = [&](unsigned t, MelTile& g) {
+        g.item = (int)(t / (unsigned)max_tiles);
+        g.lf0 = (int)(t - (unsigned)g.item * (unsigned)max_tiles) * MEL_TILE;
         const Item& it = items[g.item];
         if (g.lf0 >= it.mel_frames) return false;
         g.i0 = ((long long)it.mel_f0 + g.lf0) * W_HOP - W_NFFT / 2;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
         }
     };
 
-    long long t = blockIdx.x;
+    unsigned t = blockIdx.x;
     MelTile cur, nxt;
     while (t < total && !geom(t, cur)) t += gridDim.x;
     if (t >= total) return;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
         }
     }
     // next unit of this CTA: its raw samples travel while this tile is transformed
-    long long tn = t + gridDim.x;
+    unsigned tn = t + gridDim.x;
     while (tn < total && !geom(tn, nxt)) tn += gridDim.x;
     if (tn < total) fetch(nxt);
     __syncthreads();
@@ -250,6 +250,7 @@ void launch_logmel(const int16_t* den16, const Item* items, int n_items, int max
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     const long long total = (long long)n_items * max_tiles;
+    if (total >= (1LL << 31) - 4096) return;                       // unreachable for plans that fit in memory
     const int grid = (int)(total < 2LL * n_sm ? total : 2LL * n_sm);
     logmel_kernel<<<grid, 256, LOGMEL_SMEM, st>>>(den16, items, n_items, max_tiles, c, mel, padding, peak_normalize, pnorm, gates, out16,
                                                   mel_out, mel_max, tile_min);

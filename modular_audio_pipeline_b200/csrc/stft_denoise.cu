@@ -111,14 +111,15 @@ __global__ void __launch_bounds__(32 * STFT_WARPS, 2) stft1024_kernel(const int1
         wc = -cl * (0.5f / 1024.0f); ws = sl * (0.5f / 1024.0f);
     }
 
-    const long long total = (long long)n_chunks * tiles_per_chunk;
-    auto tile_valid = [&](long long t, Chunk& ch, int& f0) {
-        ch = chunks[t / tiles_per_chunk];
-        f0 = (int)(t % tiles_per_chunk) * STFT_TILE;
+    const unsigned total = (unsigned)n_chunks * (unsigned)tiles_per_chunk;    // < 2^31 (checked by the launcher): 32-bit index math
+    auto tile_valid = [&](unsigned t, Chunk& ch, int& f0) {
+        const unsigned c = t / (unsigned)tiles_per_chunk;
+        ch = chunks[c];
+        f0 = (int)(t - c * (unsigned)tiles_per_chunk) * STFT_TILE;
         return f0 < ch.n_frames;
     };
     // first valid tile of this CTA
-    long long t = blockIdx.x;
+    unsigned t = blockIdx.x;
     Chunk ch; int f0 = 0;
     while (t < total && !tile_valid(t, ch, f0)) t += gridDim.x;
     if (t >= total) return;
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(32 * STFT_WARPS, 2) stft1024_kernel(const int1
 
     while (t < total) {
         // next valid tile: start its span load into the other buffer
-        long long tn = t + gridDim.x;
+        unsigned tn = t + gridDim.x;
         Chunk chn; int f0n = 0;
         while (tn < total && !tile_valid(tn, chn, f0n)) tn += gridDim.x;
         if (tn < total) stft_stage_span(span0 + (buf ^ 1) * STFT_SPAN, pcm, items[chn.item], chn, f0n, tid);
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(32 * STFT_WARPS, 2) stft1024_kernel(const int1
         __syncthreads();                                              // current span landed; everyone is done with the previous tile's scratch
 
         const int16_t* span = span0 + buf * STFT_SPAN;
-        const int c = (int)(t / tiles_per_chunk), tile = (int)(t % tiles_per_chunk);
+        const int c = (int)(t / (unsigned)tiles_per_chunk), tile = (int)(t - (unsigned)c * (unsigned)tiles_per_chunk);
         const int n_tile = min(STFT_TILE, ch.n_frames - f0);
         const float* t2 = STATIONARY ? T2 + (long long)ch.item * T_PITCH : nullptr;
         const float* t2hi = STATIONARY ? T2hi + (long long)ch.item * T_PITCH : nullptr;
@@ -260,6 +261,7 @@ void launch_stft(const int16_t* pcm, const Item* items, const Chunk* chunks, int
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     const long long total = (long long)n_chunks * tiles;
+    if (total >= (1LL << 31) - 4096) return;                      // unreachable for plans that fit in memory
     const int grid = (int)std::min<long long>(total, 2LL * n_sm);
     cudaFuncSetAttribute(stft1024_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STFT_SMEM);
     cudaFuncSetAttribute(stft1024_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STFT_SMEM);
