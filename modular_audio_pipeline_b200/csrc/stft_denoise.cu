@@ -846,18 +846,21 @@ void launch_smooth_mask(const uint32_t* bits, const uint8_t* rowflag, const Chun
 // every output sample is summed in ascending frame order inside one CTA (deterministic, no atomics, no second
 // pass).  Four frames are transformed concurrently; they are 8 frames apart so their 1024-sample spans are disjoint.
 // ============================================================================================================
+// cos / sin of d pi / 4, d = 0..7 (compile-time after unrolling)
+__device__ __forceinline__ float w8c(int d) { const float c[8] = {1.f, 0.70710678118654752f, 0.f, -0.70710678118654752f, -1.f, -0.70710678118654752f, 0.f, 0.70710678118654752f}; return c[d]; }
+__device__ __forceinline__ float w8s(int d) { const float s[8] = {0.f, 0.70710678118654752f, 1.f, 0.70710678118654752f, 0.f, -0.70710678118654752f, -1.f, -0.70710678118654752f}; return s[d]; }
+
 constexpr int ISTFT_FR = ISTFT_SEG + 3;                 // 32 frames per CTA
 constexpr int OLA_LEN = (ISTFT_FR + 3) * HOP;           // 8960 floats
-constexpr size_t ISTFT_SMEM = sizeof(float) * OLA_LEN + sizeof(float) * NFFT + sizeof(c32) * (FFT512_TW1 + FFT512_TW2) + sizeof(c32) * 264 +
+constexpr size_t ISTFT_SMEM = sizeof(float) * OLA_LEN + sizeof(c32) * (FFT512_TW1 + FFT512_TW2) + sizeof(c32) * 264 +
                               sizeof(c32) * 4 * FFT512_SMEM;
 
-__global__ void __launch_bounds__(256) istft_kernel(const c32* __restrict__ S, const float* __restrict__ M,
+__global__ void __launch_bounds__(256, 3) istft_kernel(const c32* __restrict__ S, const float* __restrict__ M,
                                                     const Item* __restrict__ items, const Chunk* __restrict__ chunks, Consts cs,
                                                     int16_t* __restrict__ den16, int to_out, float* __restrict__ den_f32, int* __restrict__ peak) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* ola = reinterpret_cast<float*>(smem_raw);
-    float* winv = ola + OLA_LEN;
-    c32* tw1 = reinterpret_cast<c32*>(winv + NFFT);
+    c32* tw1 = reinterpret_cast<c32*>(ola + OLA_LEN);
     c32* tw2 = tw1 + FFT512_TW1;
     c32* tw1024 = tw2 + FFT512_TW2;
     c32* fsm = tw1024 + 264;
@@ -869,9 +872,15 @@ __global__ void __launch_bounds__(256) istft_kernel(const c32* __restrict__ S, c
     if (ch.keep <= 0 || g0 > seg_hi) return;
     const Item it = items[ch.item];
     const int tid = threadIdx.x, g = tid >> 6, t = tid & 63;
+    // hann(m) / 2 = 0.25 - 0.25 cos(2 pi m / 1024) at m = 2 t + 128 d (+ 1): 0.25 + wc cos(d pi / 4) + ws sin(d pi / 4)
+    float wc0, ws0, wc1, ws1;
+    {
+        float sn, cs;
+        sincospif((float)t * (1.0f / 256.0f), &sn, &cs); wc0 = -0.25f * cs; ws0 = 0.25f * sn;
+        sincospif((float)(2 * t + 1) * (1.0f / 512.0f), &sn, &cs); wc1 = -0.25f * cs; ws1 = 0.25f * sn;
+    }
 
     for (int i = tid; i < OLA_LEN; i += 256) ola[i] = 0.f;
-    for (int i = tid; i < NFFT; i += 256) winv[i] = cs.winv1024[i];
     for (int i = tid; i < FFT512_TW1; i += 256) tw1[i] = cs.tw1[i];
     if (tid < FFT512_TW2) tw2[tid] = cs.tw2[tid];
     for (int i = tid; i < 257; i += 256) tw1024[i] = cs.tw1024[i];
@@ -939,14 +948,16 @@ __global__ void __launch_bounds__(256) istft_kernel(const c32* __restrict__ S, c
         group_fft512(v, z, tw1, tw2, t, g);
         if (active) {
             float2* o2 = reinterpret_cast<float2*>(ola + lf * HOP);
-            const float2* w2 = reinterpret_cast<const float2*>(winv);
 #pragma unroll
             for (int d = 0; d < 8; ++d) {
                 const int n = t + 64 * d;
+                // synthesis window hann / 2 at samples 2 n, 2 n + 1 by angle addition (angle = alpha_t + d pi / 4): two FMAs each
+                // instead of a shared-memory load -- this kernel is bound by shared-memory traffic
+                const float cd = w8c(d), sd = w8s(d);
+                const float w0 = fmaf(wc0, cd, fmaf(ws0, sd, 0.25f)), w1 = fmaf(wc1, cd, fmaf(ws1, sd, 0.25f));
                 float2 acc = o2[n];
-                const float2 w = w2[n];
-                acc.x += v[d].x * w.x;
-                acc.y += -v[d].y * w.y;
+                acc.x += v[d].x * w0;
+                acc.y += -v[d].y * w1;
                 o2[n] = acc;
             }
         }
