@@ -93,6 +93,18 @@ MAF_HD void fft512_step1(c32 (&v)[8], c32* sm, const c32* tw1, int t) {
         sm[p * 72 + t] = (p == 0) ? v[0] : cmul(v[p], w);
     }
 }
+// Same step with the twiddles e^{-2 pi i t p / 512} = w^p built from the per-thread base w = e^{-2 pi i t / 512} by repeated
+// multiplication (p <= 7: < 5e-7 relative) instead of seven shared-memory loads -- for kernels bound by shared-memory traffic.
+MAF_HD void fft512_step1_base(c32 (&v)[8], c32* sm, c32 w1, int t) {
+    fft8(v);
+    c32 w = w1;
+    sm[t] = v[0];
+#pragma unroll
+    for (int p = 1; p < 8; ++p) {
+        sm[p * 72 + t] = cmul(v[p], w);
+        if (p < 7) w = cmul(w, w1);
+    }
+}
 // (barrier)
 MAF_HD void fft512_step2_load(c32 (&v)[8], const c32* sm, int t) {
     const int p = t >> 3, a = t & 7;
@@ -107,6 +119,18 @@ MAF_HD void fft512_step2_store(c32 (&v)[8], c32* sm, const c32* tw2, int t) {
     for (int c = 0; c < 8; ++c) {
         c32 w = tw2[c * 8 + a];
         sm[fft512_x2(p, a, c)] = (c == 0) ? v[0] : cmul(v[c], w);
+    }
+}
+// twiddles e^{-2 pi i 8 a c / 512} = w^c from the per-thread base w = e^{-2 pi i a / 64}, a = t & 7
+MAF_HD void fft512_step2_store_base(c32 (&v)[8], c32* sm, c32 w2, int t) {
+    const int p = t >> 3, a = t & 7;
+    fft8(v);
+    c32 w = w2;
+    sm[fft512_x2(p, a, 0)] = v[0];
+#pragma unroll
+    for (int c = 1; c < 8; ++c) {
+        sm[fft512_x2(p, a, c)] = cmul(v[c], w);
+        if (c < 7) w = cmul(w, w2);
     }
 }
 // (barrier)

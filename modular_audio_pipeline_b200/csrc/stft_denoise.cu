@@ -33,6 +33,17 @@ __device__ __forceinline__ void group_fft512(c32 (&v)[8], c32* sm, const c32* tw
     fft512_step3(v, sm, t);
 }
 
+// the same transform with the twiddles rebuilt from two per-thread bases (no twiddle tables in shared memory)
+__device__ __forceinline__ void group_fft512_base(c32 (&v)[8], c32* sm, c32 w1, c32 w2, int t, int g) {
+    fft512_step1_base(v, sm, w1, t);
+    group_bar(g);
+    fft512_step2_load(v, sm, t);
+    group_bar(g);
+    fft512_step2_store_base(v, sm, w2, t);
+    group_bar(g);
+    fft512_step3(v, sm, t);
+}
+
 // ============================================================================================================
 // K1  forward STFT.  A CTA stages the contiguous int16 span of a tile of STFT_TILE frames once (75 % overlap); every warp
 // transforms PAIRS of consecutive frames with the warp-level 1024-point complex FFT of fft_core.h (frame A in the real
@@ -852,18 +863,14 @@ __device__ __forceinline__ float w8s(int d) { const float s[8] = {0.f, 0.7071067
 
 constexpr int ISTFT_FR = ISTFT_SEG + 3;                 // 32 frames per CTA
 constexpr int OLA_LEN = (ISTFT_FR + 3) * HOP;           // 8960 floats
-constexpr size_t ISTFT_SMEM = sizeof(float) * OLA_LEN + sizeof(c32) * (FFT512_TW1 + FFT512_TW2) + sizeof(c32) * 264 +
-                              sizeof(c32) * 4 * FFT512_SMEM;
+constexpr size_t ISTFT_SMEM = sizeof(float) * OLA_LEN + sizeof(c32) * 4 * FFT512_SMEM;
 
 __global__ void __launch_bounds__(256, 3) istft_kernel(const c32* __restrict__ S, const float* __restrict__ M,
                                                     const Item* __restrict__ items, const Chunk* __restrict__ chunks, Consts cs,
                                                     int16_t* __restrict__ den16, int to_out, float* __restrict__ den_f32, int* __restrict__ peak) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* ola = reinterpret_cast<float*>(smem_raw);
-    c32* tw1 = reinterpret_cast<c32*>(ola + OLA_LEN);
-    c32* tw2 = tw1 + FFT512_TW1;
-    c32* tw1024 = tw2 + FFT512_TW2;
-    c32* fsm = tw1024 + 264;
+    c32* fsm = reinterpret_cast<c32*>(ola + OLA_LEN);
 
     const Chunk ch = chunks[blockIdx.y];
     const int seg_lo = PADS / HOP;                                  // first segment holding kept samples
@@ -880,10 +887,17 @@ __global__ void __launch_bounds__(256, 3) istft_kernel(const c32* __restrict__ S
         sincospif((float)(2 * t + 1) * (1.0f / 512.0f), &sn, &cs); wc1 = -0.25f * cs; ws1 = 0.25f * sn;
     }
 
+    // twiddle bases of this thread (the kernel is bound by shared-memory traffic: no twiddle tables, products of bases instead):
+    //   FFT step 1: e^{-2 pi i t p / 512} = w1^p;  step 2: e^{-2 pi i 8 a c / 512} = w2^c, a = t & 7;
+    //   real merge: e^{-2 pi i (t + 64 q) / 1024} = wt e^{-2 pi i q / 16}
+    c32 w1b, w2b, wtb;
+    {
+        float sn, cs_;
+        sincospif((float)t * (1.0f / 256.0f), &sn, &cs_); w1b = mk(cs_, -sn);
+        sincospif((float)(t & 7) * (1.0f / 32.0f), &sn, &cs_); w2b = mk(cs_, -sn);
+        sincospif((float)t * (1.0f / 512.0f), &sn, &cs_); wtb = mk(cs_, -sn);
+    }
     for (int i = tid; i < OLA_LEN; i += 256) ola[i] = 0.f;
-    for (int i = tid; i < FFT512_TW1; i += 256) tw1[i] = cs.tw1[i];
-    if (tid < FFT512_TW2) tw2[tid] = cs.tw2[tid];
-    for (int i = tid; i < 257; i += 256) tw1024[i] = cs.tw1024[i];
     __syncthreads();
 
     const int fbase = g0 - 1;                                       // local frame 0
@@ -934,7 +948,11 @@ __global__ void __launch_bounds__(256, 3) istft_kernel(const c32* __restrict__ S
                     z[256] = mk(2.f * pxn[0].x * pmn[0], 2.f * pxn[0].y * pmn[0]);   // 2 conj(Z256) = 2 X256
                 } else {
                     c32 zk, znk;
-                    irfft_merge_pair(mk(pxk[q].x * pmk[q], pxk[q].y * pmk[q]), mk(pxn[q].x * pmn[q], pxn[q].y * pmn[q]), tw1024[k], zk, znk);
+                    // e^{-2 pi i q / 16}, q = 1..3: (cos, -sin) of pi q / 8
+                    const c32 wq = q == 0 ? mk(1.f, 0.f) : q == 1 ? mk(0.92387953251128674f, -0.38268343236508978f)
+                                 : q == 2 ? mk(0.70710678118654752f, -0.70710678118654752f) : mk(0.38268343236508978f, -0.92387953251128674f);
+                    const c32 twk = q == 0 ? wtb : cmul(wtb, wq);
+                    irfft_merge_pair(mk(pxk[q].x * pmk[q], pxk[q].y * pmk[q]), mk(pxn[q].x * pmn[q], pxn[q].y * pmn[q]), twk, zk, znk);
                     z[k] = zk; z[512 - k] = znk;
                 }
             }
@@ -945,7 +963,7 @@ __global__ void __launch_bounds__(256, 3) istft_kernel(const c32* __restrict__ S
 #pragma unroll
         for (int m = 0; m < 8; ++m) v[m] = active ? z[t + 64 * m] : mk(0.f, 0.f);
         group_bar(g);
-        group_fft512(v, z, tw1, tw2, t, g);
+        group_fft512_base(v, z, w1b, w2b, t, g);
         if (active) {
             float2* o2 = reinterpret_cast<float2*>(ola + lf * HOP);
 #pragma unroll

@@ -22,6 +22,20 @@ static void fft512_emul(const std::vector<c32>& x, std::vector<c32>& X, const st
     for (int t = 0; t < 64; ++t) { fft512_step3(regs[t], sm.data(), t); int u = fft512_out_base(t); for (int d = 0; d < 8; ++d) X[u + 64 * d] = regs[t][d]; }
 }
 
+// fft512 with the twiddles built from per-thread bases (fft512_step1_base / fft512_step2_store_base)
+static void fft512_emul_base(const std::vector<c32>& x, std::vector<c32>& X) {
+    const double PI = 3.14159265358979323846;
+    std::vector<c32> sm(FFT512_SMEM);
+    c32 regs[64][8];
+    for (int t = 0; t < 64; ++t) {
+        for (int m = 0; m < 8; ++m) regs[t][m] = x[t + 64 * m];
+        fft512_step1_base(regs[t], sm.data(), mk((float)cos(2 * PI * t / 512), (float)-sin(2 * PI * t / 512)), t);
+    }
+    for (int t = 0; t < 64; ++t) fft512_step2_load(regs[t], sm.data(), t);
+    for (int t = 0; t < 64; ++t) fft512_step2_store_base(regs[t], sm.data(), mk((float)cos(2 * PI * (t & 7) / 64), (float)-sin(2 * PI * (t & 7) / 64)), t);
+    for (int t = 0; t < 64; ++t) { fft512_step3(regs[t], sm.data(), t); for (int d = 0; d < 8; ++d) X[t + 64 * d] = regs[t][d]; }
+}
+
 int main() {
     const double PI = 3.14159265358979323846;
     int fails = 0;
@@ -41,6 +55,14 @@ int main() {
             err = fmax(err, std::abs(s - cd(X[k].x, X[k].y))); nrm = fmax(nrm, std::abs(s));
         }
         printf("fft512   max err %.3e (max |X| %.3f)\n", err, nrm); if (err > 1e-4) ++fails;
+        std::vector<c32> Xb(512);
+        fft512_emul_base(x, Xb);
+        double errb = 0;
+        for (int k = 0; k < 512; ++k) {
+            cd s = 0; for (int n = 0; n < 512; ++n) s += cd(x[n].x, x[n].y) * std::polar(1.0, -2 * PI * n * k / 512.0);
+            errb = fmax(errb, std::abs(s - cd(Xb[k].x, Xb[k].y)));
+        }
+        printf("fft512 (twiddles from bases) max err %.3e\n", errb); if (errb > 1e-4) ++fails;
     }
     // ---- rfft1024 forward and inverse
     {
