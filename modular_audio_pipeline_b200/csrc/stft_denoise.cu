@@ -861,11 +861,13 @@ void launch_smooth_mask(const uint32_t* bits, const uint8_t* rowflag, const Chun
 __device__ __forceinline__ float w8c(int d) { const float c[8] = {1.f, 0.70710678118654752f, 0.f, -0.70710678118654752f, -1.f, -0.70710678118654752f, 0.f, 0.70710678118654752f}; return c[d]; }
 __device__ __forceinline__ float w8s(int d) { const float s[8] = {0.f, 0.70710678118654752f, 1.f, 0.70710678118654752f, 0.f, -0.70710678118654752f, -1.f, -0.70710678118654752f}; return s[d]; }
 
-constexpr int ISTFT_FR = ISTFT_SEG + 3;                 // 32 frames per CTA
-constexpr int OLA_LEN = (ISTFT_FR + 3) * HOP;           // 8960 floats
+constexpr int ISTFT_FR = ISTFT_SEG + 3;                 // 64 frames per CTA, 16 per group
+static_assert(ISTFT_FR % 4 == 0, "four groups share the frames of a CTA");
+constexpr int GSPAN = (ISTFT_FR / 4 + 3) * HOP;          // samples covered by the frames of one group (16 frames: 4864)
+constexpr int OLA_LEN = 4 * GSPAN;                      // four group spans (they overlap by 768 samples in time)
 constexpr size_t ISTFT_SMEM = sizeof(float) * OLA_LEN + sizeof(c32) * 4 * FFT512_SMEM;
 
-__global__ void __launch_bounds__(256, 3) istft_kernel(const c32* __restrict__ S, const float* __restrict__ M,
+__global__ void __launch_bounds__(256, 2) istft_kernel(const c32* __restrict__ S, const float* __restrict__ M,
                                                     const Item* __restrict__ items, const Chunk* __restrict__ chunks, Consts cs,
                                                     int16_t* __restrict__ den16, int to_out, float* __restrict__ den_f32, int* __restrict__ peak) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -897,8 +899,6 @@ __global__ void __launch_bounds__(256, 3) istft_kernel(const c32* __restrict__ S
         sincospif((float)(t & 7) * (1.0f / 32.0f), &sn, &cs_); w2b = mk(cs_, -sn);
         sincospif((float)t * (1.0f / 512.0f), &sn, &cs_); wtb = mk(cs_, -sn);
     }
-    for (int i = tid; i < OLA_LEN; i += 256) ola[i] = 0.f;
-    __syncthreads();
 
     const int fbase = g0 - 1;                                       // local frame 0
     // Group g walks local frames 8 g .. 8 g + 7.  The masked spectrum of the NEXT frame is fetched into registers while the
@@ -933,18 +933,31 @@ __global__ void __launch_bounds__(256, 3) istft_kernel(const c32* __restrict__ S
         if (f1 >= 0 && f1 < ch.n_frames) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(S + (ch.row0 + f1) * S_PITCH) + 128 * t));
     }
     fetch((ISTFT_FR / 4) * g);
+    // Overlap-add in registers: the group's frames advance by 256 samples = two of the thread's 128-sample strides, so thread t
+    // accumulates the SAME addresses across consecutive frames.  win[j] holds the group-span positions 128 (2 r + j) + 2 t (+1);
+    // after frame r the two oldest entries are complete and go to the group's own span buffer (plain stores, no read-modify-
+    // write); the four group spans overlap by 768 samples and are added in a fixed order when the samples are emitted.
+    float2 win[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) win[j] = make_float2(0.f, 0.f);
+    float2* gspan = reinterpret_cast<float2*>(ola + g * GSPAN);
     for (int r = 0; r < ISTFT_FR / 4; ++r) {
         const int lf = r + (ISTFT_FR / 4) * g;
         const int f = fbase + lf;
         const bool active = f >= 0 && f < ch.n_frames;
         c32* z = fsm + g * FFT512_SMEM;
+        c32 v[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) v[m] = mk(0.f, 0.f);
         if (active) {
+            // thread t produces z[t + 64 q] (kept: they are its own FFT inputs v[q]) and z[512 - t - 64 q], which are the inputs
+            // v[7 - q] of thread 64 - t: only those four cross the group through shared memory
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int k = t + 64 * q;
                 if (k == 0) {
                     const float a = pxk[0].x * pmk[0], b = pxk[0].y * pm512;
-                    z[0] = mk(a + b, -(a - b));                     // 2 conj(Z0)
+                    v[0] = mk(a + b, -(a - b));                     // 2 conj(Z0)
                     z[256] = mk(2.f * pxn[0].x * pmn[0], 2.f * pxn[0].y * pmn[0]);   // 2 conj(Z256) = 2 X256
                 } else {
                     c32 zk, znk;
@@ -953,36 +966,36 @@ __global__ void __launch_bounds__(256, 3) istft_kernel(const c32* __restrict__ S
                                  : q == 2 ? mk(0.70710678118654752f, -0.70710678118654752f) : mk(0.38268343236508978f, -0.92387953251128674f);
                     const c32 twk = q == 0 ? wtb : cmul(wtb, wq);
                     irfft_merge_pair(mk(pxk[q].x * pmk[q], pxk[q].y * pmk[q]), mk(pxn[q].x * pmn[q], pxn[q].y * pmn[q]), twk, zk, znk);
-                    z[k] = zk; z[512 - k] = znk;
+                    v[q] = zk; z[512 - k] = znk;
                 }
             }
         }
         if (r + 1 < ISTFT_FR / 4) fetch(lf + 1);
         group_bar(g);
-        c32 v[8];
+        if (active) {
 #pragma unroll
-        for (int m = 0; m < 8; ++m) v[m] = active ? z[t + 64 * m] : mk(0.f, 0.f);
+            for (int m = 4; m < 8; ++m) v[m] = z[t + 64 * m];
+        }
         group_bar(g);
         group_fft512_base(v, z, w1b, w2b, t, g);
-        if (active) {
-            float2* o2 = reinterpret_cast<float2*>(ola + lf * HOP);
 #pragma unroll
-            for (int d = 0; d < 8; ++d) {
-                const int n = t + 64 * d;
-                // synthesis window hann / 2 at samples 2 n, 2 n + 1 by angle addition (angle = alpha_t + d pi / 4): two FMAs each
-                // instead of a shared-memory load -- this kernel is bound by shared-memory traffic
-                const float cd = w8c(d), sd = w8s(d);
-                const float w0 = fmaf(wc0, cd, fmaf(ws0, sd, 0.25f)), w1 = fmaf(wc1, cd, fmaf(ws1, sd, 0.25f));
-                float2 acc = o2[n];
-                acc.x += v[d].x * w0;
-                acc.y += -v[d].y * w1;
-                o2[n] = acc;
-            }
+        for (int d = 0; d < 8; ++d) {
+            // synthesis window hann / 2 at samples 2 n, 2 n + 1 (n = t + 64 d) by angle addition (angle = alpha_t + d pi / 4): two
+            // FMAs each instead of a shared-memory load -- this kernel is bound by shared-memory traffic
+            const float cd = w8c(d), sd = w8s(d);
+            const float w0 = fmaf(wc0, cd, fmaf(ws0, sd, 0.25f)), w1 = fmaf(wc1, cd, fmaf(ws1, sd, 0.25f));
+            win[d].x += v[d].x * w0;
+            win[d].y += -v[d].y * w1;
         }
-        // Frames of one group overlap their successors (group barrier).  Across groups only rounds 0..2 of group g and
-        // rounds 5..7 of group g - 1 touch the same samples: one CTA-wide barrier between round 3 and round 4 orders them.
-        if (r == 3) __syncthreads(); else group_bar(g);
+        gspan[64 * (2 * r) + t] = win[0];
+        gspan[64 * (2 * r + 1) + t] = win[1];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) win[j] = win[j + 2];
+        win[6] = make_float2(0.f, 0.f); win[7] = make_float2(0.f, 0.f);
+        group_bar(g);                                               // the scratch z is rewritten by the next frame
     }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) gspan[64 * (2 * (ISTFT_FR / 4) + j) + t] = win[j];
     __syncthreads();
     // emit: segment g covers padded-chunk samples [256 g, 256 g + 256) = ola[768 + 256 (g - g0) ...]
     int pk = 0;
@@ -992,7 +1005,13 @@ __global__ void __launch_bounds__(256, 3) istft_kernel(const c32* __restrict__ S
         const long long j = (long long)g0 * HOP + i;
         const long long o = j - PADS;
         if (o < 0 || o >= ch.keep) continue;
-        const float val = ola[3 * HOP + i] / 1.5f;
+        // CTA position x = 768 + i lies in the span of group x / 2048 and, for the first 768 samples of that span, also in the
+        // previous group's; fixed order: earlier group first
+        constexpr int GSTRIDE = (ISTFT_FR / 4) * HOP;               // samples between the starts of two group spans
+        const int x = 3 * HOP + i, ga = x / GSTRIDE, xo = x - ga * GSTRIDE;
+        float sum = ola[ga * GSPAN + xo];
+        if (ga > 0 && xo < 3 * HOP) sum = ola[(ga - 1) * GSPAN + GSTRIDE + xo] + sum;
+        const float val = sum / 1.5f;
         const int q = (int)(short)(int)val;                         // astype(int16): truncate, keep low 16 bits
         den16[obase + o] = (int16_t)q;
         if (den_f32) den_f32[fbase_o + o] = val;
