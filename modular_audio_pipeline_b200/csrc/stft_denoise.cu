@@ -547,8 +547,14 @@ constexpr int SM_ROW = MAX_NF + 520 + MAX_NF;     // 584 floats, multiple of 4: 
 constexpr int NSM_THREADS = 544;                  // 17 warps: one thread per bin in the recurrence phase
 constexpr size_t NSM_SMEM = sizeof(float) * NS_TILE * SM_ROW;
 
-// frequency taps on one shared-memory row segment: 8 consecutive outputs starting at bin k0 (src = &row[MAX_NF + k0])
-__device__ __forceinline__ void freq_taps8(const float* src, int nf, const float* vf, float (&out)[8]) {
+// Column swizzle of the mask rows in shared memory: in every other block of 32 floats adjacent float4 groups trade places.
+// The frequency taps read float4s at a stride of two groups per lane -- unswizzled, the eight lanes of a quarter warp fall on
+// four bank groups (a 2-way conflict on every load); swizzled they cover all eight.  Writes of consecutive columns stay
+// conflict-free (the swizzle permutes inside a 32-float block).
+__device__ __forceinline__ int swz(int c) { return c ^ (((c >> 5) & 1) << 2); }
+
+// frequency taps on one shared-memory row (`row` = start of the row, outputs = bins k0 .. k0 + 7, i.e. columns MAX_NF + k0 ...)
+__device__ __forceinline__ void freq_taps8(const float* row, int k0, int nf, const float* vf, float (&out)[8]) {
 #pragma unroll
     for (int o = 0; o < 8; ++o) out[o] = 0.f;
     if (nf == 16) {
@@ -556,7 +562,7 @@ __device__ __forceinline__ void freq_taps8(const float* src, int nf, const float
         float in[40];
 #pragma unroll
         for (int i = 0; i < 10; ++i) {
-            const float4 q = *reinterpret_cast<const float4*>(src - 16 + 4 * i);
+            const float4 q = *reinterpret_cast<const float4*>(row + swz(MAX_NF + k0 - 16 + 4 * i));
             in[4 * i] = q.x; in[4 * i + 1] = q.y; in[4 * i + 2] = q.z; in[4 * i + 3] = q.w;
         }
         float b1[24];                                   // b1[i] = sum in[i .. i + 16]  (centre k0 - 8 + i)
@@ -578,7 +584,7 @@ __device__ __forceinline__ void freq_taps8(const float* src, int nf, const float
         for (int tp = 0; tp <= 2 * nf; ++tp) {
             const float wt = vf[tp];
 #pragma unroll
-            for (int o = 0; o < 8; ++o) out[o] += wt * src[o + tp - nf];
+            for (int o = 0; o < 8; ++o) out[o] += wt * row[swz(MAX_NF + k0 + o + tp - nf)];
         }
     }
 }
@@ -655,7 +661,7 @@ __device__ __forceinline__ void ns_walk(const c32* __restrict__ sp, int k, int b
                     float acc = vt[0] * w[0];
 #pragma unroll
                     for (int j = 1; j < 2 * NT + 1; ++j) acc = fmaf(vt[j], w[j], acc);
-                    rows[lr * SM_ROW + MAX_NF + k] = acc;
+                    rows[lr * SM_ROW + swz(MAX_NF + k)] = acc;
                 }
             }
         }
@@ -678,7 +684,7 @@ __global__ void __launch_bounds__(NSM_THREADS, 2) ns_mask_smooth_kernel(const c3
     // zero halos left and right of the 513 bins
     for (int i = tid; i < NS_TILE * (SM_ROW - NBIN); i += NSM_THREADS) {
         const int r = i / (SM_ROW - NBIN), c = i - r * (SM_ROW - NBIN);
-        rows[r * SM_ROW + (c < MAX_NF ? c : c + NBIN)] = 0.f;
+        rows[r * SM_ROW + swz(c < MAX_NF ? c : c + NBIN)] = 0.f;
     }
     if (tid < NBIN) {
         const int k = tid;
@@ -699,7 +705,7 @@ __global__ void __launch_bounds__(NSM_THREADS, 2) ns_mask_smooth_kernel(const c3
         if (f < 0 || f >= F) continue;
         const int k0 = 8 * seg;
         float out[8];
-        freq_taps8(&rows[lr * SM_ROW + MAX_NF + k0], nf, taps.vf, out);
+        freq_taps8(&rows[lr * SM_ROW], k0, nf, taps.vf, out);
         float* dst = M + (ch.row0 + f) * M_PITCH + k0;
         if (k0 + 8 <= NBIN) {
             *reinterpret_cast<float4*>(dst) = make_float4(fmaf(out[0], prop, lo), fmaf(out[1], prop, lo), fmaf(out[2], prop, lo), fmaf(out[3], prop, lo));
@@ -763,7 +769,7 @@ __global__ void __launch_bounds__(NSM_THREADS, 2) smooth_mask_kernel(const uint3
     const int tid = threadIdx.x;
     for (int i = tid; i < NS_TILE * (SM_ROW - NBIN); i += NSM_THREADS) {
         const int r = i / (SM_ROW - NBIN), c = i - r * (SM_ROW - NBIN);
-        rows[r * SM_ROW + (c < MAX_NF ? c : c + NBIN)] = 0.f;
+        rows[r * SM_ROW + swz(c < MAX_NF ? c : c + NBIN)] = 0.f;
     }
     if (tid < NBIN) {
         const int k = tid;
@@ -796,7 +802,7 @@ __global__ void __launch_bounds__(NSM_THREADS, 2) smooth_mask_kernel(const uint3
                         float acc = vt[0] * w[0];
 #pragma unroll
                         for (int j = 1; j < 2 * NT + 1; ++j) acc = fmaf(vt[j], w[j], acc);
-                        rows[lr * SM_ROW + MAX_NF + k] = acc;
+                        rows[lr * SM_ROW + swz(MAX_NF + k)] = acc;
                     }
                 }
             }
@@ -810,7 +816,7 @@ __global__ void __launch_bounds__(NSM_THREADS, 2) smooth_mask_kernel(const uint3
         if (f >= F) continue;
         const int k0 = 8 * seg;
         float out[8];
-        freq_taps8(&rows[lr * SM_ROW + MAX_NF + k0], nf, taps.vf, out);
+        freq_taps8(&rows[lr * SM_ROW], k0, nf, taps.vf, out);
         float* dst = M + (ch.row0 + f) * M_PITCH + k0;
         if (k0 + 8 <= NBIN) {
             *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
