@@ -163,6 +163,15 @@ int64_t maf_front_door_out_len(int64_t n_frames_in, int32_t in_rate, int32_t out
 int maf_front_door(maf_ctx* ctx, const int16_t* pcm_dev, int64_t n_frames_in, int32_t channels, int32_t in_rate, int32_t out_rate,
                    int32_t peak_normalize, int16_t* out_dev, void* stream);
 
+/* ---- 30 s encoder windows, the hand-off into a Whisper encoder on the same GPU (transcriber.py:229-238 ->
+ * whisper/transcribe.py seek loop: mel_segment = mel[:, seek : seek + segment_size]; pad_or_trim(mel_segment, N_FRAMES)
+ * .to(dtype); faster-whisper slices features[:, seek : seek + nb_max_frames] the same way).  mel_dev is one recording's
+ * [n_mels, frames] float32 log-mel; out_dev receives [n_windows, n_mels, window_frames] float32 (out_fp16 = 0) or IEEE
+ * half, round to nearest even (out_fp16 = 1): out[w, m, f] = mel[m, seeks[w] + f] for f < lens[w] (lens_dev NULL:
+ * window_frames) and seeks[w] + f < frames, else 0.  seeks_dev / lens_dev are int32 device arrays of n_windows entries. */
+int maf_mel_windows(maf_ctx* ctx, const float* mel_dev, int32_t n_mels, int64_t frames, const int32_t* seeks_dev,
+                    const int32_t* lens_dev, int32_t n_windows, int32_t window_frames, int32_t out_fp16, void* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

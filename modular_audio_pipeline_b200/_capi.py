@@ -74,6 +74,7 @@ SYMBOLS = {
     "maf_set_noise_clips_dev": (C.c_int, [_P, _P, _P]),
     "maf_front_door_out_len": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
     "maf_front_door": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "maf_mel_windows": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
 }
 
 _lib = None

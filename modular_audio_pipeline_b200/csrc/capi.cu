@@ -931,3 +931,15 @@ extern "C" int maf_front_door(maf_ctx* ctx, const int16_t* pcm, int64_t n_frames
     CU(cudaGetLastError());
     return MAF_OK;
 }
+
+// ---- encoder windows ---------------------------------------------------------------------------------------------
+extern "C" int maf_mel_windows(maf_ctx* ctx, const float* mel, int32_t n_mels, int64_t frames, const int32_t* seeks, const int32_t* lens,
+                               int32_t n_windows, int32_t window_frames, int32_t out_fp16, void* out, void* stream) {
+    if (!ctx || !mel || !seeks || !out) return fail(MAF_ERR_INVALID, "maf_mel_windows: bad argument");
+    if (n_mels <= 0 || n_mels > 65535 || frames <= 0 || n_windows < 0 || window_frames <= 0)
+        return fail(MAF_ERR_INVALID, "maf_mel_windows: bad shape");
+    CU(cudaSetDevice(ctx->device));
+    launch_mel_windows(mel, n_mels, frames, seeks, lens, n_windows, window_frames, out_fp16, out, (cudaStream_t)stream);
+    CU(cudaGetLastError());
+    return MAF_OK;
+}

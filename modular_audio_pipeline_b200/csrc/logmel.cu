@@ -7,6 +7,9 @@
 //                        sparse Slaney mel projection, log10(max(., 1e-10)); per-recording running maximum.
 //                        The spectrum never leaves shared memory.
 //   mel_finalize_kernel  max(L, gmax - 8), (L + 4) / 4 in place once the recording-wide maximum is known.
+//   mel_windows_kernel   the encoder's 30 s windows: mel[:, seek : seek + len] zero-padded to N_FRAMES, float32 or half
+//                        (whisper/transcribe.py seek loop: pad_or_trim(mel_segment, N_FRAMES).to(dtype)).
+#include <cuda_fp16.h>
 #include "maf_common.cuh"
 
 namespace maf {
@@ -285,6 +288,42 @@ void launch_mel_finalize(float* mel_out, const Item* items, int n_items, int n_m
         const int ny = n_items - y0 < 32768 ? n_items - y0 : 32768;
         dim3 grid(max_tiles, ny);
         mel_finalize_kernel<<<grid, 256, 0, st>>>(mel_out, items + y0, n_mels, mel_max + y0, tile_min + (long long)y0 * max_tiles);
+    }
+}
+
+// out[w, m, f] = (f < len_w && seek_w + f < frames) ? mel[m, seek_w + f] : 0; one CTA per (mel row, window), two frames per
+// thread and step, so a warp reads 256 contiguous bytes and writes 128 (half) or 256 (float) contiguous bytes.
+template <typename OUT>
+__global__ void __launch_bounds__(256) mel_windows_kernel(const float* __restrict__ mel, long long frames, const int* __restrict__ seeks,
+                                                          const int* __restrict__ lens, int window_frames, OUT* __restrict__ out) {
+    const int m = blockIdx.x, w = blockIdx.y;
+    const long long seek = seeks[w];
+    long long len = lens ? (long long)lens[w] : (long long)window_frames;
+    len = min(len, frames - seek);                                          // <= 0: an all-zero window
+    const float* row = mel + (long long)m * frames + seek;
+    OUT* orow = out + ((long long)w * gridDim.x + m) * window_frames;
+    for (int f = 2 * threadIdx.x; f < window_frames; f += 512) {
+        const float a = (f < len && seek + f >= 0) ? row[f] : 0.f;
+        const float b = (f + 1 < len && seek + f + 1 >= 0) ? row[f + 1] : 0.f;
+        if constexpr (sizeof(OUT) == 2) {
+            if (f + 1 < window_frames && (window_frames & 1) == 0) *reinterpret_cast<__half2*>(orow + f) = __floats2half2_rn(a, b);
+            else { orow[f] = __float2half_rn(a); if (f + 1 < window_frames) orow[f + 1] = __float2half_rn(b); }
+        } else {
+            if (f + 1 < window_frames && (window_frames & 1) == 0) *reinterpret_cast<float2*>(orow + f) = make_float2(a, b);
+            else { orow[f] = a; if (f + 1 < window_frames) orow[f + 1] = b; }
+        }
+    }
+}
+
+void launch_mel_windows(const float* mel, int n_mels, long long frames, const int* seeks, const int* lens, int n_windows,
+                        int window_frames, int out_fp16, void* out, cudaStream_t st) {
+    if (n_windows <= 0 || n_mels <= 0 || window_frames <= 0) return;
+    for (int w0 = 0; w0 < n_windows; w0 += 32768) {
+        const int nw = n_windows - w0 < 32768 ? n_windows - w0 : 32768;
+        dim3 grid(n_mels, nw);
+        const long long o = (long long)w0 * n_mels * window_frames;
+        if (out_fp16) mel_windows_kernel<__half><<<grid, 256, 0, st>>>(mel, frames, seeks + w0, lens ? lens + w0 : nullptr, window_frames, (__half*)out + o);
+        else mel_windows_kernel<float><<<grid, 256, 0, st>>>(mel, frames, seeks + w0, lens ? lens + w0 : nullptr, window_frames, (float*)out + o);
     }
 }
 

@@ -75,6 +75,20 @@ class FrontEnd:
                 raise MafError(self._lib.maf_last_error().decode())
         return out[:n_out]
 
+    def mel_windows(self, mel: torch.Tensor, seeks: torch.Tensor, lens: Optional[torch.Tensor], window_frames: int,
+                    out: torch.Tensor) -> torch.Tensor:
+        """Encoder windows ``out[w, m, f] = mel[m, seeks[w] + f]`` (zero past ``lens[w]`` / the end of the recording), float32 or
+        float16 -- maf_mel_windows in include/maf.h; the whisper seek loop behind transcriber.py:229-238."""
+        n = int(seeks.numel())
+        with torch.cuda.device(self.device):
+            rc = self._lib.maf_mel_windows(self._h, mel.data_ptr(), int(mel.shape[0]), int(mel.shape[1]), seeks.data_ptr(),
+                                           lens.data_ptr() if lens is not None else None, n, int(window_frames),
+                                           int(out.dtype == torch.float16), out.data_ptr(),
+                                           torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            raise MafError(self._lib.maf_last_error().decode())
+        return out
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             for p in list(self._plans):          # plans point into the context: release them first

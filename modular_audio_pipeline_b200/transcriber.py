@@ -81,6 +81,26 @@ class GpuLogMelFrontEnd:
             return torch.nn.functional.pad(mel, (0, length - mel.shape[-1]))
         return mel
 
+    def windows(self, mel: torch.Tensor, seeks, lens=None, length: int = N_FRAMES, dtype: torch.dtype = torch.float16) -> torch.Tensor:
+        """All encoder windows of one recording in one launch: ``out[w] = pad_or_trim(mel[:, seeks[w] : seeks[w] + lens[w]],
+        length).to(dtype)`` (the seek loop of whisper/transcribe.py, behind transcriber.py:229-238), float16 or float32,
+        ``[n_windows, n_mels, length]`` on the device.  ``mel`` is a float32 CUDA tensor ``[n_mels, frames]``."""
+        fe = self.frontend
+        if mel.dtype != torch.float32 or mel.dim() != 2 or not mel.is_cuda or mel.device != fe.device:
+            raise ValueError("expected a float32 [n_mels, frames] tensor on the front-end's device")
+        if dtype not in (torch.float16, torch.float32):
+            raise ValueError("dtype must be torch.float16 or torch.float32")
+        mel = mel.contiguous()
+        seeks_t = torch.as_tensor(seeks, dtype=torch.int32).reshape(-1).to(fe.device)
+        lens_t = None if lens is None else torch.as_tensor(lens, dtype=torch.int32).reshape(-1).to(fe.device)
+        if lens_t is not None and lens_t.numel() != seeks_t.numel():
+            raise ValueError("seeks and lens differ in length")
+        n = seeks_t.numel()
+        out = torch.empty(n, mel.shape[0], length, dtype=dtype, device=fe.device)
+        if n:
+            fe.mel_windows(mel, seeks_t, lens_t, length, out)
+        return out
+
 
 class GpuFrontEndTranscriber:
     """TranscriberProtocol (protocols.py:119-133) adapter: same transcriber, GPU log-mel front-end."""

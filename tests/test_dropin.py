@@ -203,3 +203,28 @@ def test_transcriber_adapter_with_fake_models(frontend):
     assert feats.shape == want.shape and np.abs(feats - want).max() <= 1e-4
     m = GpuLogMelFrontEnd.pad_or_trim(torch.zeros(80, 10), 3000)
     assert m.shape == (80, 3000)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float16", "float32"])
+def test_encoder_windows_bit_exact(frontend, dtype):
+    """The 30 s windows the encoder consumes (whisper/transcribe.py seek loop: mel[:, seek:seek+size] -> pad_or_trim ->
+    .to(dtype)) from ONE launch, bit-exact against the torch restatement -- incl. odd seeks, short last windows, a
+    window past the end, explicit segment sizes, and an odd window length."""
+    from modular_audio_pipeline_b200.transcriber import GpuLogMelFrontEnd
+    dt = getattr(torch, dtype)
+    fe = GpuLogMelFrontEnd(frontend.device)
+    fe._fe = frontend
+    g = torch.Generator().manual_seed(5)
+    mel = (torch.randn(80, 9000 + 137, generator=g) * 0.7).to(frontend.device)
+    seeks = [0, 3000, 2999, 6001, 8999, 9137, 12000, 1]
+    lens = [3000, 3000, 1234, 3000, 138, 3000, 3000, 0]
+    for length, ln in ((3000, None), (3000, lens), (1501, None)):
+        got = fe.windows(mel, seeks, ln, length=length, dtype=dt)
+        assert got.shape == (len(seeks), 80, length) and got.dtype == dt
+        for w, sk in enumerate(seeks):
+            size = length if ln is None else min(ln[w], length)
+            seg = mel[:, sk:sk + size]
+            want = GpuLogMelFrontEnd.pad_or_trim(seg, length).to(dt)
+            assert torch.equal(got[w], want), (dtype, length, w)
+    assert fe.windows(mel, [], None).shape == (0, 80, 3000)
