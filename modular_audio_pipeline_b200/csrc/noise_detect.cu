@@ -166,10 +166,24 @@ __device__ double np_lerp(double a, double b, double t) {
     return __dadd_rn(a, __dmul_rn(d, t));
 }
 
-// k-th smallest (0-based) of non-negative floats by radix select on their bit patterns; also returns via *next the
+// Recordings of up to SEL_CACHE * SEL_THREADS frames (82 s) keep their statistics in registers -- element tid + 1024 j in
+// slot j -- so the five passes over the energies and the two over the counts never go back to global memory.
+constexpr int SEL_CACHE = 8;
+
+template <typename FN>
+__device__ __forceinline__ void for_each_energy(bool cached, const float (&eR)[SEL_CACHE], const float* __restrict__ v, int n, FN fn) {
+    if (cached) {
+#pragma unroll
+        for (int j = 0; j < SEL_CACHE; ++j) { if ((int)threadIdx.x + j * SEL_THREADS < n) fn(__float_as_uint(eR[j])); }
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) fn(__float_as_uint(v[i]));
+    }
+}
+
+// k-th smallest (0-based) of non-negative floats by radix select on their bit patterns; also returns via vk1 the
 // (k+1)-th smallest.  All threads of the CTA call this; hist is 256 ints of shared memory, scratch 4 ints.
-__device__ void radix_select2(const float* __restrict__ v, int n, int k, unsigned* hist, unsigned* scratch, float& vk,
-                              float& vk1) {
+__device__ void radix_select2(bool cached, const float (&eR)[SEL_CACHE], const float* __restrict__ v, int n, int k, unsigned* hist,
+                              unsigned* scratch, float& vk, float& vk1) {
     unsigned prefix = 0, mask = 0;
     int kk = k;
     for (int shift = 24; shift >= 0; shift -= 8) {
@@ -177,14 +191,13 @@ __device__ void radix_select2(const float* __restrict__ v, int n, int k, unsigne
         __syncthreads();
         {   // neighbouring frames mostly share a digit: aggregate runs locally before touching shared memory
             int cur = -1; unsigned run = 0;
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                unsigned u = __float_as_uint(v[i]);
-                if ((u & mask) != prefix) continue;
-                int d = (u >> shift) & 255;
-                if (d == cur) { ++run; continue; }
+            for_each_energy(cached, eR, v, n, [&](unsigned u) {
+                if ((u & mask) != prefix) return;
+                const int d = (u >> shift) & 255;
+                if (d == cur) { ++run; return; }
                 if (run) atomicAdd(&hist[cur], run);
                 cur = d; run = 1;
-            }
+            });
             if (run) atomicAdd(&hist[cur], run);
         }
         __syncthreads();
@@ -196,7 +209,7 @@ __device__ void radix_select2(const float* __restrict__ v, int n, int k, unsigne
             for (int j = 0; j < 8; ++j) { h[j] = hist[8 * lane + j]; tot += h[j]; }
             unsigned incl = tot;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            for (int o = 1; o < 32; o <<= 1) { const unsigned v2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v2; }
             const unsigned excl = incl - tot;
             const unsigned hit = __ballot_sync(0xffffffffu, incl > (unsigned)kk);
             if (hit == 0) { if (lane == 31) { scratch[0] = 256; scratch[1] = incl; } }
@@ -215,11 +228,9 @@ __device__ void radix_select2(const float* __restrict__ v, int n, int k, unsigne
     if (threadIdx.x == 0) { scratch[2] = 0; scratch[3] = 0x7f800000u; }
     __syncthreads();
     unsigned cnt = 0, mn = 0x7f800000u;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        unsigned u = __float_as_uint(v[i]);
-        if (u <= prefix) ++cnt; else mn = min(mn, u);
-    }
-    atomicAdd(&scratch[2], cnt); atomicMin(&scratch[3], mn);
+    for_each_energy(cached, eR, v, n, [&](unsigned u) { if (u <= prefix) ++cnt; else mn = min(mn, u); });
+    cnt = __reduce_add_sync(0xffffffffu, cnt); mn = __reduce_min_sync(0xffffffffu, mn);
+    if ((threadIdx.x & 31) == 0) { if (cnt) atomicAdd(&scratch[2], cnt); atomicMin(&scratch[3], mn); }
     __syncthreads();
     vk1 = (scratch[2] > (unsigned)(k + 1)) ? vk : __uint_as_float(scratch[3]);
     __syncthreads();
@@ -227,40 +238,131 @@ __device__ void radix_select2(const float* __restrict__ v, int n, int k, unsigne
 
 struct RunSummary { int all, lead, trail, best_len, best_start; };
 
+// merge of the summaries of two adjacent frame ranges (L before R); lenL / lenR are their lengths, startR = first frame of R
+__device__ __forceinline__ RunSummary merge_runs(const RunSummary& L, int lenL, const RunSummary& R, int lenR, int startR) {
+    RunSummary o;
+    if (lenL <= 0) return R;
+    if (lenR <= 0) return L;
+    o.all = L.all && R.all;
+    o.lead = L.all ? lenL + R.lead : L.lead;
+    o.trail = R.all ? lenR + L.trail : R.trail;
+    o.best_len = L.best_len; o.best_start = L.best_start;
+    if (!L.all && !R.all) {                                     // the run across the seam is closed on both sides
+        const int mid = L.trail + R.lead;
+        if (mid > o.best_len) { o.best_len = mid; o.best_start = startR - L.trail; }
+    }
+    if (R.best_len > o.best_len) { o.best_len = R.best_len; o.best_start = R.best_start; }
+    if (o.all) { o.best_len = 0; o.best_start = 0; }
+    return o;
+}
+
+// A frame range with its summary; len == 0 is the identity of merge_seg.
+struct RunSeg { RunSummary r; int start, len; };
+
+__device__ __forceinline__ RunSeg merge_seg(const RunSeg& L, const RunSeg& R) {
+    RunSeg o;
+    o.r = merge_runs(L.r, L.len, R.r, R.len, R.start);
+    o.start = L.len > 0 ? L.start : R.start;
+    o.len = L.len + R.len;
+    return o;
+}
+
+__device__ __forceinline__ RunSeg shfl_down_seg(const RunSeg& s, int d) {
+    RunSeg o;
+    o.r.all = __shfl_down_sync(0xffffffffu, s.r.all, d); o.r.lead = __shfl_down_sync(0xffffffffu, s.r.lead, d);
+    o.r.trail = __shfl_down_sync(0xffffffffu, s.r.trail, d); o.r.best_len = __shfl_down_sync(0xffffffffu, s.r.best_len, d);
+    o.r.best_start = __shfl_down_sync(0xffffffffu, s.r.best_start, d);
+    o.start = __shfl_down_sync(0xffffffffu, s.start, d); o.len = __shfl_down_sync(0xffffffffu, s.len, d);
+    return o;
+}
+
+// Ordered (thread order = frame order) reduction of the CTA's segments with the associative merge: a shuffle tree per warp,
+// then one over the warps' results.  wsm = 32 RunSeg of shared memory; the result is valid in thread 0.  Replaces a serial
+// walk of thread 0 over 1024 summaries (~25 us).
+__device__ RunSeg block_merge_segs(RunSeg s, RunSeg* wsm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const RunSeg o = shfl_down_seg(s, d);
+        if (lane + d < 32) s = merge_seg(s, o);
+    }
+    if (lane == 0) wsm[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+        RunSeg e; e.r.all = 1; e.r.lead = 0; e.r.trail = 0; e.r.best_len = 0; e.r.best_start = 0; e.start = 0; e.len = 0;
+        s = lane < n_warps ? wsm[lane] : e;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const RunSeg o = shfl_down_seg(s, d);
+            if (lane + d < 32) s = merge_seg(s, o);
+        }
+    }
+    return s;
+}
+
+// the reference's rule on the merged summary: candidates in order of their start -- the leading run (closed unless
+// everything is noise), then the best interior run; an open run at the end is dropped like in the reference's loop
+__device__ __forceinline__ void pick_run(const RunSummary& acc, int hop, int sr, int& found, int& bs, int& bl) {
+    bl = 0; bs = 0;
+    if (!acc.all && acc.lead > bl) { bl = acc.lead; bs = 0; }
+    if (acc.best_len > bl) { bl = acc.best_len; bs = acc.best_start; }
+    // (i - start) * hop / sr >= 0.1 ; longest first-maximum run.  Length ordering equals frame-count ordering.
+    found = bl > 0 && __ddiv_rn((double)((long long)bl * hop), (double)sr) >= 0.1;
+}
+
+
 __global__ void __launch_bounds__(SEL_THREADS) select_clip_kernel(const float* __restrict__ energies, const int* __restrict__ zc,
                                                                    const long long* __restrict__ foff, const int* __restrict__ fcount,
                                                                    const Item* __restrict__ items, int frame_len, int hop, int sr,
                                                                    int fallback_len, Clip* __restrict__ clips, int* __restrict__ seg_out) {
     __shared__ unsigned hist[2048];
     __shared__ unsigned scratch[4];
-    __shared__ RunSummary sums[SEL_THREADS];
+    __shared__ RunSeg wsm[32];
     __shared__ double thr[2];
     const int item = blockIdx.x;
     const Item it = items[item];
     const int F = fcount[item];
     const float* E = energies + foff[item];
     const int* Z = zc + foff[item];
-    int found = 0, best_s = 0, best_e = 0;
+    const int tid = threadIdx.x;
+    int found = 0, best_s = 0, best_l = 0;
     if (F > 0) {
+        const bool cached = F <= SEL_CACHE * SEL_THREADS;
+        float eR[SEL_CACHE]; int zR[SEL_CACHE];
+        if (cached) {
+#pragma unroll
+            for (int j = 0; j < SEL_CACHE; ++j) {
+                const int i = tid + j * SEL_THREADS;
+                eR[j] = i < F ? E[i] : 0.f; zR[j] = i < F ? Z[i] : 0;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < SEL_CACHE; ++j) { eR[j] = 0.f; zR[j] = 0; }
+        }
         // --- energy 20th percentile
         {
             double vi = __dmul_rn((double)(F - 1), 0.2);        // (n - 1) * (20 / 100)
             double lo = floor(vi);
             int k = (int)lo;
             float a, b;
-            radix_select2(E, F, k, hist, scratch, a, b);
+            radix_select2(cached, eR, E, F, k, hist, scratch, a, b);
             if (k + 1 > F - 1) b = a;
-            if (threadIdx.x == 0) thr[0] = np_lerp((double)a, (double)b, __dsub_rn(vi, lo));
+            if (tid == 0) thr[0] = np_lerp((double)a, (double)b, __dsub_rn(vi, lo));
         }
         // --- ZCR median from a histogram of the integer counts (count < frame_len <= 2047)
         {
-            for (int i = threadIdx.x; i < 2048; i += blockDim.x) hist[i] = 0;
+            for (int i = tid; i < 2048; i += blockDim.x) hist[i] = 0;
             __syncthreads();
-            for (int i = threadIdx.x; i < F; i += blockDim.x) atomicAdd(&hist[min(Z[i], 2047)], 1u);
+            if (cached) {
+#pragma unroll
+                for (int j = 0; j < SEL_CACHE; ++j) { if (tid + j * SEL_THREADS < F) atomicAdd(&hist[min(zR[j], 2047)], 1u); }
+            } else {
+                for (int i = tid; i < F; i += blockDim.x) atomicAdd(&hist[min(Z[i], 2047)], 1u);
+            }
             __syncthreads();
-            if (threadIdx.x < 32) {
+            if (tid < 32) {
                 // order statistics k and k + 1 of the counts: lanes sum 64 bins each, warp scan, the crossing lanes finish
-                const int lane = threadIdx.x;
+                const int lane = tid;
                 const double vi = __dmul_rn((double)(F - 1), 0.5);
                 const double lo = floor(vi);
                 const int k = (int)lo, k1 = min(k + 1, F - 1);
@@ -288,14 +390,26 @@ __global__ void __launch_bounds__(SEL_THREADS) select_clip_kernel(const float* _
         }
         __syncthreads();
         const double eT = thr[0], zT = thr[1];
-        // --- run detection: each thread summarises a contiguous segment, thread 0 stitches them in order
+        // --- run detection: each thread summarises a contiguous segment; the segments are merged in frame order.  In cached
+        // mode the (E < eT) & (ZCR > zT) flags are first written to shared memory (the histogram's 8192 bytes) by the threads
+        // that hold the values.
+        uint8_t* flags = reinterpret_cast<uint8_t*>(hist);
+        if (cached) {
+#pragma unroll
+            for (int j = 0; j < SEL_CACHE; ++j) {
+                const int i = tid + j * SEL_THREADS;
+                if (i < F) flags[i] = (uint8_t)(((double)eR[j] < eT) && (__ddiv_rn((double)zR[j], (double)frame_len) > zT));
+            }
+            __syncthreads();
+        }
         const int per = (F + SEL_THREADS - 1) / SEL_THREADS;
-        const int s0 = threadIdx.x * per, s1 = min(F, s0 + per);
+        const int s0 = min(F, tid * per), s1 = min(F, s0 + per);
+        RunSeg seg; seg.start = s0; seg.len = s1 - s0;
         RunSummary rs; rs.all = 1; rs.lead = 0; rs.trail = 0; rs.best_len = 0; rs.best_start = 0;
         {
             int run_start = -1; bool seen_false = false;
             for (int i = s0; i < s1; ++i) {
-                bool nz = ((double)E[i] < eT) && (__ddiv_rn((double)Z[i], (double)frame_len) > zT);
+                const bool nz = cached ? flags[i] != 0 : (((double)E[i] < eT) && (__ddiv_rn((double)Z[i], (double)frame_len) > zT));
                 if (nz) {
                     if (run_start < 0) run_start = i;
                 } else {
@@ -307,36 +421,17 @@ __global__ void __launch_bounds__(SEL_THREADS) select_clip_kernel(const float* _
                     seen_false = true; rs.all = 0;
                 }
             }
-            if (s1 <= s0) { rs.all = 1; rs.lead = 0; rs.trail = 0; }
-            else if (rs.all) { rs.lead = s1 - s0; rs.trail = s1 - s0; }
+            if (rs.all) { rs.lead = s1 - s0; rs.trail = s1 - s0; }
             else rs.trail = (run_start >= 0) ? s1 - run_start : 0;
         }
-        sums[threadIdx.x] = rs;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int open_start = -1, bl = 0, bs = 0;
-            for (int t = 0; t < SEL_THREADS; ++t) {
-                const int a0 = t * per, a1 = min(F, a0 + per);
-                if (a1 <= a0) break;
-                const RunSummary r = sums[t];
-                if (r.all) { if (open_start < 0) open_start = a0; continue; }
-                // run that reaches this segment's first False
-                if (open_start >= 0 || r.lead > 0) {
-                    int st = open_start >= 0 ? open_start : a0;
-                    int en = a0 + r.lead;
-                    if (en - st > bl) { bl = en - st; bs = st; }
-                }
-                if (r.best_len > bl) { bl = r.best_len; bs = r.best_start; }
-                open_start = r.trail > 0 ? a1 - r.trail : -1;
-            }
-            // (i - start) * hop / sr >= 0.1 ; longest first-maximum run.  Length ordering equals frame-count ordering.
-            if (bl > 0 && __ddiv_rn((double)((long long)bl * hop), (double)sr) >= 0.1) { found = 1; best_s = bs; best_e = bs + bl; }
-        }
+        seg.r = rs;
+        seg = block_merge_segs(seg, wsm);
+        if (tid == 0) pick_run(seg.r, hop, sr, found, best_s, best_l);
     }
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         // sample range in GLOBAL coordinates of the recording; map to the item's local buffer
         long long gs, ge;
-        if (found) { gs = (long long)best_s * hop; ge = (long long)best_e * hop; }
+        if (found) { gs = (long long)best_s * hop; ge = (long long)(best_s + best_l) * hop; }
         else { gs = 0; ge = min((long long)fallback_len, it.n_global); }
         Clip c;
         c.start = it.pcm_off + gs - it.g0 + it.origin;
@@ -362,31 +457,13 @@ struct SelShared {                 // global scratch of one selection (SEL_SCRAT
     RunSummary sums[1024];         // one per CTA
 };
 
-// merge of the summaries of two adjacent frame ranges (L before R); lenL / lenR are their lengths, startR = first frame of R
-__device__ __forceinline__ RunSummary merge_runs(const RunSummary& L, int lenL, const RunSummary& R, int lenR, int startR) {
-    RunSummary o;
-    if (lenL <= 0) return R;
-    if (lenR <= 0) return L;
-    o.all = L.all && R.all;
-    o.lead = L.all ? lenL + R.lead : L.lead;
-    o.trail = R.all ? lenR + L.trail : R.trail;
-    o.best_len = L.best_len; o.best_start = L.best_start;
-    if (!L.all && !R.all) {                                     // the run across the seam is closed on both sides
-        const int mid = L.trail + R.lead;
-        if (mid > o.best_len) { o.best_len = mid; o.best_start = startR - L.trail; }
-    }
-    if (R.best_len > o.best_len) { o.best_len = R.best_len; o.best_start = R.best_start; }
-    if (o.all) { o.best_len = 0; o.best_start = 0; }
-    return o;
-}
-
 __global__ void __launch_bounds__(SEL_THREADS) select_clip_grid_kernel(const float* __restrict__ E, const int* __restrict__ Z, int F,
                                                                         Item it, int frame_len, int hop, int sr, int fallback_len,
                                                                         SelShared* __restrict__ g, Clip* __restrict__ clip_out,
                                                                         int* __restrict__ seg_out) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     __shared__ unsigned hist[2048];
-    __shared__ RunSummary sums[SEL_THREADS];
+    __shared__ RunSeg wsm[32];
     const int tid = threadIdx.x;
     const long long gtid = (long long)blockIdx.x * blockDim.x + tid, gsize = (long long)gridDim.x * blockDim.x;
     const bool leader = blockIdx.x == 0;
@@ -512,45 +589,31 @@ __global__ void __launch_bounds__(SEL_THREADS) select_clip_grid_kernel(const flo
         }
         if (rs.all) { rs.lead = s1 - s0; rs.trail = s1 - s0; }
         else rs.trail = (run_start >= 0) ? s1 - run_start : 0;
-        sums[tid] = rs;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        RunSummary acc = sums[0];
-        int len = min(c1, c0 + per) - c0;
-        for (int t = 1; t < SEL_THREADS; ++t) {
-            const int s0 = min(c1, c0 + t * per), s1 = min(c1, s0 + per);
-            if (s1 <= s0) break;
-            acc = merge_runs(acc, len, sums[t], s1 - s0, s0);
-            len += s1 - s0;
-        }
-        g->sums[blockIdx.x] = acc;
+        RunSeg seg; seg.r = rs; seg.start = s0; seg.len = s1 - s0;
+        seg = block_merge_segs(seg, wsm);
+        if (tid == 0) g->sums[blockIdx.x] = seg.r;
     }
     grid.sync();
-    if (leader && tid == 0) {
-        RunSummary acc = g->sums[0];
-        int len = min(F, per_cta);
-        for (int c = 1; c < (int)gridDim.x; ++c) {
-            const int a0 = min(F, c * per_cta), a1 = min(F, a0 + per_cta);
-            if (a1 <= a0) break;
-            acc = merge_runs(acc, len, g->sums[c], a1 - a0, a0);
-            len += a1 - a0;
+    if (leader) {
+        RunSeg seg; seg.r.all = 1; seg.r.lead = 0; seg.r.trail = 0; seg.r.best_len = 0; seg.r.best_start = 0; seg.start = 0; seg.len = 0;
+        if (tid < (int)gridDim.x) {
+            const int a0 = min(F, tid * per_cta), a1 = min(F, a0 + per_cta);
+            seg.r = g->sums[tid]; seg.start = a0; seg.len = a1 - a0;
         }
-        // candidates in order of their start: the leading run (closed unless everything is noise), then the best interior run;
-        // an open run at the end is dropped like in the reference's loop
-        int bl = 0, bs = 0;
-        if (!acc.all && acc.lead > bl) { bl = acc.lead; bs = 0; }
-        if (acc.best_len > bl) { bl = acc.best_len; bs = acc.best_start; }
-        const bool found = bl > 0 && __ddiv_rn((double)((long long)bl * hop), (double)sr) >= 0.1;
-        long long gs, ge;
-        if (found) { gs = (long long)bs * hop; ge = (long long)(bs + bl) * hop; }
-        else { gs = 0; ge = min((long long)fallback_len, it.n_global); }
-        Clip c;
-        c.start = it.pcm_off + gs - it.g0 + it.origin;
-        long long len2 = ge - gs; if (len2 > CHUNK) len2 = CHUNK;
-        c.len = (int)len2; c.n_frames = (int)(len2 / HOP) + 1;
-        *clip_out = c;
-        if (seg_out) { seg_out[0] = (int)gs; seg_out[1] = (int)ge; }
+        seg = block_merge_segs(seg, wsm);
+        if (tid == 0) {
+            int found, bs, bl;
+            pick_run(seg.r, hop, sr, found, bs, bl);
+            long long gs, ge;
+            if (found) { gs = (long long)bs * hop; ge = (long long)(bs + bl) * hop; }
+            else { gs = 0; ge = min((long long)fallback_len, it.n_global); }
+            Clip c;
+            c.start = it.pcm_off + gs - it.g0 + it.origin;
+            long long len2 = ge - gs; if (len2 > CHUNK) len2 = CHUNK;
+            c.len = (int)len2; c.n_frames = (int)(len2 / HOP) + 1;
+            *clip_out = c;
+            if (seg_out) { seg_out[0] = (int)gs; seg_out[1] = (int)ge; }
+        }
     }
 }
 

@@ -408,23 +408,35 @@ __global__ void __launch_bounds__(256) noise_pass_kernel(const int16_t* __restri
     }
 }
 
-__global__ void noise_finalize_kernel(const Clip* __restrict__ clips, const double* __restrict__ partial, int n_parts,
-                                      double n_std, float* __restrict__ T2, float* __restrict__ T2hi) {
+// 16 bins x 8 part-groups per CTA: the partial sums of a bin are split over 8 threads (loads in flight together), the
+// 8 group sums folded in a fixed order -- the summation order is fixed, so the thresholds are reproducible run to run.
+__global__ void __launch_bounds__(128) noise_finalize_kernel(const Clip* __restrict__ clips, const double* __restrict__ partial, int n_parts,
+                                                             double n_std, float* __restrict__ T2, float* __restrict__ T2hi) {
+    __shared__ double sh1[8][16], sh2[8][16];
     const int item = blockIdx.y;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= NBIN) return;
-    const int n = clips[item].n_frames;
+    const int kl = threadIdx.x & 15, sub = threadIdx.x >> 4;
+    const int k = blockIdx.x * 16 + kl;
+    const int per = (n_parts + 7) / 8;
+    const int p0 = min(n_parts, sub * per), p1 = min(n_parts, p0 + per);
     double s1 = 0.0, s2 = 0.0;
-    const double* pr0 = partial + (long long)item * n_parts * (2 * T_PITCH) + k;
-    int p = 0;
-    for (; p + 8 <= n_parts; p += 8) {                 // loads first (independent), fixed summation order kept
-        double a[8], b[8];
+    if (k < NBIN) {
+        const double* pr0 = partial + (long long)item * n_parts * (2 * T_PITCH) + k;
+        int p = p0;
+        for (; p + 8 <= p1; p += 8) {                  // loads first (independent), fixed summation order kept
+            double a[8], b[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { a[u] = pr0[(long long)(p + u) * (2 * T_PITCH)]; b[u] = pr0[(long long)(p + u) * (2 * T_PITCH) + T_PITCH]; }
+            for (int u = 0; u < 8; ++u) { a[u] = pr0[(long long)(p + u) * (2 * T_PITCH)]; b[u] = pr0[(long long)(p + u) * (2 * T_PITCH) + T_PITCH]; }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { s1 += a[u]; s2 += b[u]; }
+            for (int u = 0; u < 8; ++u) { s1 += a[u]; s2 += b[u]; }
+        }
+        for (; p < p1; ++p) { s1 += pr0[(long long)p * (2 * T_PITCH)]; s2 += pr0[(long long)p * (2 * T_PITCH) + T_PITCH]; }
     }
-    for (; p < n_parts; ++p) { s1 += pr0[(long long)p * (2 * T_PITCH)]; s2 += pr0[(long long)p * (2 * T_PITCH) + T_PITCH]; }
+    sh1[sub][kl] = s1; sh2[sub][kl] = s2;
+    __syncthreads();
+    if (sub != 0 || k >= NBIN) return;
+#pragma unroll
+    for (int u = 1; u < 8; ++u) { s1 += sh1[u][kl]; s2 += sh2[u][kl]; }
+    const int n = clips[item].n_frames;
     const double mean = s1 / n;
     double var = s2 / n - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -445,7 +457,7 @@ void launch_noise_threshold(const int16_t* pcm, const Clip* clips, int n_items, 
     dim3 grid(n_slices, n_items);
     noise_pass_kernel<1><<<grid, 256, 0, st>>>(pcm, clips, c, nmax, partial, n_slices);
     noise_pass_kernel<2><<<grid, 256, 0, st>>>(pcm, clips, c, nmax, partial, n_slices);
-    dim3 g2((NBIN + 127) / 128, n_items);
+    dim3 g2((NBIN + 15) / 16, n_items);
     noise_finalize_kernel<<<g2, 128, 0, st>>>(clips, partial, n_slices * 4, n_std, T2, T2hi);
 }
 
