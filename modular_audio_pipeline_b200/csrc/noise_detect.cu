@@ -82,17 +82,25 @@ __global__ void __launch_bounds__(128) frame_stats_kernel(const int16_t* __restr
     zc[it.sframe_off + f] = c;
 }
 
-// Fast path for the 16 kHz geometry (frame 400, hop 160): one WARP per frame, samples staged in shared memory.
+// Fast path for the 16 kHz geometry (frame 400, hop 160): one WARP per frame, the tile's samples staged in shared memory
+// ONCE as float32 squares plus one sign bit each (every sample belongs to 2.5 frames).
 // numpy's pairwise sum of 400 float32 squares is ((leaf(0,96) + leaf(96,104)) + (leaf(200,96) + leaf(296,104))) where a leaf
 // keeps 8 strided accumulators r[j] += x[8 i + j]^2 and folds them as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)): that is 32
 // independent sequential chains -- one per lane -- followed by exactly the xor-1, 2, 4 (inside a leaf) and xor-8, 16
 // (across leaves) butterfly, so the warp-parallel sum is bit-identical to the serial one (float addition commutes).
+// The sign-change count of a frame is a population count over the tile's change bits c[i] = sign[i] ^ sign[i-1]:
+// frames start on multiples of 160 = 5 words, so a frame is 12 whole words and half of a 13th.
 constexpr int FS_FRAMES = 64;                                    // frames per CTA
 constexpr int FS_SPAN = (FS_FRAMES - 1) * 160 + 400;             // 10480 samples
+constexpr int FS_WORDS = (FS_SPAN + 31) / 32;                    // 328 words of sign bits
+constexpr size_t FS_SMEM = sizeof(float) * (FS_SPAN + 8) + sizeof(unsigned) * 2 * (FS_WORDS + 4);
 
 __global__ void __launch_bounds__(256) frame_stats400_kernel(const int16_t* __restrict__ pcm, const Item* __restrict__ items,
                                                             float* __restrict__ energies, int* __restrict__ zc) {
-    __shared__ __align__(16) int16_t span[FS_SPAN + 8];
+    extern __shared__ __align__(16) unsigned char fs_smem[];
+    float* sq = reinterpret_cast<float*>(fs_smem);                               // [FS_SPAN + 8] squares
+    unsigned* bw = reinterpret_cast<unsigned*>(sq + FS_SPAN + 8);                // [FS_WORDS + 4] sign bits
+    unsigned* cw = bw + FS_WORDS + 4;                                            // [FS_WORDS + 4] change bits
     const Item it = items[blockIdx.y];
     const int f0 = blockIdx.x * FS_FRAMES;
     if (f0 >= it.n_sframes) return;
@@ -101,13 +109,41 @@ __global__ void __launch_bounds__(256) frame_stats400_kernel(const int16_t* __re
     const int need = (nfr - 1) * 160 + 400;
     const long long g0 = it.pcm_off + it.origin + (long long)f0 * 160;          // first sample of the tile in the pcm array
     const int16_t* p = pcm + g0;
-    if ((g0 & 7) == 0) {
-        for (int g = tid; g < (need + 7) / 8; g += 256) {
-            if (8 * g + 8 <= need) *reinterpret_cast<uint4*>(&span[8 * g]) = *reinterpret_cast<const uint4*>(p + 8 * g);
-            else for (int e = 8 * g; e < need; ++e) span[e] = p[e];
+    const bool aligned = (g0 & 7) == 0;
+    const int n_groups = (need + 7) / 8;                                         // 8 samples per thread and step; 4 threads = one sign word
+    for (int g = tid; g < ((n_groups + 31) & ~31); g += 256) {                   // whole warps: the sign words are assembled by shuffles
+        int v[8];
+        if (g < n_groups && aligned && 8 * g + 8 <= need) {
+            const uint4 q = *reinterpret_cast<const uint4*>(p + 8 * g);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int h = 0; h < 4; ++h) { v[2 * h] = (int)(short)(w[h] & 0xffffu); v[2 * h + 1] = (int)w[h] >> 16; }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = (g < n_groups && 8 * g + e < need) ? (int)p[8 * g + e] : 0;
         }
-    } else {
-        for (int e = tid; e < need; e += 256) span[e] = p[e];
+        unsigned sb = 0;
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float x = int_to_float_exact(v[e]);
+            f[e] = __fmul_rn(x, x);
+            sb |= (v[e] < 0 ? 1u : 0u) << e;
+        }
+        sb <<= 8 * (lane & 3);
+        sb |= __shfl_xor_sync(0xffffffffu, sb, 1);
+        sb |= __shfl_xor_sync(0xffffffffu, sb, 2);
+        if (g < n_groups) {
+            *reinterpret_cast<float4*>(sq + 8 * g) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(sq + 8 * g + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            if ((lane & 3) == 0) bw[g >> 2] = sb;
+        }
+    }
+    __syncthreads();
+    const int n_words = (need + 31) / 32;
+    for (int w = tid; w < n_words; w += 256) {
+        const unsigned b = bw[w];
+        cw[w] = b ^ ((b << 1) | (w ? bw[w - 1] >> 31 : 0u));                     // bit j = change between samples 32 w + j - 1 and 32 w + j
     }
     __syncthreads();
     // lane -> (leaf, accumulator): leaf offsets 0 / 96 / 200 / 296, lengths 96 / 104 / 96 / 104
@@ -115,26 +151,22 @@ __global__ void __launch_bounds__(256) frame_stats400_kernel(const int16_t* __re
     const int loff = leaf == 0 ? 0 : leaf == 1 ? 96 : leaf == 2 ? 200 : 296;
     const int lcnt = (leaf & 1) ? 13 : 12;
     for (int lf = warp; lf < nfr; lf += 8) {
-        const int16_t* x = span + lf * 160;
-        float v0 = int_to_float_exact((int)x[loff + j]);
-        float r = __fmul_rn(v0, v0);
+        const float* x = sq + lf * 160 + loff + j;
+        float r = x[0];
 #pragma unroll
         for (int i = 1; i < 13; ++i) {
-            if (i < lcnt) { const float v = int_to_float_exact((int)x[loff + j + 8 * i]); r = __fadd_rn(r, __fmul_rn(v, v)); }
+            if (i < lcnt) r = __fadd_rn(r, x[8 * i]);
         }
         r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
         r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
         r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
         r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 8));
         r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 16));
-        // sign changes between consecutive samples: lane owns pairs (i - 1, i), i = 1 + 13 lane .. 13 lane + 13
+        // sign changes of the pairs (i - 1, i), i = 1 .. 399 of the frame: bits 1..31 of word 0, words 1..11, bits 0..15 of word 12
         int c = 0;
-        const int i0 = 1 + 13 * lane;
-        int prev = x[i0 - 1 < 400 ? i0 - 1 : 399] < 0;
-#pragma unroll
-        for (int q = 0; q < 13; ++q) {
-            const int i = i0 + q;
-            if (i < 400) { const int cur = x[i] < 0; c += (cur != prev); prev = cur; }
+        if (lane < 13) {
+            const unsigned w = cw[5 * lf + lane];
+            c = __popc(lane == 0 ? (w & ~1u) : lane == 12 ? (w & 0xffffu) : w);
         }
         c = __reduce_add_sync(0xffffffffu, c);
         if (lane == 0) {
@@ -149,7 +181,8 @@ void launch_frame_stats(const int16_t* pcm, const Item* items, int n_items, int 
     if (max_frames <= 0 || n_items <= 0) return;
     if (frame_len == 400 && hop == 160) {
         dim3 grid((max_frames + FS_FRAMES - 1) / FS_FRAMES, n_items);
-        frame_stats400_kernel<<<grid, 256, 0, st>>>(pcm, items, energies, zc);
+        cudaFuncSetAttribute(frame_stats400_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM);
+        frame_stats400_kernel<<<grid, 256, FS_SMEM, st>>>(pcm, items, energies, zc);
         return;
     }
     dim3 grid((max_frames + 127) / 128, n_items);
