@@ -25,7 +25,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 static inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
 
 // ---- context --------------------------------------------------------------------------------------------------
-struct MelHost { std::vector<int> start, count, woff; std::vector<float> w; std::vector<int> qstart, qcount, qoff; std::vector<float> wq; };
+struct MelHost { std::vector<int> start, count, woff; std::vector<float> w; std::vector<int> qstart, qcount, qoff, qrow; std::vector<float> wq; };
 
 struct maf_ctx {
     int device = 0;
@@ -85,6 +85,30 @@ static MelHost build_mel(int n_mels) {
                 h.wq.push_back(in ? h.w[h.woff[m] + k - h.start[m]] : 0.0f);
             }
     }
+    // deal the quads to the kernel's 8 warps, longest first onto the least loaded warp (the runs grow from 4 bins at the
+    // bottom of the scale to 34 at the top: round-robin leaves one warp with 40 % more work than the average)
+    {
+        const int nq = n_mels / 4;
+        std::vector<int> order(nq), load(8, 0);
+        std::vector<std::vector<int>> lists(8);
+        for (int q = 0; q < nq; ++q) order[q] = q;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h.qcount[a] > h.qcount[b]; });
+        for (int q : order) {
+            int w = 0;
+            for (int i = 1; i < 8; ++i) if (load[i] < load[w]) w = i;
+            load[w] += h.qcount[q] + 8;                          // + the log / store epilogue of a quad
+            lists[w].push_back(q);
+        }
+        size_t depth = 0;
+        for (auto& l : lists) depth = std::max(depth, l.size());
+        std::vector<int> qs(8 * depth, 0), qc(8 * depth, 0), qo(8 * depth, 0), qr(8 * depth, -1);
+        for (int w = 0; w < 8; ++w)
+            for (size_t i = 0; i < lists[w].size(); ++i) {
+                const int q = lists[w][i], sl = (int)(8 * i) + w;
+                qs[sl] = h.qstart[q]; qc[sl] = h.qcount[q]; qo[sl] = h.qoff[q]; qr[sl] = q;
+            }
+        h.qstart = qs; h.qcount = qc; h.qoff = qo; h.qrow = qr;
+    }
     return h;
 }
 
@@ -114,8 +138,14 @@ extern "C" int maf_create(int device, maf_ctx** out) {
     size_t o_t512 = put(t512.data(), t512.size() * 8), o_t2 = put(t2.data(), t2.size() * 8), o_t1024 = put(t1024.data(), t1024.size() * 8);
     size_t o_t200 = put(t200.data(), t200.size() * 8), o_t400 = put(t400.data(), t400.size() * 8);
     if (m80.wq.size() / 4 > MEL_WQ_MAX || m128.wq.size() / 4 > MEL_WQ_MAX) return fail(MAF_ERR_UNSUPPORTED, "mel quad table exceeds MEL_WQ_MAX");
-    size_t o80[4] = {put(m80.qstart.data(), 20 * 4), put(m80.qcount.data(), 20 * 4), put(m80.qoff.data(), 20 * 4), put(m80.wq.data(), m80.wq.size() * 4)};
-    size_t o128[4] = {put(m128.qstart.data(), 32 * 4), put(m128.qcount.data(), 32 * 4), put(m128.qoff.data(), 32 * 4), put(m128.wq.data(), m128.wq.size() * 4)};
+    if (m80.qrow.size() > MEL_SLOTS_MAX || m128.qrow.size() > MEL_SLOTS_MAX) return fail(MAF_ERR_UNSUPPORTED, "mel slot table exceeds MEL_SLOTS_MAX");
+    auto put_mel = [&](const MelHost& m, size_t (&o)[5]) {
+        const size_t ns = m.qrow.size() * 4;
+        o[0] = put(m.qrow.data(), ns); o[1] = put(m.qstart.data(), ns); o[2] = put(m.qcount.data(), ns); o[3] = put(m.qoff.data(), ns);
+        o[4] = put(m.wq.data(), m.wq.size() * 4);
+    };
+    size_t o80[5], o128[5];
+    put_mel(m80, o80); put_mel(m128, o128);
     maf_ctx* ctx = new maf_ctx();
     ctx->device = device;
     cudaError_t e = cudaMalloc(&ctx->blob, host.size());
@@ -128,8 +158,10 @@ extern "C" int maf_create(int device, maf_ctx** out) {
     ctx->c.tw1 = (const c32*)(b + o_t512); ctx->c.tw2 = (const c32*)(b + o_t2); ctx->c.tw1024 = (const c32*)(b + o_t1024);
     ctx->c.twA = (const c32*)(b + o_t200); ctx->c.tw400 = (const c32*)(b + o_t400);
     ctx->c.tww = (const c32*)(b + o_tww);
-    ctx->mel80 = MelBank{80, (int)m80.wq.size() / 4, (const int*)(b + o80[0]), (const int*)(b + o80[1]), (const int*)(b + o80[2]), (const float4*)(b + o80[3])};
-    ctx->mel128 = MelBank{128, (int)m128.wq.size() / 4, (const int*)(b + o128[0]), (const int*)(b + o128[1]), (const int*)(b + o128[2]), (const float4*)(b + o128[3])};
+    ctx->mel80 = MelBank{80, (int)m80.wq.size() / 4, (int)m80.qrow.size(), (const int*)(b + o80[0]), (const int*)(b + o80[1]), (const int*)(b + o80[2]),
+                         (const int*)(b + o80[3]), (const float4*)(b + o80[4])};
+    ctx->mel128 = MelBank{128, (int)m128.wq.size() / 4, (int)m128.qrow.size(), (const int*)(b + o128[0]), (const int*)(b + o128[1]), (const int*)(b + o128[2]),
+                          (const int*)(b + o128[3]), (const float4*)(b + o128[4])};
     *out = ctx;
     return MAF_OK;
 }

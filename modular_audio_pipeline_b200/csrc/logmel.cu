@@ -18,7 +18,7 @@ constexpr int MEL_SPAN = (MEL_TILE - 1) * W_HOP + W_NFFT;            // 5360 sam
 constexpr int Z_PITCH = 200;
 constexpr int P_PITCH = 201;
 constexpr size_t LOGMEL_SMEM = sizeof(float) * MEL_SPAN + sizeof(c32) * MEL_TILE * Z_PITCH + sizeof(float) * MEL_TILE * P_PITCH +
-                               sizeof(float) * W_NFFT + sizeof(c32) * 200 + sizeof(c32) * 208 + sizeof(int) * 3 * 32 + sizeof(float4) * MEL_WQ_MAX;
+                               sizeof(float) * W_NFFT + sizeof(c32) * 200 + sizeof(c32) * 208 + sizeof(int) * 4 * MEL_SLOTS_MAX + sizeof(float4) * MEL_WQ_MAX;
 
 struct MelTile {            // geometry of one (item, 32-frame tile) unit
     int item, lf0;
@@ -42,8 +42,9 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     c32* tw400 = twA + 200;
     float4* m_wq = reinterpret_cast<float4*>(tw400 + 208);               // 16-byte aligned: every array before it is a multiple of 16 bytes
     int* m_qstart = reinterpret_cast<int*>(m_wq + MEL_WQ_MAX);
-    int* m_qcount = m_qstart + 32;
-    int* m_qoff = m_qcount + 32;
+    int* m_qcount = m_qstart + MEL_SLOTS_MAX;
+    int* m_qoff = m_qcount + MEL_SLOTS_MAX;
+    int* m_qrow = m_qoff + MEL_SLOTS_MAX;
     const int tid = threadIdx.x;
 
     const unsigned total = (unsigned)n_items * (unsigned)max_tiles;            // < 2^31 (checked by the launcher): 32-bit index math
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
 
     for (int i = tid; i < W_NFFT; i += 256) win[i] = cs.win400[i];
     for (int i = tid; i < 200; i += 256) twA[i] = cs.twA[i];
-    if (tid < mel.n_mels / 4) { m_qstart[tid] = mel.qstart[tid]; m_qcount[tid] = mel.qcount[tid]; m_qoff[tid] = mel.qoff[tid]; }
+    if (tid < mel.n_slots) { m_qstart[tid] = mel.qstart[tid]; m_qcount[tid] = mel.qcount[tid]; m_qoff[tid] = mel.qoff[tid]; m_qrow[tid] = mel.qrow[tid]; }
     for (int i = tid; i < mel.n_wq; i += 256) m_wq[i] = mel.wq[i];
     for (int i = tid; i < 201; i += 256) tw400[i] = cs.tw400[i];
 
@@ -93,8 +94,9 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     PeakNorm pnv; pnv.active = 0;
     if (peak_normalize) pnv = pnorm[item];
     const bool pn = pnv.active != 0;
-    Gate gt; gt.applied = 0;
+    Gate gt; gt.applied = 0; gt.lim = 0; gt.limp = 1.0f;
     if (gates) gt = gates[item];
+    const DivConst dv = limiter_div(gt);
     const int16_t* x = den16 + it.den_off;
     const long long np_global = it.n_global + padding;            // length of the zero-padded recording
     const long long i0 = cur.i0, l0 = cur.l0, own_lo = cur.own_lo, own_hi = cur.own_hi;
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     float qf;
-                    sv[e] = norm_gain_sample(sv[e], pn, pnv, gt, qf);
+                    sv[e] = norm_gain_sample(sv[e], pn, pnv, gt, dv, qf);
                     a[e] = qf * (1.0f / 32768.0f);
                 }
                 *reinterpret_cast<float4*>(span + 8 * gq) = make_float4(a[0], a[1], a[2], a[3]);
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
                     if (l >= -(long long)it.lo_avail && l < it.own_len + it.hi_avail) {
                         int sv = x[l];
                         float qf;
-                        const int q = norm_gain_sample(sv, pn, pnv, gt, qf);
+                        const int q = norm_gain_sample(sv, pn, pnv, gt, dv, qf);
                         a = qf * (1.0f / 32768.0f);
                         if (out16 && r == i && i >= own_lo && i < own_hi && l >= 0 && l < it.own_len) out16[it.out_off + l] = (int16_t)q;
                     }
@@ -201,10 +203,12 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
         const bool valid = lf0 + lf < it.mel_frames;
         float bmax = -INFINITY, bmin = INFINITY;
         float* orow = mel_out + it.mel_off + lf0 + lf;
-        for (int q = warp; q < mel.n_mels / 4; q += 8) {
-            const int cnt = m_qcount[q];
-            const float4* wts = m_wq + m_qoff[q];
-            const float* pr = pw + lf * P_PITCH + m_qstart[q];
+        for (int sl = warp; sl < mel.n_slots; sl += 8) {
+            const int q = m_qrow[sl];                                   // quads were dealt to the warps by cost on the host
+            if (q < 0) continue;
+            const int cnt = m_qcount[sl];
+            const float4* wts = m_wq + m_qoff[sl];
+            const float* pr = pw + lf * P_PITCH + m_qstart[sl];
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 4
             for (int i = 0; i < cnt; ++i) {

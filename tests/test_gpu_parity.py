@@ -131,6 +131,28 @@ def test_loudness_parity(frontend, seconds, seed, scale):
     assert d.max() <= 1 and np.mean(d != 0) <= 1e-3
 
 
+@pytest.mark.parametrize("seed,click", [(0, 32767), (1, 30011), (2, 23456), (3, 17777), (4, 29999)])
+def test_limiter_division_fused_equals_staged_and_oracle(frontend, seed, click):
+    """Limiter active (gain * peak > 1): the fused path divides with a per-thread reciprocal + per-sample correction
+    (maf_common.cuh div_by), the standalone stage with __fdiv_rn, the oracle with numpy float32 division -- the int16
+    results must be identical between the two CUDA paths and within the LSB-flip allowance of the oracle."""
+    pcm = gen(20, seed)
+    pcm = (pcm.float() * 0.15).round().to(torch.int16)
+    pcm[SR * 3 + 7] = click; pcm[SR * 11 + 5] = -click          # clicks fix the peak, the speech fixes the loudness
+    plan = frontend.plan([pcm.numel()], stationary=True, n_mels=80)
+    res = plan.process(plan.pack([pcm]))
+    den16, _, _ = plan.denoise(plan.pack([pcm]))
+    norm16 = plan.peak_normalize(plan.pack([den16[0]]))
+    staged, lufs = plan.loudness(plan.pack([norm16[0]]))
+    norm_np = norm16[0].cpu().numpy()
+    want16, want_lufs, applied = O.normalize_loudness(norm_np, SR)
+    peak = np.abs(norm_np.astype(np.int32)).max() / 32768.0
+    assert applied and 10 ** ((-16.0 - want_lufs) / 20) * peak > 1.05        # the limiter really is active
+    assert torch.equal(res.pcm[0], staged[0])
+    d = np.abs(staged[0].cpu().numpy().astype(np.int32) - want16.astype(np.int32))
+    assert d.max() <= 1 and np.mean(d != 0) <= 1e-3
+
+
 def test_loudness_silence_passthrough_and_too_short(frontend):
     from modular_audio_pipeline_b200 import MafError
     silent = torch.zeros(3 * SR, dtype=torch.int16)
