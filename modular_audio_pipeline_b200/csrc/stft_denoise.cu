@@ -1015,25 +1015,64 @@ __global__ void __launch_bounds__(256, 2) istft_kernel(const c32* __restrict__ S
 #pragma unroll
     for (int j = 0; j < 6; ++j) gspan[64 * (2 * (ISTFT_FR / 4) + j) + t] = win[j];
     __syncthreads();
-    // emit: segment g covers padded-chunk samples [256 g, 256 g + 256) = ola[768 + 256 (g - g0) ...]
+    // emit: segment g covers padded-chunk samples [256 g, 256 g + 256) = ola[768 + 256 (g - g0) ...]; eight consecutive
+    // samples per thread (16-byte shared loads, one 16-byte int16 store)
     int pk = 0;
     const long long obase = (to_out ? it.out_off : it.den_off) + ch.out_off;
     const long long fbase_o = it.out_off + ch.out_off;
-    for (int i = tid; i < ISTFT_SEG * HOP; i += 256) {
-        const long long j = (long long)g0 * HOP + i;
-        const long long o = j - PADS;
-        if (o < 0 || o >= ch.keep) continue;
-        // CTA position x = 768 + i lies in the span of group x / 2048 and, for the first 768 samples of that span, also in the
+    const long long o_first = (long long)g0 * HOP - PADS;           // kept-sample index of the CTA's first output (multiple of 8)
+    const bool vec16 = ((obase + o_first) & 7) == 0;
+    const bool vecf = den_f32 && ((fbase_o + o_first) & 3) == 0;
+    const DivConst d15 = div_const(1.5f);                           // scipy istft: / sum of squared windows (hann^2 at 75 % overlap)
+    constexpr int GSTRIDE = (ISTFT_FR / 4) * HOP;                   // samples between the starts of two group spans
+    for (int i = 8 * tid; i < ISTFT_SEG * HOP; i += 8 * 256) {
+        const long long o = o_first + i;
+        if (o + 8 <= 0 || o >= ch.keep) continue;
+        // CTA position x = 768 + i lies in the span of group x / 4096 and, for the first 768 samples of that span, also in the
         // previous group's; fixed order: earlier group first
-        constexpr int GSTRIDE = (ISTFT_FR / 4) * HOP;               // samples between the starts of two group spans
         const int x = 3 * HOP + i, ga = x / GSTRIDE, xo = x - ga * GSTRIDE;
-        float sum = ola[ga * GSPAN + xo];
-        if (ga > 0 && xo < 3 * HOP) sum = ola[(ga - 1) * GSPAN + GSTRIDE + xo] + sum;
-        const float val = sum / 1.5f;
-        const int q = (int)(short)(int)val;                         // astype(int16): truncate, keep low 16 bits
-        den16[obase + o] = (int16_t)q;
-        if (den_f32) den_f32[fbase_o + o] = val;
-        pk = max(pk, q < 0 ? -q : q);
+        const float4 a0 = *reinterpret_cast<const float4*>(ola + ga * GSPAN + xo), a1 = *reinterpret_cast<const float4*>(ola + ga * GSPAN + xo + 4);
+        float sum[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        if (ga > 0 && xo < 3 * HOP) {
+            const float* pr = ola + (ga - 1) * GSPAN + GSTRIDE + xo;
+            const float4 b0 = *reinterpret_cast<const float4*>(pr), b1 = *reinterpret_cast<const float4*>(pr + 4);
+            sum[0] = b0.x + sum[0]; sum[1] = b0.y + sum[1]; sum[2] = b0.z + sum[2]; sum[3] = b0.w + sum[3];
+            sum[4] = b1.x + sum[4]; sum[5] = b1.y + sum[5]; sum[6] = b1.z + sum[6]; sum[7] = b1.w + sum[7];
+        }
+        float val[8]; int q[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            val[e] = div_by(sum[e], d15);
+            q[e] = (int)(short)(int)val[e];                         // astype(int16): truncate, keep low 16 bits
+        }
+        if (o >= 0 && o + 8 <= ch.keep) {
+            if (vec16) {
+                uint4 w;
+                w.x = (uint32_t)(q[0] & 0xffff) | ((uint32_t)q[1] << 16); w.y = (uint32_t)(q[2] & 0xffff) | ((uint32_t)q[3] << 16);
+                w.z = (uint32_t)(q[4] & 0xffff) | ((uint32_t)q[5] << 16); w.w = (uint32_t)(q[6] & 0xffff) | ((uint32_t)q[7] << 16);
+                *reinterpret_cast<uint4*>(den16 + obase + o) = w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) den16[obase + o + e] = (int16_t)q[e];
+            }
+            if (vecf) {
+                *reinterpret_cast<float4*>(den_f32 + fbase_o + o) = make_float4(val[0], val[1], val[2], val[3]);
+                *reinterpret_cast<float4*>(den_f32 + fbase_o + o + 4) = make_float4(val[4], val[5], val[6], val[7]);
+            } else if (den_f32) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) den_f32[fbase_o + o + e] = val[e];
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pk = max(pk, q[e] < 0 ? -q[e] : q[e]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (o + e < 0 || o + e >= ch.keep) continue;
+                den16[obase + o + e] = (int16_t)q[e];
+                if (den_f32) den_f32[fbase_o + o + e] = val[e];
+                pk = max(pk, q[e] < 0 ? -q[e] : q[e]);
+            }
+        }
     }
     pk = max(pk, __shfl_xor_sync(0xffffffffu, pk, 16));
     pk = max(pk, __shfl_xor_sync(0xffffffffu, pk, 8));
