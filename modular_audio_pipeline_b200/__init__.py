@@ -13,6 +13,9 @@ def __getattr__(name):
     if name == "GpuAudioPreprocessor":
         from .preprocessor import GpuAudioPreprocessor
         return GpuAudioPreprocessor
+    if name in ("WavPrefetcher", "PinnedPool"):
+        from . import wavio
+        return getattr(wavio, name)
     if name in ("GpuLogMelFrontEnd", "GpuFrontEndTranscriber"):
         from . import transcriber
         return getattr(transcriber, name)

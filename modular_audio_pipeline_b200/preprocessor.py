@@ -21,6 +21,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 import torch
 
+from . import wavio
 from .frontend import FrontEnd, MafError
 
 logger = logging.getLogger(__name__)
@@ -47,6 +48,8 @@ class GpuAudioPreprocessor:
         self._device = device
         self._fe: Optional[FrontEnd] = None
         self._resident: Dict[str, Tuple[torch.Tensor, int, float]] = {}   # path -> (int16 device tensor, sr, mtime)
+        self._in_pool = wavio.PinnedPool()       # page-locked staging: file -> pinned -> device, device -> pinned -> file
+        self._out_pool = wavio.PinnedPool()
         os.makedirs(temp_dir, exist_ok=True)
 
     @classmethod
@@ -96,12 +99,26 @@ class GpuAudioPreprocessor:
             except OSError:
                 pass
             self._resident.pop(path, None)       # temp_dir may have been wiped (media_handler.py:98-102)
-        pcm, sr = self.read_wave(path)
-        x = torch.frombuffer(bytearray(pcm), dtype=torch.int16)
-        return x.to(self.frontend.device, non_blocking=True), sr
+        # read_wave's semantics (:71-79: the data chunk as is, channel count and width ignored), but read straight into
+        # page-locked memory so the upload is one DMA at full PCIe rate (wavio.py)
+        dev = self.frontend.device
+        try:
+            x, info = wavio.read_pcm16(path, self._in_pool)
+        except Exception as e:
+            raise AudioProcessingError(f"Failed to read WAV file: {path}", details=str(e))
+        xd = x.to(dev, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()         # the pinned buffer is reused by the next read
+        return xd, info.rate
 
     def _store(self, path: str, dev: torch.Tensor, sr: int) -> None:
-        self.write_wave(path, dev.cpu().numpy().tobytes(), sr)
+        """write_wave's file (:81-90: mono, 16-bit, caller's rate; byte-identical header) from a pinned landing buffer."""
+        try:
+            host = self._out_pool.get(dev.numel())
+            host.copy_(dev.reshape(-1), non_blocking=True)
+            torch.cuda.current_stream(dev.device).synchronize()
+            wavio.write_pcm16(path, host, sr)
+        except Exception as e:
+            raise AudioProcessingError(f"Failed to write WAV file: {path}", details=str(e))
         self._resident.clear()                   # keep exactly one stage output resident
         self._resident[path] = (dev, sr, os.path.getmtime(path))
 

@@ -40,3 +40,87 @@ def test_fft_cores_on_cpu(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert "OK" in out.stdout
+
+
+# ---- WAV container I/O (wavio.py; reference read_wave / write_wave, preprocessor.py:71-90) ---------------------------
+def _wave_write(path, raw, channels, width, rate):
+    import wave
+    with wave.open(str(path), "wb") as wf:
+        wf.setnchannels(channels); wf.setsampwidth(width); wf.setframerate(rate); wf.writeframes(raw)
+
+
+def test_wavio_reader_matches_wave_module(tmp_path):
+    import struct
+    import wave
+    import numpy as np
+    import torch
+    from modular_audio_pipeline_b200 import wavio
+    rng = np.random.default_rng(0)
+    pool = wavio.PinnedPool(pinned=False)
+    for i, (ch, width, rate, nfr) in enumerate([(1, 2, 16000, 12345), (2, 2, 48000, 4001), (1, 2, 8000, 0), (1, 1, 22050, 778),
+                                                (2, 1, 44100, 100), (1, 2, 16000, 1)]):
+        raw = rng.integers(0, 256, size=nfr * ch * width, dtype=np.uint8).tobytes()
+        p = tmp_path / f"w{i}.wav"
+        _wave_write(p, raw, ch, width, rate)
+        with wave.open(str(p), "rb") as wf:
+            want = wf.readframes(wf.getnframes())
+        x, info = wavio.read_pcm16(str(p), pool)
+        assert (info.channels, info.sampwidth, info.rate, info.nframes) == (ch, width, rate, nfr)
+        assert x.numpy().tobytes() == want == raw
+    # chunks before / after the data chunk, odd-sized chunk padding, WAVE_FORMAT_EXTENSIBLE
+    pcm = rng.integers(-32768, 32767, size=999, dtype=np.int16).tobytes()
+    fmt = struct.pack("<HHIIHH", 1, 1, 16000, 32000, 2, 16)
+    ext = struct.pack("<HHIIHHHHI", 0xFFFE, 1, 16000, 32000, 2, 16, 22, 16, 4) + b"\x01\x00\x00\x00\x00\x00\x10\x00\x80\x00\x00\xaa\x00\x38\x9b\x71"
+    for j, f in enumerate((fmt, ext)):
+        body = (b"WAVE" + b"LIST" + struct.pack("<I", 5) + b"abcde\x00" + b"fmt " + struct.pack("<I", len(f)) + f +
+                b"data" + struct.pack("<I", len(pcm)) + pcm + b"cue " + struct.pack("<I", 4) + b"\x00" * 4)
+        p = tmp_path / f"x{j}.wav"
+        p.write_bytes(b"RIFF" + struct.pack("<I", len(body)) + body)
+        with wave.open(str(p), "rb") as wf:
+            want = wf.readframes(wf.getnframes())
+        x, info = wavio.read_pcm16(str(p))
+        assert x.numpy().tobytes() == want == pcm and info.rate == 16000
+    # not PCM: the wave module's own error comes through
+    bad = tmp_path / "bad.wav"
+    body = b"WAVE" + b"fmt " + struct.pack("<I", 16) + struct.pack("<HHIIHH", 3, 1, 16000, 64000, 4, 32) + b"data" + struct.pack("<I", 8) + b"\x00" * 8
+    bad.write_bytes(b"RIFF" + struct.pack("<I", len(body)) + body)
+    with pytest.raises(wave.Error):
+        wavio.read_pcm16(str(bad))
+    with pytest.raises(Exception):
+        wavio.read_pcm16(str(tmp_path / "missing.wav"))
+
+
+def test_wavio_writer_is_byte_identical_to_wave_module(tmp_path):
+    import numpy as np
+    import torch
+    from modular_audio_pipeline_b200 import wavio
+    rng = np.random.default_rng(1)
+    for n, rate in ((0, 16000), (1, 8000), (16001, 16000), (48000, 48000)):
+        x = torch.from_numpy(rng.integers(-32768, 32767, size=n, dtype=np.int16))
+        a, b = tmp_path / "a.wav", tmp_path / "b.wav"
+        wavio.write_pcm16(str(a), x, rate)
+        _wave_write(b, x.numpy().tobytes(), 1, 2, rate)
+        assert a.read_bytes() == b.read_bytes()
+
+
+def test_wav_prefetcher_order_and_buffer_lifetime(tmp_path):
+    import numpy as np
+    import torch
+    from modular_audio_pipeline_b200 import wavio
+    rng = np.random.default_rng(2)
+    paths, want = [], []
+    for i in range(7):
+        x = rng.integers(-32768, 32767, size=1000 + 317 * i, dtype=np.int16)
+        p = tmp_path / f"p{i}.wav"
+        _wave_write(p, x.tobytes(), 1, 2, 16000)
+        paths.append(str(p)); want.append(x)
+    for depth in (2, 3):
+        held = []
+        for i, (p, x, info) in enumerate(wavio.WavPrefetcher(paths, depth=depth, pinned=False)):
+            assert p == paths[i] and info.rate == 16000 and np.array_equal(x.numpy(), want[i])
+            held.append((i, x))
+            held = held[-(depth - 1):]                      # items still guaranteed valid
+            for j, xj in held:
+                assert np.array_equal(xj.numpy(), want[j])
+    with pytest.raises(Exception):
+        list(wavio.WavPrefetcher([paths[0], str(tmp_path / "nope.wav")], pinned=False))
