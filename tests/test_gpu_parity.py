@@ -73,6 +73,36 @@ def test_denoise_parity(frontend, seconds, seed, stationary):
     assert np.mean(diff != 0) <= 1e-3
 
 
+@pytest.mark.parametrize("n", [600001, 599999, 4000, 1500, 1024])
+@pytest.mark.parametrize("stationary", [True, False])
+def test_denoise_parity_edge_lengths(frontend, n, stationary):
+    """One sample either side of the 600 000-sample chunk boundary (a second chunk of ONE sample), and recordings of a few
+    frames only (shorter than the S0 analysis needs: the leading-samples fallback clip)."""
+    pcm = gen(38.0, 3, meeting=not stationary)[:n].contiguous()
+    plan = frontend.plan([n], stationary=stationary, n_mels=0)
+    out16, outf, clip = plan.denoise(plan.pack([pcm]), want_float=True)
+    red, den16, ref_clip = O.denoise_int16(pcm.numpy(), SR, stationary=stationary)
+    assert outf[0].numel() == n
+    s = snr_db(red, outf[0].cpu().numpy())
+    assert s >= 80.0, f"SNR {s:.1f} dB"
+    diff = np.abs(out16[0].cpu().numpy().astype(np.int32) - den16.astype(np.int32))
+    assert diff.max() <= 1 and np.mean(diff != 0) <= 2e-3
+    if stationary:
+        assert tuple(clip.cpu().numpy()[0]) == tuple(ref_clip)
+
+
+def test_all_zero_recording_through_the_fused_entry(frontend):
+    """Digital silence: the stationary gate returns zeros, the loudness stage passes through (-inf LUFS, :267-269), the
+    log-mel is the constant the reference produces for zeros."""
+    z = torch.zeros(2 * SR, dtype=torch.int16)
+    plan = frontend.plan([z.numel()], stationary=True, n_mels=80)
+    res = plan.process(plan.pack([z]))
+    assert not np.isfinite(res.lufs.item())
+    assert int(res.pcm[0].abs().max()) == 0
+    want = O.log_mel_spectrogram(np.zeros(2 * SR, dtype=np.float32), 80, 0)
+    assert np.abs(res.log_mel[0].cpu().numpy() - want).max() <= 1e-4
+
+
 def test_denoise_fixed_clip_and_external_noise(frontend):
     pcm = gen(25, 7)
     x = pcm.numpy()
