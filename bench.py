@@ -377,6 +377,7 @@ def main():
     ap.add_argument("--cpu-sample", type=float, default=120.0, help="seconds of audio EACH host thread of the CPU baseline processes per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="plans / streams in flight in the HostPipeline e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -506,11 +507,11 @@ def main():
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
             return pipe, te.item()
 
-        pipe, dt = run_pipe(3, False)
+        pipe, dt = run_pipe(args.e2e_depth, False)
         e2e = {"value": audio_s / dt, "unit": "audio-s/s", "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
                "ms_per_step": dt * 1e3, "steps": ksteps,
                "api": "HostPipeline.submit: pinned host PCM in (H2D), kernels, final PCM + LUFS back to pinned host memory (D2H) every "
-                      "step, depth-3 overlap; the log-mel is handed to the transcriber on the device"}
+                      f"step, depth-{args.e2e_depth} overlap; the log-mel is handed to the transcriber on the device"}
         del pipe
         torch.cuda.empty_cache()
         pipe, dt = run_pipe(2, True)

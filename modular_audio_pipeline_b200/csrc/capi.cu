@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <stddef.h>
+#include <stdint.h>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -536,6 +537,27 @@ extern "C" int maf_set_noise_clips(maf_plan* pl, const int64_t* offsets, const i
 template <typename T> static T* ws_ptr(void* ws, const WsBuf& b) { return reinterpret_cast<T*>(static_cast<unsigned char*>(ws) + b.off); }
 
 __global__ void fill_int_kernel(int* p, int n, int v) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+__global__ void zero_bytes_kernel(unsigned char* p, size_t bytes) {
+    const size_t n16 = bytes / 16, gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = gtid; i < n16; i += (size_t)gridDim.x * blockDim.x) reinterpret_cast<uint4*>(p)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (gtid < bytes - 16 * n16) p[16 * n16 + gtid] = 0;
+}
+__global__ void copy_bytes_kernel(unsigned char* dst, const unsigned char* src, size_t bytes) {
+    const size_t n16 = bytes / 16, gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = gtid; i < n16; i += (size_t)gridDim.x * blockDim.x) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+    if (gtid < bytes - 16 * n16) dst[16 * n16 + gtid] = src[16 * n16 + gtid];
+}
+namespace maf {
+static int fill_grid(size_t bytes) { const size_t b = (bytes / 16 + 255) / 256; return (int)(b < 1 ? 1 : b > 1184 ? 1184 : b); }
+void launch_zero_bytes(void* p, size_t bytes, cudaStream_t st) {
+    if (bytes) zero_bytes_kernel<<<fill_grid(bytes), 256, 0, st>>>(static_cast<unsigned char*>(p), bytes);
+}
+void launch_copy_bytes(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (!bytes) return;
+    if ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) { cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st); return; }
+    copy_bytes_kernel<<<fill_grid(bytes), 256, 0, st>>>(static_cast<unsigned char*>(dst), static_cast<const unsigned char*>(src), bytes);
+}
+}  // namespace maf
 __global__ void abs_max_kernel(const int16_t* __restrict__ x, const Item* __restrict__ items, int* __restrict__ peak) {
     const Item it = items[blockIdx.y];
     int pk = 0;
@@ -588,7 +610,7 @@ static int run_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pc
     const int n = pl->n_items;
     Clip* clips = ws_ptr<Clip>(ws, pl->clips);
     mark(pl, ST_BEGIN, st);
-    CU(cudaMemsetAsync(ws_ptr<int>(ws, pl->peak), 0, 4LL * n, st));
+    launch_zero_bytes(ws_ptr<int>(ws, pl->peak), 4LL * n, st);
     if (p.stationary) {
         const int16_t* noise_src = pcm;
         const Clip* use_clips = clips;
@@ -626,7 +648,7 @@ static int run_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pc
         launch_noise_threshold(noise_src, use_clips, n, pl->n_slices, pl->ctx->c, ws_ptr<unsigned>(ws, pl->nmax),
                                ws_ptr<double>(ws, pl->partial), ws_ptr<float>(ws, pl->T2), ws_ptr<float>(ws, pl->T2hi), 1.5, st);
         pl->launches += 3;
-        CU(cudaMemsetAsync(ws_ptr<uint8_t>(ws, pl->rowflag), 0, pl->rowflag.bytes, st));
+        launch_zero_bytes(ws_ptr<uint8_t>(ws, pl->rowflag), pl->rowflag.bytes, st);
     }
     mark(pl, ST_NOISE, st);
     launch_stft(pcm, pl->d_items, pl->d_chunks, pl->n_chunks, pl->max_chunk_frames, pl->ctx->c, p.stationary, ws_ptr<float>(ws, pl->T2),
@@ -658,7 +680,7 @@ static int run_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pc
 static int run_loudness_stats(maf_plan* pl, const int16_t* src, const Item* items, int peak_normalize, void* ws, cudaStream_t st) {
     if (pl->too_short) return fail(MAF_ERR_TOO_SHORT, "Audio must have length greater than the block size");
     const int n = pl->n_items;
-    CU(cudaMemsetAsync(ws_ptr<int>(ws, pl->peak_norm), 0, 4LL * n, st));
+    launch_zero_bytes(ws_ptr<int>(ws, pl->peak_norm), 4LL * n, st);
     if (peak_normalize) { launch_peak_factor(ws_ptr<int>(ws, pl->peak), n, pl->target_peak, ws_ptr<PeakNorm>(ws, pl->pnorm), st); pl->launches += 1; }
     launch_kweight_energy(src, items, n, pl->max_kgroups, pl->tile_len, pl->kgeo, pl->kw, (const KwScan*)pl->d_kscan, peak_normalize, ws_ptr<PeakNorm>(ws, pl->pnorm),
                           ws_ptr<double>(ws, pl->sub), ws_ptr<int>(ws, pl->peak_norm), st);
@@ -722,7 +744,7 @@ extern "C" int maf_process(maf_plan* pl, const int16_t* pcm, const int16_t* nois
         pl->launches += 1;
     }
     if (lufs) { gather_lufs_kernel<<<(pl->n_items + 255) / 256, 256, 0, st>>>(gates, pl->n_items, lufs); pl->launches += 1; }
-    if (clip && pl->p.stationary) CU(cudaMemcpyAsync(clip, ws_ptr<int>(ws, pl->seg), 8LL * pl->n_items, cudaMemcpyDeviceToDevice, st));
+    if (clip && pl->p.stationary) launch_copy_bytes(clip, ws_ptr<int>(ws, pl->seg), 8LL * pl->n_items, st);
     CU(cudaGetLastError());
     if (pl->prof_steps) pl->prof_calls += 1;
     return MAF_OK;
@@ -768,7 +790,7 @@ extern "C" int maf_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* nois
     CU(cudaSetDevice(pl->ctx->device));
     int rc = run_denoise(pl, pcm, noise_pcm, ws, out_pcm, 1, out_f32, st);
     if (rc) return rc;
-    if (clip && pl->p.stationary) CU(cudaMemcpyAsync(clip, ws_ptr<int>(ws, pl->seg), 8LL * pl->n_items, cudaMemcpyDeviceToDevice, st));
+    if (clip && pl->p.stationary) launch_copy_bytes(clip, ws_ptr<int>(ws, pl->seg), 8LL * pl->n_items, st);
     return MAF_OK;
 }
 
@@ -776,7 +798,7 @@ extern "C" int maf_peak_normalize(maf_plan* pl, const int16_t* pcm, void* ws, in
     if (!pl || !pcm || !ws || !out_pcm) return fail(MAF_ERR_INVALID, "maf_peak_normalize: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(pl->ctx->device));
-    CU(cudaMemsetAsync(ws_ptr<int>(ws, pl->peak), 0, 4LL * pl->n_items, st));
+    launch_zero_bytes(ws_ptr<int>(ws, pl->peak), 4LL * pl->n_items, st);
     long long bx = std::max<long long>(1, std::min<long long>(1024, (pl->max_own + 4095) / 4096));
     dim3 grid((unsigned)bx, pl->n_items);
     abs_max_kernel<<<grid, 256, 0, st>>>(pcm, pl->d_items_io, ws_ptr<int>(ws, pl->peak));

@@ -60,7 +60,7 @@ void launch_front_door(const int16_t* x, long long n_in, int channels, long long
                        double target_peak, int peak_normalize, int16_t* out, long long n_out, cudaStream_t st) {
     if (n_in <= 0 || n_out <= 0) return;
     if (peak_normalize) {
-        cudaMemsetAsync(peak_scratch, 0, sizeof(int), st);
+        launch_zero_bytes(peak_scratch, sizeof(int), st);
         const long long n = n_in * channels;
         long long bx = (n + 256 * 16 - 1) / (256 * 16);
         if (bx > 2048) bx = 2048;

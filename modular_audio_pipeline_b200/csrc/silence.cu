@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) silence_flags_kernel(const unsigned long 
 
 void launch_ms_energy(const int16_t* x, long long n, int rate, long long n_ms, unsigned long long* bucket, unsigned long long* total,
                       cudaStream_t st) {
-    cudaMemsetAsync(total, 0, 8, st);
+    launch_zero_bytes(total, 8, st);
     if (n_ms <= 0) return;
     ms_energy_kernel<<<(unsigned)((n_ms + 255) / 256), 256, 0, st>>>(x, n, (double)rate / 1000.0, n_ms, bucket, total);
 }

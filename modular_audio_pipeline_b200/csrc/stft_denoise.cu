@@ -452,8 +452,8 @@ void launch_noise_threshold(const int16_t* pcm, const Clip* clips, int n_items, 
                             const Consts& c, unsigned* nmax, double* partial, float* T2, float* T2hi, double n_std,
                             cudaStream_t st) {
     if (n_items <= 0) return;
-    cudaMemsetAsync(nmax, 0, sizeof(unsigned) * (size_t)n_items * T_PITCH, st);
-    cudaMemsetAsync(partial, 0, sizeof(double) * (size_t)n_items * n_slices * 4 * 2 * T_PITCH, st);
+    launch_zero_bytes(nmax, sizeof(unsigned) * (size_t)n_items * T_PITCH, st);
+    // `partial` needs no clearing: pass 2 writes every (slice, group, bin) entry, zeros included
     dim3 grid(n_slices, n_items);
     noise_pass_kernel<1><<<grid, 256, 0, st>>>(pcm, clips, c, nmax, partial, n_slices);
     noise_pass_kernel<2><<<grid, 256, 0, st>>>(pcm, clips, c, nmax, partial, n_slices);
