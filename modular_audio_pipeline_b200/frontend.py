@@ -317,8 +317,10 @@ def capture_graph(fn, device=None):
 
 
 class HostPipeline:
-    """Host-buffer entry with copy / compute overlap: ``depth`` plans (each with its own device buffers and stream) are
-    used round-robin, so the H2D copy and the kernels of batch i+1 run while batch i's results travel back over PCIe.
+    """Host-buffer entry with copy / compute overlap: a three-stage pipeline -- upload stream, kernel stream, download stream,
+    chained by events -- over ``depth`` slots (plan + device / pinned buffers each), so the H2D copy of batch i+1 and the D2H
+    copy of batch i-1 run while the kernels of batch i do.  All kernels are issued to ONE stream in submission order: steps
+    never time-slice the SMs against each other, each stage is busy with exactly one batch.
 
     ``submit(slot_inputs)`` is asynchronous; ``results(slot)`` waits for that slot and returns pinned host tensors
     (final int16 PCM, float32 log-mel, float64 LUFS) in the plan's layouts.
@@ -333,7 +335,9 @@ class HostPipeline:
         self.plans = [fe.plan(lengths, **plan_kw) for _ in range(depth)]
         p0 = self.plans[0]
         dev = fe.device
-        self.streams = [torch.cuda.Stream(dev) for _ in range(depth)]
+        self.s_in, self.s_k, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_k = [torch.cuda.Event() for _ in range(depth)]
         self.d_in = [torch.empty(max(p0.total_pcm, 8), dtype=torch.int16, device=dev) for _ in range(depth)]
         self.d_out = [torch.empty(max(p0.total_out, 8), dtype=torch.int16, device=dev) for _ in range(depth)]
         self.d_mel = [torch.empty(max(p0.total_mel, 4), dtype=torch.float32, device=dev) for _ in range(depth)]
@@ -359,16 +363,23 @@ class HostPipeline:
         """Process the batch currently in ``h_in[slot]`` (slot = submission count mod depth).  Returns the slot."""
         slot = self._n % self.depth
         self._n += 1
-        plan, st = self.plans[slot], self.streams[slot]
+        plan = self.plans[slot]
         self.done[slot].synchronize()                      # the slot's previous results must have been consumed
-        with torch.cuda.stream(st):
+        with torch.cuda.stream(self.s_in):
             self.d_in[slot].copy_(self.h_in[slot], non_blocking=True)
+            self.ev_in[slot].record(self.s_in)
+        self.s_k.wait_event(self.ev_in[slot])
+        with torch.cuda.stream(self.s_k):
             res = plan.process(self.d_in[slot], out_pcm=self.d_out[slot], mel=self.d_mel[slot] if plan.params.n_mels else None)
+            self.ev_k[slot].record(self.s_k)
+        res.lufs.record_stream(self.s_out)
+        self.s_out.wait_event(self.ev_k[slot])
+        with torch.cuda.stream(self.s_out):
             self.h_out[slot].copy_(self.d_out[slot], non_blocking=True)
             if plan.params.n_mels and self.mel_to_host:
                 self.h_mel[slot].copy_(self.d_mel[slot], non_blocking=True)
             self.h_lufs[slot].copy_(res.lufs, non_blocking=True)
-            self.done[slot].record(st)
+            self.done[slot].record(self.s_out)
         return slot
 
     def next_slot(self) -> int:
