@@ -764,9 +764,9 @@ void launch_ns_mask(const c32* S, const Chunk* chunks, int n_chunks, int max_fra
 // ============================================================================================================
 // K2  separable triangular smoothing of the stationary gate (scipy.signal.fftconvolve(mask, outer(vf, vt)/sum, 'same'),
 // zero padded): raw = bit | rowflag ? 1 : 1 - prop (blend, then smooth).  Same structure as the non-stationary mask
-// kernel: a CTA owns 32 output frames, one thread per bin walks the 32 + 2 nt raw rows (one warp-uniform 4-byte load of
-// the frame's bit word per row, eight rows in flight), applies the time taps in a register window and leaves the rows in
-// shared memory for the frequency taps.
+// kernel: a CTA owns 32 output frames, one thread per bin walks the 32 + 2 nt raw rows (bit words staged in shared memory,
+// one broadcast load per row), applies the time taps in a register window and leaves the rows in shared memory for the
+// frequency taps.
 // ============================================================================================================
 template <int NT>
 __global__ void __launch_bounds__(NSM_THREADS, 2) smooth_mask_kernel(const uint32_t* __restrict__ bits, const uint8_t* __restrict__ rowflag,
@@ -779,44 +779,42 @@ __global__ void __launch_bounds__(NSM_THREADS, 2) smooth_mask_kernel(const uint3
     const int base = NS_TILE * blockIdx.x;                        // outputs [base, base + 32), raw rows [base - NT, base + 32 + NT)
     if (base >= F) return;
     const int tid = threadIdx.x;
+    // the tile's bit words (W rows x 17 words) go to shared memory with ONE round of loads per CTA: the per-bin walk below
+    // used to wait for a global load every eight rows (46 % of the kernel's stall samples)
+    constexpr int BW = (NBIN + 31) / 32;                          // 17 words per row
+    __shared__ uint32_t bw[W * BW];
+    for (int i = tid; i < W * BW; i += NSM_THREADS) {
+        const int r = i / BW, c = i - r * BW;
+        const int rr = base - NT + r;
+        bw[i] = (rr >= 0 && rr < F) ? __ldg(bits + (ch.row0 + rr) * B_PITCH + c) : 0u;
+    }
     for (int i = tid; i < NS_TILE * (SM_ROW - NBIN); i += NSM_THREADS) {
         const int r = i / (SM_ROW - NBIN), c = i - r * (SM_ROW - NBIN);
         rows[r * SM_ROW + swz(c < MAX_NF ? c : c + NBIN)] = 0.f;
     }
+    const bool rf = tid < NBIN ? rowflag[(long long)blockIdx.y * M_PITCH + tid] != 0 : false;
+    __syncthreads();
     if (tid < NBIN) {
         const int k = tid;
         const float lo = 1.0f - prop;
-        const bool rf = rowflag[(long long)blockIdx.y * M_PITCH + k] != 0;
-        const uint32_t* bp = bits + ch.row0 * B_PITCH + (k >> 5);
+        const uint32_t* bp = bw + (k >> 5);
         const int sh = k & 31;
         float vt[2 * NT + 1], w[2 * NT + 1];
 #pragma unroll
         for (int i = 0; i < 2 * NT + 1; ++i) { vt[i] = taps.vt[i]; w[i] = 0.f; }
 #pragma unroll
-        for (int b0 = 0; b0 < W; b0 += 8) {
-            uint32_t wd[8];
+        for (int i = 0; i < W; ++i) {
+            const int rr = base - NT + i;
+            const float R = (rr >= 0 && rr < F) ? ((((bp[i * BW] >> sh) & 1u) | (rf ? 1u : 0u)) ? 1.0f : lo) : 0.f;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int rr = base - NT + b0 + q;
-                wd[q] = (b0 + q < W && rr >= 0 && rr < F) ? __ldg(bp + (long long)rr * B_PITCH) : 0u;
-            }
+            for (int j = 0; j < 2 * NT; ++j) w[j] = w[j + 1];
+            w[2 * NT] = R;                                        // w[j] = raw mask of frame rr - 2 NT + j
+            if (i >= 2 * NT) {
+                const int lr = i - 2 * NT;                        // output frame rr - NT = base + lr
+                float acc = vt[0] * w[0];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int i = b0 + q;
-                if (i < W) {
-                    const int rr = base - NT + i;
-                    const float R = (rr >= 0 && rr < F) ? ((((wd[q] >> sh) & 1u) | (rf ? 1u : 0u)) ? 1.0f : lo) : 0.f;
-#pragma unroll
-                    for (int j = 0; j < 2 * NT; ++j) w[j] = w[j + 1];
-                    w[2 * NT] = R;                                // w[j] = raw mask of frame rr - 2 NT + j
-                    if (i >= 2 * NT) {
-                        const int lr = i - 2 * NT;                // output frame rr - NT = base + lr
-                        float acc = vt[0] * w[0];
-#pragma unroll
-                        for (int j = 1; j < 2 * NT + 1; ++j) acc = fmaf(vt[j], w[j], acc);
-                        rows[lr * SM_ROW + swz(MAX_NF + k)] = acc;
-                    }
-                }
+                for (int j = 1; j < 2 * NT + 1; ++j) acc = fmaf(vt[j], w[j], acc);
+                rows[lr * SM_ROW + swz(MAX_NF + k)] = acc;
             }
         }
     }
