@@ -15,9 +15,11 @@ reference's.  This is I/O only -- no arithmetic on samples happens here.
 """
 from __future__ import annotations
 
+import os
 import struct
 import threading
 import wave
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 from typing import Iterable, Iterator, List, Optional, Tuple
 
@@ -41,6 +43,42 @@ class WavInfo:
 
 class _Unrecognised(Exception):
     pass
+
+
+# Large data chunks are READ with several pread calls in flight (the syscalls release the GIL): copying out of the page cache
+# is a per-core memcpy, one thread tops out near 3 GB/s where eight reach 13+ GB/s (115 MB: 33 -> 8 ms).  Writes stay on one
+# thread: allocating the pages of a new file serialises on the inode (measured on tmpfs: 50 ms with one thread, 60-70 ms with 2-8).
+_PAR_MIN = 8 << 20
+_PAR_THREADS = max(1, min(8, os.cpu_count() or 1))
+_pool: Optional[ThreadPoolExecutor] = None
+
+
+def _io_pool() -> ThreadPoolExecutor:
+    global _pool
+    if _pool is None:
+        _pool = ThreadPoolExecutor(_PAR_THREADS, thread_name_prefix="wavio")
+    return _pool
+
+
+def _chunked(fd: int, mv: memoryview, offset: int, write: bool) -> int:
+    """Move all of `mv` to / from `fd` at `offset`; returns the bytes moved (short only at end of file when reading)."""
+    n = len(mv)
+
+    def work(lo: int, hi: int) -> int:
+        done = 0
+        while lo < hi:
+            k = os.pwrite(fd, mv[lo:hi], offset + lo) if write else os.preadv(fd, [mv[lo:hi]], offset + lo)
+            if k <= 0:
+                break
+            lo += k; done += k
+        return done
+
+    if write or n < _PAR_MIN or _PAR_THREADS == 1:
+        return work(0, n)
+    step = -(-n // _PAR_THREADS)
+    step = (step + (1 << 20) - 1) & ~((1 << 20) - 1)
+    futs = [_io_pool().submit(work, lo, min(n, lo + step)) for lo in range(0, n, step)]
+    return sum(f.result() for f in futs)
 
 
 def read_header(f) -> WavInfo:
@@ -118,8 +156,7 @@ def read_pcm16(path: str, pool: Optional[PinnedPool] = None) -> Tuple[torch.Tens
         if info is not None and info.data_bytes % 2 == 0:
             n = info.data_bytes // 2
             out = pool.get(n) if pool is not None else torch.empty(n, dtype=torch.int16)
-            f.seek(info.data_offset)
-            got = f.readinto(memoryview(out.numpy()).cast("B")) if n else 0
+            got = _chunked(f.fileno(), memoryview(out.numpy()).cast("B"), info.data_offset, write=False) if n else 0
             if got == info.data_bytes:
                 return out, info
     # anything unusual: the wave module decides (and raises what the reference would raise)
@@ -145,10 +182,12 @@ def write_pcm16(path: str, pcm: torch.Tensor, rate: int) -> None:
     """Mono 16-bit PCM WAV from an int16 CPU tensor; the file equals the ``wave`` module's byte for byte."""
     if pcm.dtype != torch.int16 or pcm.device.type != "cpu" or not pcm.is_contiguous():
         raise ValueError("write_pcm16 takes a contiguous int16 CPU tensor")
-    with open(path, "wb") as f:
+    with open(path, "wb", buffering=0) as f:
         f.write(pcm16_header(pcm.numel(), rate))
         if pcm.numel():
-            f.write(memoryview(pcm.numpy()).cast("B"))
+            mv = memoryview(pcm.numpy()).cast("B")
+            if _chunked(f.fileno(), mv, 44, write=True) != len(mv):
+                raise OSError(f"short write to {path}")
 
 
 class WavPrefetcher:
