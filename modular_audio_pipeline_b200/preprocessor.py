@@ -264,3 +264,62 @@ class GpuAudioPreprocessor:
         out = res.pcm[0].clone(), float(res.lufs.item()), (res.log_mel[0].clone() if n_mels else None)
         plan.close()
         return out
+
+    def process_files(self, paths, batch_size: int = 64, n_mels: int = 80, mel_padding: int = 0, target_lufs: float = -16.0,
+                      write_output: bool = True):
+        """The orchestrator's chain (pipeline.py:331-347 + the transcriber's log-mel) for MANY files, one fused launch sequence per
+        batch: every file's data chunk is read straight into a page-locked batch buffer at its plan offset, one H2D copy, the
+        kernels, one D2H copy of the final PCM, and -- with ``write_output`` -- the same file the chained Protocol calls
+        would have left in ``temp_dir`` (``<stem>_denoised_norm_loudnorm.wav``; ``<stem>_norm_loudnorm.wav`` when noise
+        reduction is disabled).  Files must be 16-bit mono at ``self.sample_rate`` (the pipeline's contract,
+        media_handler.py:219-223).  Yields ``(output path or None, LUFS, log-mel CUDA tensor [n_mels, frames] or None)``
+        in input order; results are bit-identical to the chained calls."""
+        paths = [str(p) for p in paths]
+        fe = self.frontend
+        dev = fe.device
+        denoise = bool(self.noise_config.enabled)
+        for b0 in range(0, len(paths), max(1, batch_size)):
+            group = paths[b0:b0 + max(1, batch_size)]
+            try:
+                infos = [wavio.read_info(p) for p in group]
+                for p, i in zip(group, infos):
+                    if i.channels != 1 or i.sampwidth != 2 or i.rate != self.sample_rate:
+                        raise ValueError(f"{p}: {i.channels} ch / {8 * i.sampwidth} bit / {i.rate} Hz; the fused batch entry takes "
+                                         f"16-bit mono at {self.sample_rate} Hz (use normalize_audio for other input)")
+                lengths = [i.data_bytes // 2 for i in infos]
+                plan = fe.plan(lengths, sample_rate=self.sample_rate, stationary=self.stationary,
+                               auto_detect_noise=bool(self.noise_config.auto_detect_noise),
+                               noise_sample_duration_s=float(self.noise_config.noise_sample_duration_s),
+                               target_lufs=target_lufs, n_mels=n_mels, mel_padding=mel_padding)
+                h_in = self._in_pool.get(max(plan.total_pcm, 8))
+                h_in.zero_()
+                for p, i, lay, n in zip(group, infos, plan.layout, lengths):
+                    wavio.read_data_into(p, i, h_in[lay.pcm_off: lay.pcm_off + n])
+                d_in = h_in.to(dev, non_blocking=True)
+                if denoise:
+                    res = plan.process(d_in)
+                    pcm_out, mels, lufs = res.pcm, res.log_mel, res.lufs
+                else:
+                    norm = plan.peak_normalize(d_in)
+                    pcm_out, lufs = plan.loudness(plan.pack(norm))
+                    mels = plan.log_mel(plan.pack(pcm_out)) if n_mels else []
+                lufs_h = lufs.cpu().numpy()
+                mel_out = [m.clone() for m in mels] if n_mels else [None] * len(group)
+                outs: List[Optional[str]] = [None] * len(group)
+                if write_output:
+                    for k, (p, x) in enumerate(zip(group, pcm_out)):
+                        host = self._out_pool.get(x.numel())
+                        host.copy_(x, non_blocking=True)
+                        torch.cuda.current_stream(dev).synchronize()
+                        stem = Path(p).stem + ("_denoised" if denoise else "") + "_norm_loudnorm"
+                        outs[k] = os.path.join(self.temp_dir, f"{stem}.wav")
+                        wavio.write_pcm16(outs[k], host, self.sample_rate)
+                else:
+                    torch.cuda.current_stream(dev).synchronize()
+                plan.close()
+            except AudioProcessingError:
+                raise
+            except Exception as e:
+                raise AudioProcessingError("Batch processing failed", details=str(e))
+            for k in range(len(group)):
+                yield outs[k], float(lufs_h[k]), mel_out[k]

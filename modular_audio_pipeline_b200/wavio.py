@@ -171,6 +171,37 @@ def read_pcm16(path: str, pool: Optional[PinnedPool] = None) -> Tuple[torch.Tens
     return x, WavInfo(ch, sw, sr, len(raw) // (ch * sw), -1, len(raw))
 
 
+def read_info(path: str) -> WavInfo:
+    """Header fields only (``data_offset`` is -1 when the file needs the ``wave`` module's own parser)."""
+    with open(path, "rb") as f:
+        try:
+            return read_header(f)
+        except _Unrecognised:
+            pass
+    with wave.open(path, "rb") as wf:
+        ch, sw, sr, nf = wf.getnchannels(), wf.getsampwidth(), wf.getframerate(), wf.getnframes()
+    return WavInfo(ch, sw, sr, nf, -1, nf * ch * sw)
+
+
+def read_data_into(path: str, info: WavInfo, out: torch.Tensor) -> None:
+    """The data chunk described by `info` straight into `out` (int16 CPU tensor of exactly ``info.data_bytes // 2`` samples,
+    e.g. a slice of a pinned batch buffer at the plan's offset for this file)."""
+    if out.dtype != torch.int16 or out.device.type != "cpu" or not out.is_contiguous() or 2 * out.numel() != info.data_bytes:
+        raise ValueError("read_data_into: `out` must be a contiguous int16 CPU tensor of the data chunk's size")
+    if not out.numel():
+        return
+    mv = memoryview(out.numpy()).cast("B")
+    if info.data_offset >= 0:
+        with open(path, "rb") as f:
+            if _chunked(f.fileno(), mv, info.data_offset, write=False) == info.data_bytes:
+                return
+    with wave.open(path, "rb") as wf:
+        raw = wf.readframes(wf.getnframes())
+    if len(raw) != info.data_bytes:
+        raise OSError(f"{path}: data chunk changed size")
+    mv[:] = raw
+
+
 def pcm16_header(n_samples: int, rate: int, channels: int = 1) -> bytes:
     """The 44-byte header ``wave.open(path, 'wb')`` writes for 16-bit PCM (``preprocessor.py:81-88``: mono, 2 bytes)."""
     data = 2 * n_samples
@@ -227,4 +258,4 @@ class WavPrefetcher:
             yield item
 
 
-__all__ = ["WavInfo", "PinnedPool", "read_header", "read_pcm16", "pcm16_header", "write_pcm16", "WavPrefetcher"]
+__all__ = ["WavInfo", "PinnedPool", "read_header", "read_info", "read_data_into", "read_pcm16", "pcm16_header", "write_pcm16", "WavPrefetcher"]

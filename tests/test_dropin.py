@@ -228,3 +228,35 @@ def test_encoder_windows_bit_exact(frontend, dtype):
             want = GpuLogMelFrontEnd.pad_or_trim(seg, length).to(dt)
             assert torch.equal(got[w], want), (dtype, length, w)
     assert fe.windows(mel, [], None).shape == (0, 80, 3000)
+
+
+@pytest.mark.gpu
+def test_process_files_equals_chained_protocol_calls(tmp_path, frontend):
+    """The fused file-batch entry leaves the same WAV the three chained Protocol calls leave (bit for bit), for ragged lengths
+    and more files than one batch holds; the log-mel equals log_mel of that file."""
+    from modular_audio_pipeline_b200 import GpuAudioPreprocessor
+    from modular_audio_pipeline_b200.transcriber import GpuLogMelFrontEnd
+    secs = [4.0, 7.31, 2.5, 11.0, 3.003]
+    paths = []
+    for i, s in enumerate(secs):
+        p = tmp_path / f"in{i}.wav"
+        _write_wav(p, speech_noise(s, 20 + i).numpy())
+        paths.append(str(p))
+    chained = GpuAudioPreprocessor(SR, str(tmp_path / "a"), device=frontend.device)
+    fused = GpuAudioPreprocessor(SR, str(tmp_path / "b"), device=frontend.device)
+    chained._fe = fused._fe = frontend
+    lm = GpuLogMelFrontEnd(frontend.device); lm._fe = frontend
+    got = list(fused.process_files(paths, batch_size=2, n_mels=80, mel_padding=160))
+    assert len(got) == len(paths)
+    for p, (out, lufs, mel) in zip(paths, got):
+        want_path = chained.normalize_loudness(chained.normalize_audio(chained.reduce_stationary_noise(p)))
+        assert os.path.basename(out) == os.path.basename(want_path)
+        w, _, _ = _read_wav(want_path)
+        g, sr, ch = _read_wav(out)
+        assert sr == SR and ch == 1 and np.array_equal(g, w)
+        assert np.isfinite(lufs)
+        want_mel = lm.log_mel_spectrogram(torch.from_numpy(g.copy()), 80, 160)
+        assert torch.equal(mel, want_mel)
+    # no files written, no mel
+    res = list(fused.process_files(paths[:1], n_mels=0, write_output=False))
+    assert res[0][0] is None and res[0][2] is None
