@@ -10,6 +10,7 @@
 //                      non-noise frame (an open run at the end is dropped, like the reference's loop).
 #include <cooperative_groups.h>
 #include "maf_common.cuh"
+#include "run_merge.h"
 
 namespace maf {
 
@@ -269,37 +270,6 @@ __device__ void radix_select2(bool cached, const float (&eR)[SEL_CACHE], const f
     __syncthreads();
 }
 
-struct RunSummary { int all, lead, trail, best_len, best_start; };
-
-// merge of the summaries of two adjacent frame ranges (L before R); lenL / lenR are their lengths, startR = first frame of R
-__device__ __forceinline__ RunSummary merge_runs(const RunSummary& L, int lenL, const RunSummary& R, int lenR, int startR) {
-    RunSummary o;
-    if (lenL <= 0) return R;
-    if (lenR <= 0) return L;
-    o.all = L.all && R.all;
-    o.lead = L.all ? lenL + R.lead : L.lead;
-    o.trail = R.all ? lenR + L.trail : R.trail;
-    o.best_len = L.best_len; o.best_start = L.best_start;
-    if (!L.all && !R.all) {                                     // the run across the seam is closed on both sides
-        const int mid = L.trail + R.lead;
-        if (mid > o.best_len) { o.best_len = mid; o.best_start = startR - L.trail; }
-    }
-    if (R.best_len > o.best_len) { o.best_len = R.best_len; o.best_start = R.best_start; }
-    if (o.all) { o.best_len = 0; o.best_start = 0; }
-    return o;
-}
-
-// A frame range with its summary; len == 0 is the identity of merge_seg.
-struct RunSeg { RunSummary r; int start, len; };
-
-__device__ __forceinline__ RunSeg merge_seg(const RunSeg& L, const RunSeg& R) {
-    RunSeg o;
-    o.r = merge_runs(L.r, L.len, R.r, R.len, R.start);
-    o.start = L.len > 0 ? L.start : R.start;
-    o.len = L.len + R.len;
-    return o;
-}
-
 __device__ __forceinline__ RunSeg shfl_down_seg(const RunSeg& s, int d) {
     RunSeg o;
     o.r.all = __shfl_down_sync(0xffffffffu, s.r.all, d); o.r.lead = __shfl_down_sync(0xffffffffu, s.r.lead, d);
@@ -322,8 +292,7 @@ __device__ RunSeg block_merge_segs(RunSeg s, RunSeg* wsm) {
     if (lane == 0) wsm[warp] = s;
     __syncthreads();
     if (warp == 0) {
-        RunSeg e; e.r.all = 1; e.r.lead = 0; e.r.trail = 0; e.r.best_len = 0; e.r.best_start = 0; e.start = 0; e.len = 0;
-        s = lane < n_warps ? wsm[lane] : e;
+        s = lane < n_warps ? wsm[lane] : empty_seg();
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const RunSeg o = shfl_down_seg(s, d);
@@ -333,16 +302,12 @@ __device__ RunSeg block_merge_segs(RunSeg s, RunSeg* wsm) {
     return s;
 }
 
-// the reference's rule on the merged summary: candidates in order of their start -- the leading run (closed unless
-// everything is noise), then the best interior run; an open run at the end is dropped like in the reference's loop
+// the duration test of the reference's loop on the longest closed run: (i - start) * hop / sr >= 0.1 (length ordering equals
+// frame-count ordering)
 __device__ __forceinline__ void pick_run(const RunSummary& acc, int hop, int sr, int& found, int& bs, int& bl) {
-    bl = 0; bs = 0;
-    if (!acc.all && acc.lead > bl) { bl = acc.lead; bs = 0; }
-    if (acc.best_len > bl) { bl = acc.best_len; bs = acc.best_start; }
-    // (i - start) * hop / sr >= 0.1 ; longest first-maximum run.  Length ordering equals frame-count ordering.
+    pick_longest_closed(acc, bs, bl);
     found = bl > 0 && __ddiv_rn((double)((long long)bl * hop), (double)sr) >= 0.1;
 }
-
 
 __global__ void __launch_bounds__(SEL_THREADS) select_clip_kernel(const float* __restrict__ energies, const int* __restrict__ zc,
                                                                    const long long* __restrict__ foff, const int* __restrict__ fcount,
@@ -438,25 +403,9 @@ __global__ void __launch_bounds__(SEL_THREADS) select_clip_kernel(const float* _
         const int per = (F + SEL_THREADS - 1) / SEL_THREADS;
         const int s0 = min(F, tid * per), s1 = min(F, s0 + per);
         RunSeg seg; seg.start = s0; seg.len = s1 - s0;
-        RunSummary rs; rs.all = 1; rs.lead = 0; rs.trail = 0; rs.best_len = 0; rs.best_start = 0;
-        {
-            int run_start = -1; bool seen_false = false;
-            for (int i = s0; i < s1; ++i) {
-                const bool nz = cached ? flags[i] != 0 : (((double)E[i] < eT) && (__ddiv_rn((double)Z[i], (double)frame_len) > zT));
-                if (nz) {
-                    if (run_start < 0) run_start = i;
-                } else {
-                    if (run_start >= 0) {
-                        if (!seen_false && run_start == s0) rs.lead = i - s0;
-                        else if (i - run_start > rs.best_len) { rs.best_len = i - run_start; rs.best_start = run_start; }
-                        run_start = -1;
-                    }
-                    seen_false = true; rs.all = 0;
-                }
-            }
-            if (rs.all) { rs.lead = s1 - s0; rs.trail = s1 - s0; }
-            else rs.trail = (run_start >= 0) ? s1 - run_start : 0;
-        }
+        const RunSummary rs = summarize_range(s0, s1, [&](int i) {
+            return cached ? flags[i] != 0 : (((double)E[i] < eT) && (__ddiv_rn((double)Z[i], (double)frame_len) > zT));
+        });
         seg.r = rs;
         seg = block_merge_segs(seg, wsm);
         if (tid == 0) pick_run(seg.r, hop, sr, found, best_s, best_l);
@@ -605,30 +554,16 @@ __global__ void __launch_bounds__(SEL_THREADS) select_clip_grid_kernel(const flo
     const int c0 = min(F, blockIdx.x * per_cta), c1 = min(F, c0 + per_cta);
     {
         const int s0 = min(c1, c0 + tid * per), s1 = min(c1, s0 + per);
-        RunSummary rs; rs.all = 1; rs.lead = 0; rs.trail = 0; rs.best_len = 0; rs.best_start = 0;
-        int run_start = -1; bool seen_false = false;
-        for (int i = s0; i < s1; ++i) {
-            const bool nz = ((double)E[i] < eT) && (__ddiv_rn((double)Z[i], (double)frame_len) > zT);
-            if (nz) {
-                if (run_start < 0) run_start = i;
-            } else {
-                if (run_start >= 0) {
-                    if (!seen_false && run_start == s0) rs.lead = i - s0;
-                    else if (i - run_start > rs.best_len) { rs.best_len = i - run_start; rs.best_start = run_start; }
-                    run_start = -1;
-                }
-                seen_false = true; rs.all = 0;
-            }
-        }
-        if (rs.all) { rs.lead = s1 - s0; rs.trail = s1 - s0; }
-        else rs.trail = (run_start >= 0) ? s1 - run_start : 0;
+        const RunSummary rs = summarize_range(s0, s1, [&](int i) {
+            return ((double)E[i] < eT) && (__ddiv_rn((double)Z[i], (double)frame_len) > zT);
+        });
         RunSeg seg; seg.r = rs; seg.start = s0; seg.len = s1 - s0;
         seg = block_merge_segs(seg, wsm);
         if (tid == 0) g->sums[blockIdx.x] = seg.r;
     }
     grid.sync();
     if (leader) {
-        RunSeg seg; seg.r.all = 1; seg.r.lead = 0; seg.r.trail = 0; seg.r.best_len = 0; seg.r.best_start = 0; seg.start = 0; seg.len = 0;
+        RunSeg seg = empty_seg();
         if (tid < (int)gridDim.x) {
             const int a0 = min(F, tid * per_cta), a1 = min(F, a0 + per_cta);
             seg.r = g->sums[tid]; seg.start = a0; seg.len = a1 - a0;

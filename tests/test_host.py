@@ -124,3 +124,13 @@ def test_wav_prefetcher_order_and_buffer_lifetime(tmp_path):
                 assert np.array_equal(xj.numpy(), want[j])
     with pytest.raises(Exception):
         list(wavio.WavPrefetcher([paths[0], str(tmp_path / "nope.wav")], pinned=False))
+
+
+def test_run_merge_logic_on_cpu(tmp_path):
+    """csrc/run_merge.h (per-thread run summaries + associative merge, as used by select_clip_kernel and the grid-wide
+    selection) against the literal loop of the reference's _detect_noise_segments, randomised, incl. empty and all-noise."""
+    exe = tmp_path / "host_runs_check"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tests", "host", "host_runs_check.cpp")])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "OK" in out.stdout
