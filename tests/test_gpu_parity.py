@@ -142,6 +142,16 @@ def test_peak_normalize_bit_exact(frontend, seed):
     plan = frontend.plan([pcm.numel()], n_mels=0)
     out = plan.peak_normalize(plan.pack([pcm]))[0].cpu().numpy()
     assert np.array_equal(out, O.peak_normalize(pcm.numpy()))
+    try:                                                    # pydub.effects.normalize = audioop.max + audioop.mul (stdlib C code)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", DeprecationWarning)
+            import audioop
+        b = pcm.numpy().tobytes()
+        ref = np.frombuffer(audioop.mul(b, 2, O.peak_normalize_factor(audioop.max(b, 2))), dtype=np.int16)
+        assert np.array_equal(out, ref)
+    except ImportError:
+        pass
     silent = torch.zeros(8000, dtype=torch.int16)
     plan = frontend.plan([8000], n_mels=0)
     assert np.array_equal(plan.peak_normalize(plan.pack([silent]))[0].cpu().numpy(), silent.numpy())
@@ -383,6 +393,23 @@ def test_front_door_bit_exact(frontend, channels, in_rate, out_rate):
     assert np.array_equal(got.cpu().numpy(), want)
     raw = frontend.front_door(torch.from_numpy(x).to(frontend.device), channels, in_rate, out_rate, normalize=False)
     assert np.array_equal(raw.cpu().numpy(), O.front_door(x, channels, in_rate, out_rate, normalize=False))
+    # and directly against the C implementation pydub calls (stdlib audioop, still shipped with Python 3.12): max / mul / ratecv /
+    # tomono in pydub's order -- this stage's parity IS pinned to the reference's own arithmetic
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", DeprecationWarning)
+            import audioop
+    except ImportError:
+        return
+    b = x.tobytes()
+    peak = audioop.max(b, 2)
+    b = audioop.mul(b, 2, O.peak_normalize_factor(peak)) if peak else b
+    if in_rate != out_rate:
+        b, _ = audioop.ratecv(b, 2, channels, in_rate, out_rate, None)
+    if channels == 2:
+        b = audioop.tomono(b, 2, 0.5, 0.5)
+    assert np.array_equal(got.cpu().numpy(), np.frombuffer(b, dtype=np.int16))
 
 
 # ---- full size: BASELINE config 2 (1 h, non-stationary, 128-mel, 30 s pad), the workload bench.py times ----------------
