@@ -611,6 +611,7 @@ static int run_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pc
     Clip* clips = ws_ptr<Clip>(ws, pl->clips);
     mark(pl, ST_BEGIN, st);
     launch_zero_bytes(ws_ptr<int>(ws, pl->peak), 4LL * n, st);
+    pl->launches += 1;
     if (p.stationary) {
         const int16_t* noise_src = pcm;
         const Clip* use_clips = clips;
@@ -649,6 +650,7 @@ static int run_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pc
                                ws_ptr<double>(ws, pl->partial), ws_ptr<float>(ws, pl->T2), ws_ptr<float>(ws, pl->T2hi), 1.5, st);
         pl->launches += 3;
         launch_zero_bytes(ws_ptr<uint8_t>(ws, pl->rowflag), pl->rowflag.bytes, st);
+        pl->launches += 2;                                   // + the nmax clear inside launch_noise_threshold
     }
     mark(pl, ST_NOISE, st);
     launch_stft(pcm, pl->d_items, pl->d_chunks, pl->n_chunks, pl->max_chunk_frames, pl->ctx->c, p.stationary, ws_ptr<float>(ws, pl->T2),
@@ -681,6 +683,7 @@ static int run_loudness_stats(maf_plan* pl, const int16_t* src, const Item* item
     if (pl->too_short) return fail(MAF_ERR_TOO_SHORT, "Audio must have length greater than the block size");
     const int n = pl->n_items;
     launch_zero_bytes(ws_ptr<int>(ws, pl->peak_norm), 4LL * n, st);
+    pl->launches += 1;
     if (peak_normalize) { launch_peak_factor(ws_ptr<int>(ws, pl->peak), n, pl->target_peak, ws_ptr<PeakNorm>(ws, pl->pnorm), st); pl->launches += 1; }
     launch_kweight_energy(src, items, n, pl->max_kgroups, pl->tile_len, pl->kgeo, pl->kw, (const KwScan*)pl->d_kscan, peak_normalize, ws_ptr<PeakNorm>(ws, pl->pnorm),
                           ws_ptr<double>(ws, pl->sub), ws_ptr<int>(ws, pl->peak_norm), st);
@@ -744,7 +747,7 @@ extern "C" int maf_process(maf_plan* pl, const int16_t* pcm, const int16_t* nois
         pl->launches += 1;
     }
     if (lufs) { gather_lufs_kernel<<<(pl->n_items + 255) / 256, 256, 0, st>>>(gates, pl->n_items, lufs); pl->launches += 1; }
-    if (clip && pl->p.stationary) launch_copy_bytes(clip, ws_ptr<int>(ws, pl->seg), 8LL * pl->n_items, st);
+    if (clip && pl->p.stationary) { launch_copy_bytes(clip, ws_ptr<int>(ws, pl->seg), 8LL * pl->n_items, st); pl->launches += 1; }
     CU(cudaGetLastError());
     if (pl->prof_steps) pl->prof_calls += 1;
     return MAF_OK;
@@ -790,7 +793,7 @@ extern "C" int maf_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* nois
     CU(cudaSetDevice(pl->ctx->device));
     int rc = run_denoise(pl, pcm, noise_pcm, ws, out_pcm, 1, out_f32, st);
     if (rc) return rc;
-    if (clip && pl->p.stationary) launch_copy_bytes(clip, ws_ptr<int>(ws, pl->seg), 8LL * pl->n_items, st);
+    if (clip && pl->p.stationary) { launch_copy_bytes(clip, ws_ptr<int>(ws, pl->seg), 8LL * pl->n_items, st); pl->launches += 1; }
     return MAF_OK;
 }
 
