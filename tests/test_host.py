@@ -134,3 +134,34 @@ def test_run_merge_logic_on_cpu(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert "OK" in out.stdout
+
+
+def test_ctypes_table_matches_header_arity_and_pointer_positions():
+    """Every prototype in include/maf.h against the ctypes table: same number of parameters, pointers where the header has
+    pointers, 64-bit integers where it has int64_t / size_t / long long, double / float where it says so."""
+    from modular_audio_pipeline_b200 import _capi
+    header = open(os.path.join(ROOT, "include", "maf.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = re.findall(r"\b(?:const\s+char\s*\*|int64_t|int|void|size_t|long\s+long)\s+(maf_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) >= 30
+    seen = set()
+    for name, params in protos:
+        seen.add(name)
+        params = " ".join(params.split())
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        res, args = _capi.SYMBOLS[name]
+        assert len(plist) == len(args), f"{name}: header has {len(plist)} parameters, ctypes table {len(args)}"
+        for p, a in zip(plist, args):
+            if "*" in p:
+                assert a not in (C.c_int, C.c_int32, C.c_int64, C.c_size_t, C.c_float, C.c_double), f"{name}: '{p}' is a pointer, table has {a}"
+            elif re.search(r"\b(int64_t|size_t|long long)\b", p):
+                assert a in (C.c_int64, C.c_size_t, C.c_longlong), f"{name}: '{p}' vs {a}"
+            elif re.search(r"\bdouble\b", p):
+                assert a is C.c_double, f"{name}: '{p}' vs {a}"
+            elif re.search(r"\bfloat\b", p):
+                assert a is C.c_float, f"{name}: '{p}' vs {a}"
+            elif re.search(r"\b(int32_t|int)\b", p):
+                assert a in (C.c_int32, C.c_int), f"{name}: '{p}' vs {a}"
+            else:
+                raise AssertionError(f"{name}: unrecognised parameter '{p}'")
+    assert seen == set(_capi.SYMBOLS), sorted(set(_capi.SYMBOLS) ^ seen)
