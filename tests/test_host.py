@@ -165,3 +165,30 @@ def test_ctypes_table_matches_header_arity_and_pointer_positions():
             else:
                 raise AssertionError(f"{name}: unrecognised parameter '{p}'")
     assert seen == set(_capi.SYMBOLS), sorted(set(_capi.SYMBOLS) ^ seen)
+
+
+def test_ctypes_structs_match_header_layout(tmp_path):
+    """sizeof / offsetof of the three structs in include/maf.h as the C compiler lays them out, against the ctypes mirrors."""
+    from modular_audio_pipeline_b200 import _capi
+    structs = {"maf_item_desc": _capi.ItemDesc, "maf_params": _capi.Params, "maf_layout": _capi.Layout}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "maf.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        src.append(f'printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            src.append(f'printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    src += ['return 0; }']
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(c)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        cname, field, val = line.split()
+        cls = structs[cname]
+        if field == "size":
+            assert C.sizeof(cls) == int(val), line
+        else:
+            assert getattr(cls, field).offset == int(val), line
+        seen += 1
+    assert seen == sum(len(cls._fields_) + 1 for cls in structs.values())
