@@ -192,3 +192,33 @@ def test_ctypes_structs_match_header_layout(tmp_path):
             assert getattr(cls, field).offset == int(val), line
         seen += 1
     assert seen == sum(len(cls._fields_) + 1 for cls in structs.values())
+
+
+def test_property_wavio_roundtrip_and_wave_module_interop(tmp_path):
+    """hypothesis: write_pcm16 -> read_pcm16 is the identity, the wave module reads our files and we read the wave module's,
+    for arbitrary lengths (incl. 0 and odd), rates and contents."""
+    import wave
+    import numpy as np
+    import torch
+    pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+    from modular_audio_pipeline_b200 import wavio
+    pool = wavio.PinnedPool(pinned=False)
+
+    @settings(max_examples=60, deadline=None)
+    @given(n=st.integers(0, 5000), rate=st.sampled_from([8000, 16000, 22050, 44100, 48000]), seed=st.integers(0, 2 ** 31 - 1))
+    def check(n, rate, seed):
+        x = torch.from_numpy(np.random.default_rng(seed).integers(-32768, 32768, size=n).astype(np.int16))
+        p = str(tmp_path / "rt.wav")
+        wavio.write_pcm16(p, x, rate)
+        y, info = wavio.read_pcm16(p, pool)
+        assert torch.equal(x, y) and (info.rate, info.channels, info.sampwidth, info.nframes) == (rate, 1, 2, n)
+        with wave.open(p, "rb") as wf:
+            assert (wf.getframerate(), wf.getnchannels(), wf.getsampwidth(), wf.getnframes()) == (rate, 1, 2, n)
+            assert wf.readframes(n) == x.numpy().tobytes()
+        i2 = wavio.read_info(p)
+        out = torch.empty(n, dtype=torch.int16)
+        wavio.read_data_into(p, i2, out)
+        assert torch.equal(out, x)
+
+    check()

@@ -138,3 +138,33 @@ def test_front_door_restatement_matches_stdlib_audioop():
     y = audioop.ratecv(y, 2, 2, 48000, 16000, None)[0]
     y = np.frombuffer(audioop.tomono(y, 2, 0.5, 0.5), dtype=np.int16)
     assert np.array_equal(y, O.front_door(x, 2, 48000, 16000))
+
+
+def test_property_ratecv_closed_form_any_rate_pair():
+    """hypothesis: the closed-form ratecv (output m reads input ceil(m in / out)) equals audioop.ratecv for arbitrary rate
+    pairs -- up- and down-sampling, coprime rates -- lengths and channel counts; audioop.mul's floor for arbitrary factors."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        audioop = pytest.importorskip("audioop")
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(ch=st.sampled_from([1, 2]), a=st.integers(4000, 96000), b=st.sampled_from([8000, 16000, 22050, 44100, 48000, 7919]),
+           n=st.integers(1, 3000), seed=st.integers(0, 2 ** 31 - 1))
+    def check_ratecv(ch, a, b, n, seed):
+        x = np.random.default_rng(seed).integers(-32768, 32768, size=n * ch).astype(np.int16)
+        want = np.frombuffer(audioop.ratecv(x.tobytes(), 2, ch, a, b, None)[0], dtype=np.int16)
+        assert np.array_equal(want, O.ratecv(x, ch, a, b))
+
+    @settings(max_examples=150, deadline=None)
+    @given(peak=st.integers(1, 32767), n=st.integers(1, 2000), seed=st.integers(0, 2 ** 31 - 1))
+    def check_mul(peak, n, seed):
+        x = np.random.default_rng(seed).integers(-peak, peak + 1, size=n).astype(np.int16)
+        x[0] = peak
+        want = np.frombuffer(audioop.mul(x.tobytes(), 2, O.peak_normalize_factor(audioop.max(x.tobytes(), 2))), dtype=np.int16)
+        assert np.array_equal(want, O.peak_normalize(x))
+
+    check_ratecv()
+    check_mul()
