@@ -146,14 +146,35 @@ int64_t maf_plan_den_offset(const maf_plan* plan, int32_t item);   /* int16 inde
 int maf_sharded_clip_contrib(maf_plan* plan, const int16_t* pcm_dev, const int32_t* seg_dev, int32_t* clip_dev, void* stream);
 int maf_set_noise_clips_dev(maf_plan* plan, const int32_t* seg_dev, void* stream);
 
-/* ---- silence detection for AudioPreprocessor.remove_silence / detect_silence_segments (preprocessor.py:290-405 ->
- * pydub.silence.detect_silence over audioop.rms).  maf_ms_energy: exact integer sum of squares per millisecond
- * bucket [int(i r), int((i+1) r)), r = rate / 1000, and of the whole recording (seg.rms -> seg.dBFS).
- * maf_silence_flags: flags[i] = (audioop.rms of the window_ms buckets starting at i) <= thresh, i < n_starts. */
+/* ---- normalize_loudness on MULTI-CHANNEL 16-bit input (preprocessor.py:256-261: the reference averages the channels in float32,
+ * `samples.reshape(-1, channels).mean(axis=1)`, meters the mean and writes the gained MONO signal, :271-282).  pcm_dev holds
+ * n_frames interleaved frames of `channels` int16 samples; out_dev receives n_frames mono samples -- untouched when the
+ * recording is too quiet (*lufs_dev non-finite or < -70: the reference returns its input path, :267-269).
+ * workspace_dev: maf_loudness_interleaved_ws() bytes. */
+int64_t maf_loudness_interleaved_ws(int64_t n_frames, int32_t sample_rate);
+int maf_loudness_interleaved(maf_ctx* ctx, const int16_t* pcm_dev, int64_t n_frames, int32_t channels, int32_t sample_rate,
+                             float target_lufs, void* workspace_dev, int16_t* out_dev, double* lufs_dev, void* stream);
+
+/* ---- silence detection / removal for AudioPreprocessor.remove_silence and detect_silence_segments (preprocessor.py:290-405 ->
+ * pydub.silence.detect_silence / detect_nonsilent over audioop.rms, then the margin / cross-fade / position loop :330-358 over
+ * AudioSegment.__getitem__ / append).
+ * maf_ms_energy: exact integer sum of squares per millisecond bucket [int(i r), int((i+1) r)), r = rate / 1000, and of the
+ * whole recording (seg.rms -> seg.dBFS; the host turns that ONE scalar into the threshold with the reference's float64
+ * expression, `db_to_float(seg.dBFS - offset) * 32768`).
+ * maf_silence: everything else on the device -- window RMS from prefix sums, pydub's merge of silent starts into ranges,
+ * detect_nonsilent's complement, the reference's margin / min(20, dur // 4) ms cross-fade / running-position bookkeeping,
+ * and (out_dev != NULL) the compaction of the kept chunks with pydub's cross-fade into out_dev (at most out_cap frames).
+ * The workspace starts with the result block the host copies back (maf_silence_layout: result_bytes):
+ *   int32 status (0 ok, 1 no non-silent segment -> the reference returns its input, 2 pydub ValueError "crossfade is longer than
+ *   the original AudioSegment", 3 pydub TooManyMissingFrames), int32 n_silent, int32 n_chunks, int32 j_base, int64 n_out, int64 n_ms,
+ *   then at off_silent int32[max_ranges][2] silent ranges in ms, at off_map int32[max_ranges + 1][4] per kept chunk
+ *   (processed_start_ms, duration_ms, original_start_ms, original_end_ms) -> TimestampMapping (protocols.py:35-41). */
 int maf_ms_energy(maf_ctx* ctx, const int16_t* pcm_dev, int64_t n, int32_t sample_rate, int64_t n_ms, uint64_t* bucket_dev,
                   uint64_t* total_dev, void* stream);
-int maf_silence_flags(maf_ctx* ctx, const uint64_t* bucket_dev, int64_t n, int32_t sample_rate, int64_t n_starts, int32_t window_ms,
-                      double thresh, uint8_t* flags_dev, void* stream);
+int maf_silence_layout(int64_t n_ms, int32_t window_ms, int64_t* ws_bytes, int64_t* result_bytes, int64_t* max_ranges,
+                       int64_t* off_silent, int64_t* off_map);
+int maf_silence(maf_ctx* ctx, const int16_t* pcm_dev, int64_t n, int32_t sample_rate, const uint64_t* bucket_dev, int64_t n_ms,
+                int32_t window_ms, double thresh, int32_t margin_ms, void* workspace_dev, int16_t* out_dev, int64_t out_cap, void* stream);
 
 /* ---- front door of AudioPreprocessor.normalize_audio for 16-bit input that is not yet mono at the target rate
  * (preprocessor.py:227-233: pydub normalize(seg).set_frame_rate(sr).set_channels(1) -> audioop.max / mul / ratecv /

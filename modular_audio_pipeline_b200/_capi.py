@@ -69,7 +69,11 @@ SYMBOLS = {
     "maf_plan_buffer": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "maf_plan_den_offset": (C.c_int64, [_P, C.c_int32]),
     "maf_ms_energy": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int64, _P, _P, _P]),
-    "maf_silence_flags": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_double, _P, _P]),
+    "maf_loudness_interleaved_ws": (C.c_int64, [C.c_int64, C.c_int32]),
+    "maf_loudness_interleaved": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_float, _P, _P, _P, _P]),
+    "maf_silence_layout": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "maf_silence": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_int32, C.c_double, C.c_int32, _P, _P, C.c_int64, _P]),
     "maf_sharded_clip_contrib": (C.c_int, [_P, _P, _P, _P, _P]),
     "maf_set_noise_clips_dev": (C.c_int, [_P, _P, _P]),
     "maf_front_door_out_len": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),

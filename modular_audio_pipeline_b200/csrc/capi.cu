@@ -195,6 +195,7 @@ struct maf_plan {
     long long max_own = 0;
     int frame_len = 0, frame_hop = 0, tile_len = 0, n_slices = 1;
     bool too_short = false, sharded = false, have_noise_clips = false;
+    std::string clip_err;              // why the stationary denoise of this plan must fail (noise clip <= noverlap)
     double target_peak = 0.0, inv_block = 0.0;
     KWeight kw{};
     SmoothTaps taps{};
@@ -207,7 +208,7 @@ struct maf_plan {
     // optional per-stage CUDA-event timing (maf_plan_profile): ring of event sets, one per maf_process call
     int prof_steps = 0; long long prof_calls = 0; std::vector<cudaEvent_t> prof_ev;   // [(step, boundary)]
     // host-path staging (maf_process_host)
-    cudaStream_t hstream = nullptr;
+    cudaStream_t hstream = nullptr; bool host_ready = false;
     void* h_ws = nullptr; int16_t* h_pcm = nullptr; int16_t* h_out = nullptr; float* h_mel = nullptr; double* h_lufs = nullptr;
     int* h_clip = nullptr; int16_t* h_noise = nullptr; long long h_noise_cap = 0;
 };
@@ -308,9 +309,23 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
     if (p.n_mels != 0 && p.n_mels != 80 && p.n_mels != 128) return fail(MAF_ERR_INVALID, "n_mels must be 0, 80 or 128");
     if (p.n_mels && p.sample_rate != 16000) return fail(MAF_ERR_UNSUPPORTED, "Whisper log-mel is defined at 16 kHz");
     if (p.mel_padding < 0 || (p.mel_padding > 0 && p.mel_padding < W_HOP)) return fail(MAF_ERR_INVALID, "mel_padding must be 0 or >= 160");
+    // several kernels index items with blockIdx.y (noise statistics, frame statistics, the peak scan)
+    if (n_items > 65535) return fail(MAF_ERR_UNSUPPORTED, "more than 65535 items in one plan: split the batch");
     CU(cudaSetDevice(ctx->device));
     maf_plan* pl = new maf_plan();
     pl->ctx = ctx; pl->device = ctx->device; pl->p = p; pl->n_items = n_items;
+    if (p.stationary && !p.external_noise) {
+        // scipy.signal.stft raises "noverlap must be less than nperseg" for a noise clip of <= 768 samples (preprocessor.py:207-208
+        // turns that into AudioProcessingError); the shortest run the detector accepts is 100 ms, the fallback clip is
+        // noise_sample_duration_s long (preprocessor.py:189-197).  Reported by the denoise entry points, not here: the peak /
+        // loudness / log-mel stages of such a plan are fine.
+        const int hop_s0 = (int)(p.sample_rate * 0.010);
+        const int min_run = hop_s0 > 0 ? (int)ceil(0.1 * p.sample_rate / hop_s0) * hop_s0 : 0;
+        if (p.auto_detect_noise && min_run <= NFFT - HOP)
+            pl->clip_err = "sample rate too low: a detected 100 ms noise clip would be <= 768 samples (scipy.signal.stft: noverlap must be less than nperseg)";
+        else if ((long long)(p.sample_rate * (double)p.noise_sample_duration_s) <= NFFT - HOP)
+            pl->clip_err = "noise_sample_duration_s gives a noise clip of <= 768 samples (scipy.signal.stft: noverlap must be less than nperseg)";
+    }
     if (design_taps(p.sample_rate, pl->taps)) { delete pl; return fail(MAF_ERR_UNSUPPORTED, "smoothing taps exceed kernel limits for this rate"); }
     design_kweight((double)p.sample_rate, pl->kw);
     {   // noisereduce non-stationary defaults: time_constant_s = 2.0, thresh_n_mult_nonstationary = 2, sigmoid_slope_nonstationary = 10
@@ -337,6 +352,8 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
         if (d.own_len <= 0 || d.n_global <= 0 || d.origin < 0 || d.origin + d.own_len > d.buf_len || d.g0 < 0 || d.g0 + d.own_len > d.n_global)
             { delete pl; return fail(MAF_ERR_INVALID, "maf_plan_create: inconsistent item descriptor"); }
         if (d.n_global > 2000000000LL) { delete pl; return fail(MAF_ERR_UNSUPPORTED, "recordings above 2^31 samples are not supported"); }
+        if (p.stationary && !p.external_noise && d.n_global <= NFFT - HOP && pl->clip_err.empty())
+            pl->clip_err = "recording of <= 768 samples: its noise clip is shorter than noverlap (scipy.signal.stft: noverlap must be less than nperseg)";
         if (!whole) {
             pl->sharded = true;
             if (d.n_global <= CHUNK || d.g0 % CHUNK != 0 || (d.g0 + d.own_len != d.n_global && d.own_len % CHUNK != 0))
@@ -388,7 +405,7 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
             long long len = std::min<long long>((long long)(p.sample_rate * (double)p.noise_sample_duration_s), d.n_global);
             if (len > CHUNK) len = CHUNK;
             fixed[i].start = it.pcm_off + d.origin - d.g0;       // absolute offset in the pcm array of global sample 0
-            fixed[i].len = (int)len; fixed[i].n_frames = (int)(len / HOP) + 1;
+            fixed[i].len = (int)len; fixed[i].n_frames = clip_frames((int)len);
             pl->seg_fixed.push_back(0); pl->seg_fixed.push_back((int)len);
         }
         // loudness tiles / blocks
@@ -433,6 +450,12 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
     pl->n_chunks = (int)pl->chunks.size();
     pl->total_pcm = pcm_cur; pl->total_out = out_cur; pl->total_mel = mel_cur; pl->total_rows = row_cur;
     pl->total_sframes = sf_cur; pl->total_den = den_cur; pl->total_ktiles = kt_cur; pl->total_tiles = tile_cur;
+    {   // the persistent kernels index (chunk, tile) / (item, tile) units with 32-bit arithmetic
+        const long long st_units = (long long)pl->n_chunks * ((pl->max_chunk_frames + STFT_TILE - 1) / STFT_TILE);
+        const long long mel_units = (long long)n_items * std::max(1, pl->max_mel_tiles);
+        if (st_units >= (1LL << 31) - 4096 || mel_units >= (1LL << 31) - 4096)
+            { delete pl; return fail(MAF_ERR_UNSUPPORTED, "plan too large: more than 2^31 tiles, split the batch"); }
+    }
     pl->n_slices = std::max(1, std::min(32, (592 + n_items - 1) / n_items));
     // workspace layout
     long long cur = 0;
@@ -525,8 +548,10 @@ extern "C" int maf_set_noise_clips(maf_plan* pl, const int64_t* offsets, const i
     std::vector<Clip> cl(pl->n_items);
     for (int i = 0; i < pl->n_items; ++i) {
         if (lengths[i] <= 0 || offsets[i] < 0) return fail(MAF_ERR_INVALID, "maf_set_noise_clips: empty clip");
+        if (lengths[i] <= NFFT - HOP) return fail(MAF_ERR_INVALID, "maf_set_noise_clips: noise clip of <= 768 samples (scipy.signal.stft: noverlap must be less than nperseg)");
         const int len = std::min<int>(lengths[i], CHUNK);
-        cl[i].start = offsets[i]; cl[i].len = len; cl[i].n_frames = len / HOP + 1;
+        pl->seg_fixed[2 * i] = 0; pl->seg_fixed[2 * i + 1] = lengths[i];      // reported range: the whole external clip
+        cl[i].start = offsets[i]; cl[i].len = len; cl[i].n_frames = clip_frames(len);
     }
     CU(cudaMemcpy(pl->d_clips_fixed, cl.data(), sizeof(Clip) * pl->n_items, cudaMemcpyHostToDevice));
     pl->have_noise_clips = true;
@@ -608,6 +633,7 @@ static int run_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pc
                        cudaStream_t st) {
     const maf_params& p = pl->p;
     const int n = pl->n_items;
+    if (!pl->clip_err.empty()) return fail(MAF_ERR_INVALID, pl->clip_err);
     Clip* clips = ws_ptr<Clip>(ws, pl->clips);
     mark(pl, ST_BEGIN, st);
     launch_zero_bytes(ws_ptr<int>(ws, pl->peak), 4LL * n, st);
@@ -618,6 +644,7 @@ static int run_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pc
         if (p.external_noise) {
             if (!pl->have_noise_clips || !noise_pcm) return fail(MAF_ERR_INVALID, "external_noise set but no noise clips / noise pcm supplied");
             noise_src = noise_pcm; use_clips = pl->d_clips_fixed;
+            if (!pl->sharded) CU(cudaMemcpyAsync(ws_ptr<int>(ws, pl->seg), pl->seg_fixed.data(), 8LL * n, cudaMemcpyHostToDevice, st));
         } else if (p.auto_detect_noise) {
             if (pl->sharded) return fail(MAF_ERR_INVALID, "sharded plans need external noise clips (run maf_frame_stats / maf_select_clip first)");
             launch_frame_stats(pcm, pl->d_items, n, pl->max_sframes, pl->frame_len, pl->frame_hop, ws_ptr<float>(ws, pl->E), ws_ptr<int>(ws, pl->ZC), st);
@@ -653,9 +680,10 @@ static int run_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pc
         pl->launches += 2;                                   // + the nmax clear inside launch_noise_threshold
     }
     mark(pl, ST_NOISE, st);
-    launch_stft(pcm, pl->d_items, pl->d_chunks, pl->n_chunks, pl->max_chunk_frames, pl->ctx->c, p.stationary, ws_ptr<float>(ws, pl->T2),
-                ws_ptr<float>(ws, pl->T2hi), ws_ptr<c32>(ws, pl->S), ws_ptr<uint32_t>(ws, pl->bits), ws_ptr<uint8_t>(ws, pl->rowflag),
-                (const NsParams*)pl->d_ns, ws_ptr<float>(ws, pl->P), ws_ptr<float>(ws, pl->Q), st);
+    if (launch_stft(pcm, pl->d_items, pl->d_chunks, pl->n_chunks, pl->max_chunk_frames, pl->ctx->c, p.stationary, ws_ptr<float>(ws, pl->T2),
+                    ws_ptr<float>(ws, pl->T2hi), ws_ptr<c32>(ws, pl->S), ws_ptr<uint32_t>(ws, pl->bits), ws_ptr<uint8_t>(ws, pl->rowflag),
+                    (const NsParams*)pl->d_ns, ws_ptr<float>(ws, pl->P), ws_ptr<float>(ws, pl->Q), st))
+        return fail(MAF_ERR_UNSUPPORTED, "STFT tile count exceeds 2^31");
     pl->launches += 1;
     mark(pl, ST_STFT, st);
     if (!p.stationary) {
@@ -710,8 +738,9 @@ static int run_logmel(maf_plan* pl, const int16_t* src, const Item* items, int p
         const int nt = n * std::max(1, pl->max_mel_tiles);
         fill_int_kernel<<<(nt + 255) / 256, 256, 0, st>>>(ws_ptr<int>(ws, pl->mel_tmin), nt, (int)0x7fffffff);
     }
-    launch_logmel(src, items, n, pl->max_mel_tiles, pl->ctx->c, pick_mel(pl), pl->p.mel_padding, peak_normalize,
-                  ws_ptr<PeakNorm>(ws, pl->pnorm), gates, out16, mel, ws_ptr<int>(ws, pl->mel_max), ws_ptr<int>(ws, pl->mel_tmin), st);
+    if (launch_logmel(src, items, n, pl->max_mel_tiles, pl->ctx->c, pick_mel(pl), pl->p.mel_padding, peak_normalize,
+                      ws_ptr<PeakNorm>(ws, pl->pnorm), gates, out16, mel, ws_ptr<int>(ws, pl->mel_max), ws_ptr<int>(ws, pl->mel_tmin), st))
+        return fail(MAF_ERR_UNSUPPORTED, "log-mel tile count exceeds 2^31");
     pl->launches += 3;
     mark(pl, ST_LOGMEL, st);
     if (finalize) {
@@ -757,15 +786,23 @@ extern "C" int maf_process_host(maf_plan* pl, const int16_t* pcm_host, const int
                                 float* mel_host, double* lufs_host, int32_t* clip_host) {
     if (!pl || !pcm_host || !out_host) return fail(MAF_ERR_INVALID, "maf_process_host: NULL argument");
     CU(cudaSetDevice(pl->ctx->device));
-    if (!pl->hstream) {
-        CU(cudaStreamCreateWithFlags(&pl->hstream, cudaStreamNonBlocking));
-        CU(cudaMalloc(&pl->h_ws, pl->ws_bytes));
-        CU(cudaMalloc((void**)&pl->h_pcm, 2 * std::max<long long>(8, pl->total_pcm)));
-        CU(cudaMalloc((void**)&pl->h_out, 2 * std::max<long long>(8, pl->total_out)));
-        CU(cudaMalloc((void**)&pl->h_mel, 4 * std::max<long long>(4, pl->total_mel)));
-        CU(cudaMalloc((void**)&pl->h_lufs, 8LL * pl->n_items));
-        CU(cudaMalloc((void**)&pl->h_clip, 8LL * pl->n_items));
-        CU(cudaMemsetAsync(pl->h_clip, 0, 8LL * pl->n_items, pl->hstream));
+    if (!pl->host_ready) {
+        // allocate into locals; the plan takes them only when every allocation succeeded (a partial set would leave NULL
+        // buffers behind a "ready" flag and fault on the next call)
+        cudaStream_t hs = nullptr; void* bufs[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        const size_t sizes[6] = {(size_t)pl->ws_bytes, (size_t)(2 * std::max<long long>(8, pl->total_pcm)), (size_t)(2 * std::max<long long>(8, pl->total_out)),
+                                 (size_t)(4 * std::max<long long>(4, pl->total_mel)), (size_t)(8LL * pl->n_items), (size_t)(8LL * pl->n_items)};
+        cudaError_t e = cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking);
+        for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaMalloc(&bufs[i], sizes[i]);
+        if (e == cudaSuccess) e = cudaMemsetAsync(bufs[5], 0, sizes[5], hs);
+        if (e != cudaSuccess) {
+            for (void* b : bufs) if (b) cudaFree(b);
+            if (hs) cudaStreamDestroy(hs);
+            return fail(MAF_ERR_CUDA, std::string("maf_process_host: staging allocation failed: ") + cudaGetErrorString(e));
+        }
+        pl->hstream = hs; pl->h_ws = bufs[0]; pl->h_pcm = (int16_t*)bufs[1]; pl->h_out = (int16_t*)bufs[2]; pl->h_mel = (float*)bufs[3];
+        pl->h_lufs = (double*)bufs[4]; pl->h_clip = (int*)bufs[5];
+        pl->host_ready = true;
     }
     cudaStream_t st = pl->hstream;
     if (noise_host && noise_len > 0) {
@@ -829,6 +866,53 @@ extern "C" int maf_loudness(maf_plan* pl, const int16_t* pcm, void* ws, int16_t*
     return MAF_OK;
 }
 
+// Multi-channel normalize_loudness (preprocessor.py:256-282): channel mean in float32, BS.1770 loudness of the mean, gain /
+// limiter / int16 of the MONO signal.  Workspace layout: Item | Gate | absmax, peak | sub-block energies | float mean.
+static long long loud_il_layout(long long n_frames, int tile_len, long long* o_gate, long long* o_max, long long* o_sub, long long* o_m) {
+    const long long n_tiles = (n_frames + tile_len - 1) / tile_len;
+    long long cur = align_up((long long)sizeof(Item), 256);
+    *o_gate = cur; cur = align_up(cur + (long long)sizeof(Gate), 256);
+    *o_max = cur; cur = align_up(cur + 16, 256);
+    *o_sub = cur; cur = align_up(cur + 8 * std::max<long long>(1, n_tiles), 256);
+    *o_m = cur; cur = align_up(cur + 4 * n_frames, 256);
+    return cur;
+}
+
+extern "C" int64_t maf_loudness_interleaved_ws(int64_t n_frames, int32_t sample_rate) {
+    if (n_frames <= 0 || sample_rate <= 0) return 0;
+    long long a, b, c, d;
+    return loud_il_layout(n_frames, (int)(0.4 * 0.25 * (double)sample_rate), &a, &b, &c, &d);
+}
+
+extern "C" int maf_loudness_interleaved(maf_ctx* ctx, const int16_t* pcm, int64_t n_frames, int32_t channels, int32_t sr, float target_lufs,
+                                        void* ws, int16_t* out, double* lufs, void* stream) {
+    if (!ctx || !pcm || !ws || !out || n_frames <= 0) return fail(MAF_ERR_INVALID, "maf_loudness_interleaved: bad argument");
+    if (channels < 1 || channels > 128) return fail(MAF_ERR_UNSUPPORTED, "maf_loudness_interleaved: 1..128 channels");
+    if (sr < 4000 || sr > 96000) return fail(MAF_ERR_INVALID, "sample_rate out of range");
+    if ((double)n_frames < 0.4 * (double)sr) return fail(MAF_ERR_TOO_SHORT, "Audio must have length greater than the block size");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tile_len = (int)(0.4 * 0.25 * (double)sr);
+    const double T = (double)n_frames / (double)sr;
+    const long long nb = (long long)(nearbyint((T - 0.4) / (0.4 * 0.25)) + 1);
+    for (long long j = 0; j < nb; ++j) {                           // the sub-block decomposition needs pyloudnorm's bounds to be regular
+        const long long l = (long long)(0.4 * (j * 0.25) * (double)sr), u = (long long)(0.4 * (j * 0.25 + 1) * (double)sr);
+        if (l != j * tile_len || u != l + 4LL * tile_len) return fail(MAF_ERR_UNSUPPORTED, "irregular loudness block grid at this rate / length");
+    }
+    long long o_gate, o_max, o_sub, o_m;
+    loud_il_layout(n_frames, tile_len, &o_gate, &o_max, &o_sub, &o_m);
+    unsigned char* b = static_cast<unsigned char*>(ws);
+    Item it{};
+    it.ktile_first = 0; it.n_ktiles = (int)((n_frames + tile_len - 1) / tile_len); it.n_blocks = (int)nb;
+    CU(cudaMemcpyAsync(b, &it, sizeof(it), cudaMemcpyHostToDevice, st));
+    KWeight kw; design_kweight((double)sr, kw);
+    launch_loudness_interleaved(pcm, n_frames, channels, tile_len, it.n_ktiles, (const Item*)b, kw, 1.0 / (0.4 * (double)sr), (double)target_lufs,
+                                (float*)(b + o_m), (double*)(b + o_sub), (unsigned*)(b + o_max), (int*)(b + o_max + 4), (Gate*)(b + o_gate), out, st);
+    if (lufs) gather_lufs_kernel<<<1, 32, 0, st>>>((const Gate*)(b + o_gate), 1, lufs);
+    CU(cudaGetLastError());
+    return MAF_OK;
+}
+
 extern "C" int maf_logmel(maf_plan* pl, const int16_t* pcm, void* ws, float* mel, void* stream) {
     if (!pl || !pcm || !ws || !mel) return fail(MAF_ERR_INVALID, "maf_logmel: NULL argument");
     if (!pl->p.n_mels) return fail(MAF_ERR_INVALID, "maf_logmel: plan was created with n_mels = 0");
@@ -882,7 +966,7 @@ __global__ void clip_contrib_kernel(const int16_t* __restrict__ pcm, Item it, co
 }
 __global__ void set_clip_dev_kernel(const int* __restrict__ seg, Clip* __restrict__ clips) {
     long long len = (long long)seg[1] - seg[0]; if (len > CHUNK) len = CHUNK; if (len < 0) len = 0;
-    Clip c; c.start = 0; c.len = (int)len; c.n_frames = (int)(len / HOP) + 1;
+    Clip c; c.start = 0; c.len = (int)len; c.n_frames = clip_frames((int)len);
     clips[0] = c;
 }
 
@@ -957,11 +1041,26 @@ extern "C" int maf_ms_energy(maf_ctx* ctx, const int16_t* pcm, int64_t n, int32_
     return MAF_OK;
 }
 
-extern "C" int maf_silence_flags(maf_ctx* ctx, const uint64_t* bucket, int64_t n, int32_t sr, int64_t n_starts, int32_t window_ms,
-                                 double thresh, uint8_t* flags, void* stream) {
-    if (!ctx || !bucket || !flags || window_ms <= 0) return fail(MAF_ERR_INVALID, "maf_silence_flags: bad argument");
+extern "C" int maf_silence_layout(int64_t n_ms, int32_t window_ms, int64_t* ws_bytes, int64_t* result_bytes, int64_t* max_ranges,
+                                  int64_t* off_silent, int64_t* off_map) {
+    if (n_ms < 0 || window_ms <= 0) return fail(MAF_ERR_INVALID, "maf_silence_layout: bad argument");
+    size_t a = 0, b = 0; long long cap = 0, os = 0, om = 0;
+    silence_layout(n_ms, window_ms, &a, &b, &cap, &os, &om);
+    if (ws_bytes) *ws_bytes = (int64_t)a;
+    if (result_bytes) *result_bytes = (int64_t)b;
+    if (max_ranges) *max_ranges = cap;
+    if (off_silent) *off_silent = os;
+    if (off_map) *off_map = om;
+    return MAF_OK;
+}
+
+extern "C" int maf_silence(maf_ctx* ctx, const int16_t* pcm, int64_t n, int32_t sr, const uint64_t* bucket, int64_t n_ms, int32_t window_ms,
+                           double thresh, int32_t margin_ms, void* ws, int16_t* out, int64_t out_cap, void* stream) {
+    if (!ctx || !pcm || !bucket || !ws || n <= 0 || n_ms < 0 || window_ms <= 0 || margin_ms < 0 || sr <= 0)
+        return fail(MAF_ERR_INVALID, "maf_silence: bad argument");
+    if (n_ms > 2000000000LL) return fail(MAF_ERR_UNSUPPORTED, "maf_silence: recording longer than 2^31 ms");
     CU(cudaSetDevice(ctx->device));
-    launch_silence_flags((const unsigned long long*)bucket, n, sr, n_starts, window_ms, thresh, flags, (cudaStream_t)stream);
+    launch_silence(pcm, n, sr, (const unsigned long long*)bucket, n_ms, window_ms, thresh, margin_ms, ws, out, out_cap, (cudaStream_t)stream);
     CU(cudaGetLastError());
     return MAF_OK;
 }

@@ -248,19 +248,20 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
   }
 }
 
-void launch_logmel(const int16_t* den16, const Item* items, int n_items, int max_tiles, const Consts& c,
+int launch_logmel(const int16_t* den16, const Item* items, int n_items, int max_tiles, const Consts& c,
                    const MelBank& mel, int padding, int peak_normalize, const PeakNorm* pnorm,
                    const Gate* gates, int16_t* out16, float* mel_out, int* mel_max, int* tile_min, cudaStream_t st) {
-    if (n_items <= 0) return;
+    if (n_items <= 0) return 0;
     cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOGMEL_SMEM);
     if (max_tiles < 1) max_tiles = 1;
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     const long long total = (long long)n_items * max_tiles;
-    if (total >= (1LL << 31) - 4096) return;                       // unreachable for plans that fit in memory
+    if (total >= (1LL << 31) - 4096) return -1;                    // maf_plan_create rejects such plans; never skip work silently
     const int grid = (int)(total < 2LL * n_sm ? total : 2LL * n_sm);
     logmel_kernel<<<grid, 256, LOGMEL_SMEM, st>>>(den16, items, n_items, max_tiles, c, mel, padding, peak_normalize, pnorm, gates, out16,
                                                   mel_out, mel_max, tile_min);
+    return 0;
 }
 
 // whisper.audio.log_mel_spectrogram: log_spec = maximum(log_spec, log_spec.max() - 8.0); (log_spec + 4.0) / 4.0.

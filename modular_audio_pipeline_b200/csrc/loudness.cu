@@ -9,6 +9,7 @@
 //   gate_kernel            400 ms / 75 % overlap block energies = 4 consecutive sub-blocks, absolute (-70 LUFS) and
 //                          relative (-10 LU) gates, integrated loudness, float32 gain and limiter peak per recording.
 //   apply_gain_kernel      gain / limiter / int16 truncation when the log-mel kernel (which fuses it) is not run.
+#include <algorithm>
 #include "maf_common.cuh"
 
 namespace maf {
@@ -349,6 +350,83 @@ void launch_apply_gain(const int16_t* den16, const Item* items, int n_items, lon
         apply_gain_kernel<<<grid, 256, 0, st>>>(den16, items + y0, peak_normalize, pnorm ? pnorm + y0 : nullptr,
                                                 gates ? gates + y0 : nullptr, use_gate, out16);
     }
+}
+
+// ---- multi-channel input to normalize_loudness (preprocessor.py:256-261) ------------------------------------------------------
+// The reference averages the channels in float32 before metering (`samples.reshape(-1, channels).mean(axis=1)`) and writes the
+// gained MONO signal.  The mean is not int16-representable, so this path works on float32 samples: it is outside the pipeline's
+// own call chain (normalize_audio has already produced mono) and kept simple rather than fast -- one thread per 100 ms
+// sub-block runs the two K-weighting biquads from a zero state two sub-blocks earlier (the slowest mode, the double pole of the
+// 38 Hz high pass, has decayed by e^-47 by then), float64 recurrences with lfilter's float32 round trip between the stages.
+__global__ void __launch_bounds__(256) downmix_mean_kernel(const int16_t* __restrict__ x, long long n_frames, int channels,
+                                                           float* __restrict__ m, unsigned* __restrict__ absmax) {
+    float pk = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_frames; i += (long long)gridDim.x * blockDim.x) {
+        int sum = 0;                                                // sum of <= 128 int16 / 32768 values is exact in float32 in any order
+        for (int c = 0; c < channels; ++c) sum += x[i * channels + c];
+        const float v = __fdiv_rn(__fmul_rn((float)sum, 1.0f / 32768.0f), (float)channels);
+        m[i] = v;
+        pk = fmaxf(pk, fabsf(v));
+    }
+    for (int o = 16; o > 0; o >>= 1) pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, o));
+    if ((threadIdx.x & 31) == 0 && pk > 0.f) atomicMax(absmax, __float_as_uint(pk));
+}
+
+__global__ void __launch_bounds__(128) kweight_float_kernel(const float* __restrict__ m, long long n, int tile_len, int n_tiles, KWeight kw,
+                                                            double* __restrict__ sub_energy) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const long long own0 = (long long)t * tile_len;
+    long long i0 = own0 - 2LL * tile_len; if (i0 < 0) i0 = 0;
+    long long i1 = own0 + tile_len; if (i1 > n) i1 = n;
+    double z10 = 0.0, z11 = 0.0, z20 = 0.0, z21 = 0.0, acc = 0.0;
+    for (long long i = i0; i < i1; ++i) {
+        const double xv = (double)m[i];
+        const double y1d = kw.b1[0] * xv + z10;                    // scipy.signal.lfilter: direct form II transposed
+        z10 = kw.b1[1] * xv - kw.a1[1] * y1d + z11;
+        z11 = kw.b1[2] * xv - kw.a1[2] * y1d;
+        const double y1 = (double)(float)y1d;                      // float32 storage between the stages
+        const double y2d = kw.b2[0] * y1 + z20;
+        z20 = kw.b2[1] * y1 - kw.a2[1] * y2d + z21;
+        z21 = kw.b2[2] * y1 - kw.a2[2] * y2d;
+        const float y2 = (float)y2d;
+        if (i >= own0) acc += (double)__fmul_rn(y2, y2);
+    }
+    sub_energy[t] = acc;
+}
+
+__global__ void gate_float_fix_kernel(Gate* __restrict__ g, const unsigned* __restrict__ absmax) {
+    Gate gt = *g;
+    if (gt.applied) {
+        gt.limp = __fmul_rn(gt.gain, __uint_as_float(*absmax));     // max |gain * x| = gain * max |x| in float32 (monotone rounding)
+        gt.lim = gt.limp > 1.0f ? 1 : 0;
+        *g = gt;
+    }
+}
+
+// normalized = gain * samples; if peak > 1: normalized /= peak; clip(normalized * 32768, -32768, 32767).astype(int16)
+__global__ void __launch_bounds__(256) apply_gain_float_kernel(const float* __restrict__ m, long long n, const Gate* __restrict__ g,
+                                                               int16_t* __restrict__ out) {
+    const Gate gt = *g;
+    if (!gt.applied) return;                                        // the reference returns its input path: nothing is written
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v = __fmul_rn(gt.gain, m[i]);
+        if (gt.lim) v = __fdiv_rn(v, gt.limp);
+        v = fminf(fmaxf(__fmul_rn(v, 32768.0f), -32768.0f), 32767.0f);
+        out[i] = (int16_t)(int)v;
+    }
+}
+
+void launch_loudness_interleaved(const int16_t* x, long long n_frames, int channels, int tile_len, int n_tiles, const Item* item_dev,
+                                 const KWeight& kw, double inv_block, double target_lufs, float* m, double* sub, unsigned* absmax,
+                                 int* peak_dummy, Gate* gate, int16_t* out, cudaStream_t st) {
+    launch_zero_bytes(absmax, 16, st);                             // absmax + the unused integer peak the gate kernel reads
+    const int grid = (int)std::min<long long>(2368, (n_frames + 255) / 256);
+    downmix_mean_kernel<<<grid, 256, 0, st>>>(x, n_frames, channels, m, absmax);
+    kweight_float_kernel<<<(n_tiles + 127) / 128, 128, 0, st>>>(m, n_frames, tile_len, n_tiles, kw, sub);
+    launch_gate(sub, item_dev, 1, inv_block, target_lufs, peak_dummy, gate, st);
+    gate_float_fix_kernel<<<1, 1, 0, st>>>(gate, absmax);
+    apply_gain_float_kernel<<<grid, 256, 0, st>>>(m, n_frames, gate, out);
 }
 
 }  // namespace maf

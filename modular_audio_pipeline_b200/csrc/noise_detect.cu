@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_clip_kernel(const float* _
         Clip c;
         c.start = it.pcm_off + gs - it.g0 + it.origin;
         long long len = ge - gs; if (len > CHUNK) len = CHUNK;
-        c.len = (int)len; c.n_frames = (int)(len / HOP) + 1;
+        c.len = (int)len; c.n_frames = clip_frames((int)len);
         clips[item] = c;
         if (seg_out) { seg_out[2 * item] = (int)gs; seg_out[2 * item + 1] = (int)ge; }
     }
@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_clip_grid_kernel(const flo
             Clip c;
             c.start = it.pcm_off + gs - it.g0 + it.origin;
             long long len2 = ge - gs; if (len2 > CHUNK) len2 = CHUNK;
-            c.len = (int)len2; c.n_frames = (int)(len2 / HOP) + 1;
+            c.len = (int)len2; c.n_frames = clip_frames((int)len2);
             *clip_out = c;
             if (seg_out) { seg_out[0] = (int)gs; seg_out[1] = (int)ge; }
         }

@@ -264,15 +264,15 @@ __global__ void __launch_bounds__(32 * STFT_WARPS, 2) stft1024_kernel(const int1
     }
 }
 
-void launch_stft(const int16_t* pcm, const Item* items, const Chunk* chunks, int n_chunks, int max_frames,
+int launch_stft(const int16_t* pcm, const Item* items, const Chunk* chunks, int n_chunks, int max_frames,
                  const Consts& c, int stationary, const float* T2, const float* T2hi, c32* S, uint32_t* bits,
                  uint8_t* rowflag, const NsParams* ns, float* P, float* Q, cudaStream_t st) {
-    if (n_chunks <= 0) return;
+    if (n_chunks <= 0) return 0;
     const int tiles = (max_frames + STFT_TILE - 1) / STFT_TILE;
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     const long long total = (long long)n_chunks * tiles;
-    if (total >= (1LL << 31) - 4096) return;                      // unreachable for plans that fit in memory
+    if (total >= (1LL << 31) - 4096) return -1;                   // maf_plan_create rejects such plans; never skip work silently
     const int grid = (int)std::min<long long>(total, 2LL * n_sm);
     cudaFuncSetAttribute(stft1024_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STFT_SMEM);
     cudaFuncSetAttribute(stft1024_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STFT_SMEM);
@@ -280,6 +280,7 @@ void launch_stft(const int16_t* pcm, const Item* items, const Chunk* chunks, int
         stft1024_kernel<true><<<grid, 32 * STFT_WARPS, STFT_SMEM, st>>>(pcm, items, chunks, n_chunks, tiles, c, T2, T2hi, S, bits, rowflag, nullptr, nullptr, nullptr);
     else
         stft1024_kernel<false><<<grid, 32 * STFT_WARPS, STFT_SMEM, st>>>(pcm, items, chunks, n_chunks, tiles, c, nullptr, nullptr, S, nullptr, nullptr, ns, P, Q);
+    return 0;
 }
 
 // ============================================================================================================
@@ -300,7 +301,14 @@ __global__ void __launch_bounds__(256) noise_pass_kernel(const int16_t* __restri
     const int item = blockIdx.y;
     const Clip cl = clips[item];
     const int tid = threadIdx.x, g = tid >> 6, t = tid & 63;
-    for (int i = tid; i < NFFT; i += 256) win[i] = cs.win1024[i];
+    // a clip shorter than n_fft gets scipy's shrunken window / hop (see clip_nperseg in maf_common.cuh)
+    const int np = clip_nperseg(cl.len), step = np - (NFFT - HOP), half = np / 2;
+    if (np == NFFT) {
+        for (int i = tid; i < NFFT; i += 256) win[i] = cs.win1024[i];
+    } else {
+        for (int i = tid; i < NFFT; i += 256)                         // periodic Hann(np) / sum, zero-padded to n_fft at the end
+            win[i] = i < np ? (float)((0.5 - 0.5 * cospi(2.0 * (double)i / (double)np)) / (0.5 * (double)np)) : 0.f;
+    }
     for (int i = tid; i < FFT512_TW1; i += 256) tw1[i] = cs.tw1[i];
     if (tid < FFT512_TW2) tw2[tid] = cs.tw2[tid];
     for (int i = tid; i < 257; i += 256) tw1024[i] = cs.tw1024[i];
@@ -338,9 +346,9 @@ __global__ void __launch_bounds__(256) noise_pass_kernel(const int16_t* __restri
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
             const int n = t + 64 * m;
-            const long long i = (long long)f * HOP - NFFT / 2 + 2 * n;     // clip-relative sample index
+            const long long i = (long long)f * step - half + 2 * n;        // clip-relative sample index
             float a = 0.f, b = 0.f;
-            if (active) {
+            if (active && 2 * n < np) {                                    // (the window is zero beyond np anyway; never read past the segment)
                 if (i >= 0 && i < cl.len) a = (float)base[i];
                 if (i + 1 >= 0 && i + 1 < cl.len) b = (float)base[i + 1];
             }

@@ -61,9 +61,9 @@ class FrontEnd:
         pydub normalize -> set_frame_rate -> set_channels(1), i.e. audioop.max / mul / ratecv / tomono): interleaved int16
         CUDA tensor in, mono int16 CUDA tensor at ``out_rate`` out."""
         if pcm.dtype != torch.int16 or not pcm.is_cuda or not pcm.is_contiguous():
-            raise MafError("front_door: contiguous int16 CUDA tensor expected")
+            raise MafError(_capi.MAF_ERR_INVALID, "front_door: contiguous int16 CUDA tensor expected")
         if channels not in (1, 2) or pcm.numel() % channels:
-            raise MafError("front_door: 1 or 2 interleaved channels expected")
+            raise MafError(_capi.MAF_ERR_UNSUPPORTED, "front_door: 1 or 2 interleaved channels expected")
         n_in = pcm.numel() // channels
         n_out = int(self._lib.maf_front_door_out_len(n_in, int(in_rate), int(out_rate)))
         out = torch.empty(max(n_out, 1), dtype=torch.int16, device=self.device)
@@ -71,8 +71,7 @@ class FrontEnd:
             with torch.cuda.device(self.device):
                 rc = self._lib.maf_front_door(self._h, pcm.data_ptr(), n_in, int(channels), int(in_rate), int(out_rate), int(bool(normalize)),
                                               out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
-            if rc:
-                raise MafError(self._lib.maf_last_error().decode())
+            check(rc)
         return out[:n_out]
 
     def mel_windows(self, mel: torch.Tensor, seeks: torch.Tensor, lens: Optional[torch.Tensor], window_frames: int,
@@ -80,14 +79,81 @@ class FrontEnd:
         """Encoder windows ``out[w, m, f] = mel[m, seeks[w] + f]`` (zero past ``lens[w]`` / the end of the recording), float32 or
         float16 -- maf_mel_windows in include/maf.h; the whisper seek loop behind transcriber.py:229-238."""
         n = int(seeks.numel())
+        if mel.dtype != torch.float32 or mel.dim() != 2 or not mel.is_cuda or not mel.is_contiguous():
+            raise MafError(_capi.MAF_ERR_INVALID, "mel_windows: contiguous float32 [n_mels, frames] CUDA tensor expected")
+        if seeks.dtype != torch.int32 or not seeks.is_cuda or (lens is not None and (lens.dtype != torch.int32 or not lens.is_cuda)):
+            raise MafError(_capi.MAF_ERR_INVALID, "mel_windows: seeks / lens must be int32 CUDA tensors")
+        if lens is not None and int(lens.numel()) != n:
+            raise MafError(_capi.MAF_ERR_INVALID, "mel_windows: seeks and lens differ in length")
+        if out.dtype not in (torch.float16, torch.float32) or not out.is_cuda or out.numel() != n * int(mel.shape[0]) * int(window_frames):
+            raise MafError(_capi.MAF_ERR_INVALID, "mel_windows: out must be a float16 / float32 CUDA tensor [n_windows, n_mels, window_frames]")
         with torch.cuda.device(self.device):
             rc = self._lib.maf_mel_windows(self._h, mel.data_ptr(), int(mel.shape[0]), int(mel.shape[1]), seeks.data_ptr(),
                                            lens.data_ptr() if lens is not None else None, n, int(window_frames),
                                            int(out.dtype == torch.float16), out.data_ptr(),
                                            torch.cuda.current_stream(self.device).cuda_stream)
-        if rc:
-            raise MafError(self._lib.maf_last_error().decode())
+        check(rc)
         return out
+
+    def loudness_interleaved(self, pcm: torch.Tensor, channels: int, sample_rate: int, target_lufs: float = -16.0):
+        """normalize_loudness on multi-channel 16-bit input (preprocessor.py:256-282): float32 channel mean -> BS.1770 loudness ->
+        gain / limiter / int16 of the MONO signal.  Returns ``(mono int16 CUDA tensor, float64 LUFS CUDA tensor [1])``; the
+        output is meaningless when the LUFS is non-finite or below -70 (the reference returns its input path then)."""
+        if pcm.dtype != torch.int16 or not pcm.is_cuda or not pcm.is_contiguous() or channels < 1 or pcm.numel() % channels:
+            raise MafError(_capi.MAF_ERR_INVALID, "loudness_interleaved: contiguous int16 CUDA tensor of whole frames expected")
+        n = pcm.numel() // channels
+        dev = self.device
+        ws = torch.empty(max(256, int(self._lib.maf_loudness_interleaved_ws(n, int(sample_rate)))), dtype=torch.uint8, device=dev)
+        out = torch.empty(max(n, 1), dtype=torch.int16, device=dev)
+        lufs = torch.empty(1, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            check(self._lib.maf_loudness_interleaved(self._h, pcm.data_ptr(), n, int(channels), int(sample_rate), float(target_lufs),
+                                                     ws.data_ptr(), out.data_ptr(), lufs.data_ptr(),
+                                                     torch.cuda.current_stream(dev).cuda_stream))
+        return out[:n], lufs
+
+    def silence(self, x: torch.Tensor, sr: int, window_ms: int, offset_db: float, margin_ms: int = 0, compact: bool = False):
+        """pydub's silence scan and (``compact``) the reference's remove_silence loop (preprocessor.py:311-358) on device-resident
+        int16 samples -- maf_ms_energy + maf_silence in include/maf.h.  Returns ``(status, silent_ranges_ms [K, 2] int32 numpy,
+        chunk_table [C, 4] int32 numpy (processed_start_ms, duration_ms, original_start_ms, original_end_ms), cleaned int16 CUDA
+        tensor or None)``.  Two scalar-sized device->host reads: the recording's sum of squares (the threshold is the reference's
+        own float64 expression, evaluated on the host) and the result block; no per-millisecond data leaves the device."""
+        import math
+        import numpy as np
+        if x.dtype != torch.int16 or not x.is_cuda or not x.is_contiguous() or x.dim() != 1:
+            raise MafError(_capi.MAF_ERR_INVALID, "silence: contiguous 1-D int16 CUDA tensor expected")
+        n = int(x.numel())
+        if n == 0:
+            raise MafError(_capi.MAF_ERR_INVALID, "silence: empty recording")
+        n_ms = int(round(1000 * (float(n) / sr)))                  # pydub len(seg)
+        dev = self.device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        bucket = torch.empty(n_ms + 1, dtype=torch.int64, device=dev)
+        total = torch.empty(1, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            check(self._lib.maf_ms_energy(self._h, x.data_ptr(), n, int(sr), n_ms, bucket.data_ptr(), total.data_ptr(), st))
+        rms = int(math.sqrt(total.item() / n))                    # audioop.rms truncates
+        dbfs = 20 * math.log10(rms / 32768.0) if rms > 0 else -float("inf")   # seg.dBFS
+        thresh = (10 ** ((dbfs - offset_db) / 20)) * 32768.0      # db_to_float(silence_thresh) * seg.max_possible_amplitude
+        ws_b, res_b, cap, off_s, off_m = (C.c_int64() for _ in range(5))
+        check(self._lib.maf_silence_layout(n_ms, int(window_ms), C.byref(ws_b), C.byref(res_b), C.byref(cap), C.byref(off_s), C.byref(off_m)))
+        ws = torch.empty(ws_b.value, dtype=torch.uint8, device=dev)
+        out = None
+        out_cap = 0
+        if compact:
+            # chunks overlap only when the margins exceed the silent gap between them; + the sub-millisecond padding per chunk
+            per_chunk = max(0, 2 * int(margin_ms) - int(window_ms)) + 3
+            out_cap = n + cap.value * per_chunk * int(math.ceil(sr / 1000.0))
+            out = torch.empty(out_cap, dtype=torch.int16, device=dev)
+        with torch.cuda.device(dev):
+            check(self._lib.maf_silence(self._h, x.data_ptr(), n, int(sr), bucket.data_ptr(), n_ms, int(window_ms), C.c_double(thresh),
+                                        int(margin_ms), ws.data_ptr(), None if out is None else out.data_ptr(), out_cap, st))
+        res = ws[: res_b.value].cpu().numpy()                      # header + range / mapping tables (a few KB)
+        status, n_silent, n_chunks, _j_base = (int(v) for v in res[:16].view(np.int32))
+        n_out = int(res[16:24].view(np.int64)[0])
+        silent = res[off_s.value: off_s.value + 8 * n_silent].view(np.int32).reshape(-1, 2).copy()
+        table = res[off_m.value: off_m.value + 16 * n_chunks].view(np.int32).reshape(-1, 4).copy()
+        return status, silent, table, (out[:n_out] if out is not None and status == 0 else None)
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -248,10 +314,17 @@ class Plan:
         if pcm.dtype != torch.int16 or pcm.device != self.device or pcm.numel() < self.total_pcm or not pcm.is_contiguous():
             raise ValueError("expected a contiguous int16 tensor in the plan's layout on the plan's device")
 
-    def denoise(self, pcm: torch.Tensor, noise_pcm: Optional[torch.Tensor] = None, want_float: bool = False):
+    def out_buffer(self) -> torch.Tensor:
+        """A fresh int16 device buffer in the plan's OUTPUT layout.  For a single-item plan the output layout equals the input
+        layout, so a stage's output buffer can be handed to the next stage as is (no re-pack)."""
+        return torch.empty(max(self.total_out, 8), dtype=torch.int16, device=self.device)
+
+    def denoise(self, pcm: torch.Tensor, noise_pcm: Optional[torch.Tensor] = None, want_float: bool = False,
+                out: Optional[torch.Tensor] = None):
         self._check_in(pcm)
         dev = self.device
-        out = torch.empty(max(self.total_out, 8), dtype=torch.int16, device=dev)
+        if out is None:
+            out = self.out_buffer()
         outf = torch.empty(max(self.total_out, 8), dtype=torch.float32, device=dev) if want_float else None
         clip = torch.zeros(self.n_items, 2, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
@@ -259,16 +332,18 @@ class Plan:
                                         _ptr(clip), self._stream()))
         return self.split_out(out), (self.split_out(outf) if want_float else None), clip
 
-    def peak_normalize(self, pcm: torch.Tensor) -> List[torch.Tensor]:
+    def peak_normalize(self, pcm: torch.Tensor, out: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
         self._check_in(pcm)
-        out = torch.empty(max(self.total_out, 8), dtype=torch.int16, device=self.device)
+        if out is None:
+            out = self.out_buffer()
         with torch.cuda.device(self.device):
             check(self._lib.maf_peak_normalize(self._h, _ptr(pcm), _ptr(self.workspace), _ptr(out), self._stream()))
         return self.split_out(out)
 
-    def loudness(self, pcm: torch.Tensor):
+    def loudness(self, pcm: torch.Tensor, out: Optional[torch.Tensor] = None):
         self._check_in(pcm)
-        out = torch.empty(max(self.total_out, 8), dtype=torch.int16, device=self.device)
+        if out is None:
+            out = self.out_buffer()
         lufs = torch.empty(self.n_items, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
             check(self._lib.maf_loudness(self._h, _ptr(pcm), _ptr(self.workspace), _ptr(out), _ptr(lufs), self._stream()))

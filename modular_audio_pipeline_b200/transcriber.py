@@ -21,7 +21,7 @@ import torch
 
 from .frontend import FrontEnd
 
-__all__ = ["GpuLogMelFrontEnd", "GpuFrontEndTranscriber"]
+__all__ = ["GpuLogMelFrontEnd", "GpuFeatureExtractor", "GpuFrontEndTranscriber"]
 
 N_SAMPLES = 480000      # whisper.audio.N_SAMPLES: 30 s at 16 kHz
 N_FRAMES = 3000
@@ -64,10 +64,10 @@ class GpuLogMelFrontEnd:
         return mel if device is None else mel.to(device)
 
     def feature_extractor(self, waveform, padding: int = 160, chunk_length: Optional[int] = None) -> np.ndarray:
+        """faster-whisper ``FeatureExtractor.__call__`` arithmetic: log-mel of the WHOLE waveform plus ``padding`` zeros.
+        ``chunk_length`` does not touch the samples there -- it only re-sizes the extractor's ``n_samples`` /
+        ``nb_max_frames`` bookkeeping, which ``GpuFeatureExtractor`` (below) mirrors on the wrapped object."""
         x = self._to_int16(waveform)
-        if chunk_length is not None:                     # faster-whisper pads / trims to chunk_length seconds first
-            n = chunk_length * 16000
-            x = x[:n] if x.numel() >= n else torch.nn.functional.pad(x, (0, n - x.numel()))
         return self.log_mel_spectrogram(x, self.n_mels, padding).cpu().numpy()
 
     n_mels = 80
@@ -102,6 +102,39 @@ class GpuLogMelFrontEnd:
         return out
 
 
+class GpuFeatureExtractor:
+    """Stands in for ``WhisperModel.feature_extractor`` (faster-whisper ``feature_extractor.FeatureExtractor``): the CALL runs the
+    GPU log-mel, every attribute -- ``sampling_rate``, ``hop_length``, ``chunk_length``, ``n_samples``, ``nb_max_frames``,
+    ``time_per_frame``, ``mel_filters``, ``n_fft``, which ``WhisperModel.transcribe`` / ``generate_segments`` read off the
+    object -- is the wrapped extractor's own, reads and writes alike."""
+
+    def __init__(self, original, front_end: "GpuLogMelFrontEnd"):
+        object.__setattr__(self, "_original", original)
+        object.__setattr__(self, "_front_end", front_end)
+
+    def __getattr__(self, name):                       # only reached for names not found on the proxy itself
+        return getattr(object.__getattribute__(self, "_original"), name)
+
+    def __setattr__(self, name, value):
+        setattr(object.__getattribute__(self, "_original"), name, value)
+
+    @property
+    def n_mels(self) -> int:
+        mf = getattr(self._original, "mel_filters", None)
+        return int(mf.shape[0]) if mf is not None else 80
+
+    def __call__(self, waveform, padding: int = 160, chunk_length: Optional[int] = None) -> np.ndarray:
+        o = self._original
+        if chunk_length is not None:                   # FeatureExtractor.__call__: bookkeeping only, the waveform is not trimmed
+            sr = int(getattr(o, "sampling_rate", 16000))
+            hop = int(getattr(o, "hop_length", 160))
+            o.n_samples = chunk_length * sr
+            o.nb_max_frames = o.n_samples // hop
+        fe = self._front_end
+        x = fe._to_int16(waveform)
+        return fe.log_mel_spectrogram(x, self.n_mels, padding).cpu().numpy()
+
+
 class GpuFrontEndTranscriber:
     """TranscriberProtocol (protocols.py:119-133) adapter: same transcriber, GPU log-mel front-end."""
 
@@ -109,6 +142,8 @@ class GpuFrontEndTranscriber:
         self.inner = inner
         self.front_end = front_end or GpuLogMelFrontEnd()
         self._installed = False
+        self._saved_extractor = None                   # (model, original feature_extractor)
+        self._saved_whisper = None                     # (module, original log_mel_spectrogram)
 
     def is_loaded(self) -> bool:
         return self.inner.is_loaded()
@@ -117,23 +152,40 @@ class GpuFrontEndTranscriber:
         self.inner.load_model()
         self._install()
 
+    def _uninstall(self) -> None:
+        if self._saved_extractor is not None:
+            model, orig = self._saved_extractor
+            if isinstance(getattr(model, "feature_extractor", None), GpuFeatureExtractor):
+                model.feature_extractor = orig
+            self._saved_extractor = None
+        if self._saved_whisper is not None:
+            mod, orig = self._saved_whisper
+            if getattr(mod, "log_mel_spectrogram", None) == self.front_end.log_mel_spectrogram:
+                mod.log_mel_spectrogram = orig
+            self._saved_whisper = None
+        self._installed = False
+
     def unload_model(self) -> None:
+        """pipeline.py:532-533 calls this from cleanup(): the model and the process-wide whisper module get their own
+        front-end back before the wrapped transcriber drops the model."""
+        self._uninstall()
         if hasattr(self.inner, "unload_model"):
             self.inner.unload_model()
-        self._installed = False
 
     def _install(self) -> None:
         if self._installed:
             return
         model = getattr(self.inner, "_model", None)
-        if model is not None and hasattr(model, "feature_extractor"):          # faster-whisper WhisperModel
-            fe = self.front_end
-            fe.n_mels = getattr(getattr(model, "feature_extractor"), "mel_filters", np.zeros((80, 201))).shape[0]
-            model.feature_extractor = fe.feature_extractor
+        ext = getattr(model, "feature_extractor", None) if model is not None else None
+        if ext is not None and not isinstance(ext, GpuFeatureExtractor):       # faster-whisper WhisperModel
+            model.feature_extractor = GpuFeatureExtractor(ext, self.front_end)
+            self._saved_extractor = (model, ext)
             self._installed = True
-        mod = sys.modules.get("whisper.transcribe")                            # openai-whisper: patch the name it calls
+        mod = sys.modules.get("whisper.transcribe")                            # openai-whisper: patch the name transcribe() calls
         if mod is not None and hasattr(mod, "log_mel_spectrogram"):
-            mod.log_mel_spectrogram = self.front_end.log_mel_spectrogram
+            if mod.log_mel_spectrogram != self.front_end.log_mel_spectrogram:
+                self._saved_whisper = (mod, mod.log_mel_spectrogram)
+                mod.log_mel_spectrogram = self.front_end.log_mel_spectrogram
             self._installed = True
 
     def transcribe(self, input_wav: str) -> Dict[str, Any]:

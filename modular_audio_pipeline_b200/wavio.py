@@ -258,4 +258,109 @@ class WavPrefetcher:
             yield item
 
 
-__all__ = ["WavInfo", "PinnedPool", "read_header", "read_info", "read_data_into", "read_pcm16", "pcm16_header", "write_pcm16", "WavPrefetcher"]
+def batch_offsets(lengths: List[int], align: int = 8) -> Tuple[List[int], int]:
+    """Item offsets of a batch plan's PCM layout (every item starts on a multiple of `align` samples; include/maf.h
+    maf_layout.pcm_off) and the total length."""
+    offs, cur = [], 0
+    for n in lengths:
+        offs.append(cur)
+        cur += (int(n) + align - 1) // align * align
+    return offs, cur
+
+
+class BatchReader:
+    """File batches for the fused batch entry (``GpuAudioPreprocessor.process_files``): batch k + 1 is read on background threads
+    -- every file's data chunk straight into a page-locked batch buffer at its plan offset, files of a batch in parallel --
+    while the caller uploads / processes batch k.  Iterating yields ``(paths, infos, lengths, offsets, pinned int16 tensor)``;
+    a yielded buffer is overwritten once the caller asks for the batch after the next one (``depth`` buffers), so the caller
+    must have finished its H2D copy by then."""
+
+    def __init__(self, paths: Iterable[str], batch_size: int, depth: int = 2, pinned: Optional[bool] = None):
+        self.paths = list(paths)
+        self.batch_size = max(1, int(batch_size))
+        self.depth = max(2, depth)
+        self._pools = [PinnedPool(pinned) for _ in range(self.depth)]
+        self._groups = [self.paths[i:i + self.batch_size] for i in range(0, len(self.paths), self.batch_size)]
+        self._driver = ThreadPoolExecutor(1, thread_name_prefix="wavio-batch")
+        # per-file level; the per-chunk level of large files (_chunked) has its own pool, so the two never wait on each other
+        self._files = ThreadPoolExecutor(_PAR_THREADS, thread_name_prefix="wavio-file")
+        self._futs: dict = {}
+
+    def _read(self, k: int):
+        group = self._groups[k]
+        pool = self._files
+        infos = list(pool.map(read_info, group))
+        for p, i in zip(group, infos):
+            if i.sampwidth != 2 or i.data_bytes % 2:
+                raise ValueError(f"{p}: {8 * i.sampwidth}-bit samples; 16-bit PCM expected")
+        lengths = [i.data_bytes // 2 for i in infos]
+        offs, total = batch_offsets(lengths)
+        buf = self._pools[k % self.depth].get(max(total, 8))
+        for o, n in zip(offs, lengths):                     # alignment gaps between the items
+            buf[o + n: o + (n + 7) // 8 * 8].zero_()
+        list(pool.map(lambda a: read_data_into(a[0], a[1], buf[a[2]: a[2] + a[3]]), zip(group, infos, offs, lengths)))
+        return group, infos, lengths, offs, buf[:max(total, 8)]
+
+    def _start(self, k: int) -> None:
+        if k < len(self._groups) and k not in self._futs:
+            self._futs[k] = self._driver.submit(self._read, k)
+
+    def __iter__(self):
+        try:
+            self._start(0)
+            for k in range(len(self._groups)):
+                self._start(k + 1)                          # into the other buffer while the caller works on batch k
+                yield self._futs.pop(k).result()
+        finally:
+            self._driver.shutdown(wait=True, cancel_futures=True)
+            self._files.shutdown(wait=True)
+
+
+class WriteJob:
+    """One queued ``write_pcm16``; ``wait()`` returns when the file is complete and re-raises the writer's error."""
+
+    def __init__(self, path: str):
+        self.path = path
+        self.done = threading.Event()
+        self.error: Optional[BaseException] = None
+        self.stat: Optional[Tuple[int, int]] = None        # (st_mtime_ns, st_size) of the finished file
+
+    def wait(self) -> "WriteJob":
+        self.done.wait()
+        if self.error is not None:
+            raise self.error
+        return self
+
+
+class WavWriter:
+    """Background WAV writes: a job waits for the device->host copy of its samples (a CUDA event), then writes the file with
+    ``write_pcm16`` (byte-identical to the ``wave`` module).  Different files are written in parallel (page-cache allocation
+    serialises per inode, not across files)."""
+
+    def __init__(self, threads: int = 4):
+        self._ex = ThreadPoolExecutor(max(1, threads), thread_name_prefix="wavio-write")
+
+    def submit(self, path: str, host: torch.Tensor, rate: int, event=None) -> WriteJob:
+        job = WriteJob(path)
+
+        def run():
+            try:
+                if event is not None:
+                    event.synchronize()
+                write_pcm16(path, host, rate)
+                st = os.stat(path)
+                job.stat = (st.st_mtime_ns, st.st_size)
+            except BaseException as e:                      # surfaced by job.wait()
+                job.error = e
+            finally:
+                job.done.set()
+
+        self._ex.submit(run)
+        return job
+
+    def close(self) -> None:
+        self._ex.shutdown(wait=True)
+
+
+__all__ = ["WavInfo", "PinnedPool", "read_header", "read_info", "read_data_into", "read_pcm16", "pcm16_header", "write_pcm16", "WavPrefetcher",
+           "batch_offsets", "BatchReader", "WriteJob", "WavWriter"]

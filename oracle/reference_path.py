@@ -314,9 +314,12 @@ def integrated_loudness(x: np.ndarray, rate: int) -> float:
     return gate_loudness(block_energies(x, rate))
 
 
-def normalize_loudness(pcm: np.ndarray, rate: int, target_lufs: float = -16.0):
-    """preprocessor.py:256-279, WAV-free.  Returns (int16 out, LUFS, applied) -- ``applied`` False = pass-through."""
+def normalize_loudness(pcm: np.ndarray, rate: int, target_lufs: float = -16.0, channels: int = 1):
+    """preprocessor.py:256-279, WAV-free.  Returns (int16 out, LUFS, applied) -- ``applied`` False = pass-through.
+    ``channels`` > 1: ``pcm`` is interleaved and the reference meters / writes the float32 channel mean (:260-261)."""
     samples = np.asarray(pcm, dtype=np.int16).astype(np.float32) / np.float32(32768.0)
+    if channels > 1:
+        samples = samples.reshape(-1, channels).mean(axis=1)
     loudness = integrated_loudness(samples, rate)
     if not np.isfinite(loudness) or loudness < -70:
         return np.asarray(pcm, dtype=np.int16).copy(), loudness, False
@@ -472,12 +475,25 @@ def _audioop():
 
 
 def _seg_len_ms(n: int, sr: int) -> int:
-    return int(round(1000.0 * n / sr))
+    """pydub ``len(seg)``: round(1000 * (frame_count / frame_rate)) -- Python's round-half-even on that float."""
+    return int(round(1000 * (float(n) / sr)))
 
 
 def _seg_slice(pcm: np.ndarray, sr: int, a_ms, b_ms) -> np.ndarray:
+    """pydub ``AudioSegment.__getitem__(slice)``: both ends clipped to len(seg) ms, positions converted with
+    int(ms * (frame_rate / 1000.0)); a slice that runs past the last frame (len(seg) rounds UP by a fraction of a millisecond)
+    is padded with silence to the expected length, unless more than 2 ms of frames are missing (TooManyMissingFrames)."""
     r = sr / 1000.0
-    return pcm[int(a_ms * r): int(b_ms * r)]
+    n_ms = _seg_len_ms(len(pcm), sr)
+    a_ms, b_ms = min(a_ms, n_ms), min(b_ms, n_ms)
+    f0, f1 = int(a_ms * r), int(b_ms * r)
+    data = pcm[f0:f1]
+    missing = max(f1 - f0, 0) - len(data)
+    if missing:
+        if missing > 2 * r:
+            raise ValueError("TooManyMissingFrames: you should never be filling in more than 2 ms with silence here")
+        data = np.concatenate([data, np.zeros(missing, dtype=np.int16)])
+    return data
 
 
 def detect_silence_ms(pcm: np.ndarray, sr: int, min_silence_len: int = 250, offset_db: float = 40.0):
@@ -555,11 +571,13 @@ def remove_silence(pcm: np.ndarray, sr: int, min_silence_len=250, offset_db=40.0
         chunk = _seg_slice(pcm, sr, s, e)
         dur = _seg_len_ms(len(chunk), sr)
         maps.append((pos / 1000.0, (pos + dur) / 1000.0, s / 1000.0, e / 1000.0))
-        if len(cleaned) == 0:
+        if _seg_len_ms(len(cleaned), sr) == 0:              # `if len(cleaned) == 0` is a length in ms
             cleaned = chunk.copy()
         else:
             cf = min(20, dur // 4)
             ncf = int(cf * (sr / 1000.0))
+            if cf > _seg_len_ms(len(cleaned), sr):          # AudioSegment.append -> preprocessor.py:374-375 AudioProcessingError
+                raise ValueError(f"Crossfade is longer than the original AudioSegment ({cf}ms > {_seg_len_ms(len(cleaned), sr)}ms)")
             if ncf > 0:
                 xf = _fade(cleaned[-ncf:], 0, -120)
                 fin = _fade(chunk[:ncf], -120, 0)

@@ -1,4 +1,5 @@
-"""Regenerate tests/golden/*.npz from the CPU oracle (run from the repo root: python tests/golden/make_golden.py).
+"""Regenerate tests/golden/*.npz from the CPU oracle (run from the repo root: python tests/golden/make_golden.py), or -- where
+the reference's libraries are installed -- from the libraries themselves (python tests/golden/make_golden.py --from-libraries).
 
 The reference ships no golden vectors and its numerical dependencies (noisereduce, pyloudnorm, pydub, whisper) are
 not installable offline, so these fixtures pin the ORACLE (oracle/reference_path.py), which restates those
@@ -19,13 +20,41 @@ from modular_audio_pipeline_b200.synth import speech_noise  # noqa: E402
 from oracle import reference_path as O  # noqa: E402
 
 
+def front_end_from_libraries(pcm, sr, stationary, n_mels):
+    """The same stage chain through the REAL libraries the reference calls (preprocessor.py:171-211, :227-233, :256-279,
+    transcriber.py:229-238) -- only possible where noisereduce / pyloudnorm / pydub / whisper are installed (they are not in
+    the build container; tests/test_pin_reference.py is the matching check)."""
+    import noisereduce as nr
+    import pydub
+    import pyloudnorm as pyln
+    import whisper
+    from pydub.effects import normalize
+    audio = pcm.astype(np.float32)
+    clip = O.choose_noise_clip(audio, sr)                                  # the reference's own code (:92-147, :179-197)
+    red = nr.reduce_noise(y=audio, sr=sr, y_noise=audio[clip[0]:clip[1]], prop_decrease=0.8, stationary=stationary)
+    den16 = red.astype(np.int16)
+    seg = pydub.AudioSegment(data=den16.tobytes(), sample_width=2, frame_rate=sr, channels=1)
+    norm16 = np.frombuffer(normalize(seg)._data, dtype=np.int16)
+    samples = norm16.astype(np.float32) / 32768.0
+    lufs = pyln.Meter(sr).integrated_loudness(samples)
+    y = pyln.normalize.loudness(samples, lufs, -16.0)
+    peak = np.abs(y).max()
+    if peak > 1.0:
+        y = y / peak
+    loud16 = np.clip(y * 32768, -32768, 32767).astype(np.int16)
+    mel = whisper.audio.log_mel_spectrogram(torch.from_numpy(loud16.astype(np.float32) / 32768.0), n_mels).numpy()
+    return {"denoised_f32": red, "denoised_i16": den16, "noise_clip": clip, "norm_i16": norm16, "loud_i16": loud16, "lufs": lufs,
+            "applied": True, "log_mel": mel}
+
+
 def main():
     import torchaudio
     from transformers import WhisperFeatureExtractor
     here = os.path.dirname(os.path.abspath(__file__))
+    from_libs = "--from-libraries" in sys.argv
     for name, seconds, seed, stationary, n_mels in [("clip_a", 3.0, 0, True, 80), ("clip_b", 3.0, 1, False, 128)]:
         pcm = speech_noise(seconds, seed, meeting=not stationary).numpy()
-        r = O.front_end(pcm, 16000, stationary, n_mels, 0)
+        r = front_end_from_libraries(pcm, 16000, stationary, n_mels) if from_libs else O.front_end(pcm, 16000, stationary, n_mels, 0)
         x = r["loud_i16"].astype(np.float32) / 32768.0
         fe = WhisperFeatureExtractor(feature_size=n_mels)
         hf = fe(x, sampling_rate=16000, return_tensors="np", padding="max_length")["input_features"][0]

@@ -4,6 +4,7 @@ reference class, and (GPU) the path-in / path-out methods in the order AudioPipe
 import importlib.util
 import inspect
 import os
+from pathlib import Path
 import sys
 import types
 import wave
@@ -182,27 +183,102 @@ def test_normalize_audio_front_door_48k_stereo(tmp_path, frontend):
     assert d.max() <= 1 and np.mean(d != 0) <= 5e-3
 
 
-@pytest.mark.gpu
-def test_transcriber_adapter_with_fake_models(frontend):
-    from modular_audio_pipeline_b200.transcriber import GpuFrontEndTranscriber, GpuLogMelFrontEnd
-    x = speech_noise(3, 1)
+class _FwExtractor:
+    """The attribute surface of faster-whisper 1.2.1 ``feature_extractor.FeatureExtractor`` that ``WhisperModel.transcribe`` /
+    ``generate_segments`` read off ``model.feature_extractor`` (recalled from its published source; the package is not
+    installable here)."""
 
-    class FakeFW:                                     # faster-whisper style model
-        def __init__(self): self.feature_extractor = types.SimpleNamespace(mel_filters=np.zeros((128, 201)))
+    def __init__(self, n_mels=128):
+        self.n_fft, self.hop_length, self.chunk_length, self.sampling_rate = 400, 160, 30, 16000
+        self.n_samples = self.chunk_length * self.sampling_rate
+        self.nb_max_frames = self.n_samples // self.hop_length
+        self.time_per_frame = self.hop_length / self.sampling_rate
+        self.mel_filters = np.zeros((n_mels, 201), dtype=np.float32)
+
+    def __call__(self, waveform, padding=160, chunk_length=None):
+        raise AssertionError("the CPU extractor must not run once the GPU front-end is installed")
+
+
+class _FwModel:
+    """``WhisperModel.transcribe`` as far as the feature extractor is concerned: reads ``sampling_rate`` first, extracts features
+    of the WHOLE recording with ``chunk_length`` forwarded, then walks windows of ``nb_max_frames`` with ``time_per_frame``."""
+
+    def __init__(self, n_mels=128):
+        self.feature_extractor = _FwExtractor(n_mels)
+
+    def transcribe(self, audio, chunk_length=None):
+        sr = self.feature_extractor.sampling_rate
+        duration = audio.shape[0] / sr
+        feats = self.feature_extractor(audio, chunk_length=chunk_length)
+        nb = self.feature_extractor.nb_max_frames
+        content_frames = feats.shape[-1] - 1
+        windows = [(seek, min(nb, content_frames - seek)) for seek in range(0, content_frames, nb)]
+        return feats, {"duration": duration, "windows": windows, "time_per_frame": self.feature_extractor.time_per_frame,
+                       "n_samples": self.feature_extractor.n_samples}
+
+
+def _adapter_roundtrip(front_end, x_f32, want_fn):
+    from modular_audio_pipeline_b200.transcriber import GpuFeatureExtractor, GpuFrontEndTranscriber
 
     class Inner:
-        def __init__(self): self._model = FakeFW()
+        def __init__(self): self._model = _FwModel(128)
         def is_loaded(self): return True
         def load_model(self): pass
+        def unload_model(self): self.unloaded = True
         def transcribe(self, p):
-            feats = self._model.feature_extractor(x.numpy().astype(np.float32) / 32768.0, padding=160)
-            return {"segments": [], "features": feats}
-    t = GpuFrontEndTranscriber(Inner(), GpuLogMelFrontEnd())
-    feats = t.transcribe("x.wav")["features"]
-    want = O.log_mel_spectrogram(x.numpy().astype(np.float32) / 32768.0, 128, 160)
-    assert feats.shape == want.shape and np.abs(feats - want).max() <= 1e-4
+            feats, info = self._model.transcribe(x_f32, chunk_length=20)
+            return {"segments": [], "features": feats, "info": info}
+    inner = Inner()
+    original = inner._model.feature_extractor
+    mod = types.ModuleType("whisper.transcribe")
+    sentinel = mod.log_mel_spectrogram = lambda *a, **k: None
+    saved = sys.modules.get("whisper.transcribe")
+    sys.modules["whisper.transcribe"] = mod
+    try:
+        t = GpuFrontEndTranscriber(inner, front_end)
+        out = t.transcribe("x.wav")
+        assert isinstance(inner._model.feature_extractor, GpuFeatureExtractor)
+        assert mod.log_mel_spectrogram == front_end.log_mel_spectrogram
+        feats, info = out["features"], out["info"]
+        # chunk_length re-sizes the bookkeeping of the WRAPPED extractor, it does not trim the waveform
+        assert original.n_samples == 20 * 16000 and original.nb_max_frames == 2000 and info["n_samples"] == 320000
+        assert info["duration"] == x_f32.shape[0] / 16000 and info["time_per_frame"] == 0.01
+        want = want_fn(x_f32, 128, 160)
+        assert feats.shape == want.shape and feats.shape[-1] == (x_f32.shape[0] + 160) // 160
+        assert np.abs(feats - want).max() <= 1e-4
+        assert info["windows"][0] == (0, 2000) and len(info["windows"]) == -(-(feats.shape[-1] - 1) // 2000)
+        t.unload_model()                                  # pipeline.py:532-533
+        assert inner._model.feature_extractor is original and mod.log_mel_spectrogram is sentinel and inner.unloaded
+    finally:
+        if saved is None:
+            sys.modules.pop("whisper.transcribe", None)
+        else:
+            sys.modules["whisper.transcribe"] = saved
+
+
+def test_transcriber_adapter_keeps_the_extractor_surface_cpu():
+    """the adapter must not replace ``WhisperModel.feature_extractor`` by a bare callable -- transcribe() reads
+    ``sampling_rate`` / ``nb_max_frames`` / ``time_per_frame`` off it.  Host logic only: the log-mel comes from the oracle."""
+    class OracleFrontEnd:                                 # the two calls GpuFeatureExtractor makes on GpuLogMelFrontEnd
+        def _to_int16(self, w): return torch.from_numpy(np.round(np.asarray(w, dtype=np.float32) * 32768.0).astype(np.int16))
+        def log_mel_spectrogram(self, x, n_mels=80, padding=0, device=None):
+            return torch.from_numpy(O.log_mel_spectrogram(x.numpy().astype(np.float32) / 32768.0, n_mels, padding))
+    x = speech_noise(47.0, 1).numpy().astype(np.float32) / 32768.0
+    _adapter_roundtrip(OracleFrontEnd(), x, O.log_mel_spectrogram)
+
+
+@pytest.mark.gpu
+def test_transcriber_adapter_with_fake_models(frontend):
+    from modular_audio_pipeline_b200.transcriber import GpuLogMelFrontEnd
+    fe = GpuLogMelFrontEnd(frontend.device)
+    fe._fe = frontend
+    x = speech_noise(47.0, 1).numpy().astype(np.float32) / 32768.0
+    _adapter_roundtrip(fe, x, O.log_mel_spectrogram)
     m = GpuLogMelFrontEnd.pad_or_trim(torch.zeros(80, 10), 3000)
     assert m.shape == (80, 3000)
+    # openai-whisper's call: log_mel_spectrogram(audio, n_mels, padding=N_SAMPLES) on a path or an array
+    got = fe.log_mel_spectrogram(x, 80, 480000)
+    assert got.is_cuda and np.abs(got.cpu().numpy() - O.log_mel_spectrogram(x, 80, 480000)).max() <= 1e-4
 
 
 @pytest.mark.gpu
@@ -260,3 +336,157 @@ def test_process_files_equals_chained_protocol_calls(tmp_path, frontend):
     # no files written, no mel
     res = list(fused.process_files(paths[:1], n_mels=0, write_output=False))
     assert res[0][0] is None and res[0][2] is None
+
+
+# ---- remove_silence / detect_silence_segments on the device (csrc/silence.cu) against the oracle's per-millisecond loop over
+# ---- the real stdlib audioop ---------------------------------------------------------------------------------------------
+def _gappy(seconds, seed, sr=SR, n_gaps=6, sigma=0.0002):
+    """speech + faint noise with some stretches of near / exact digital silence of assorted lengths"""
+    x = speech_noise(seconds, seed, sr=sr, sigma=sigma).numpy().copy()
+    rng = np.random.default_rng(seed)
+    for k in range(n_gaps):
+        a = int(rng.integers(0, max(1, len(x) - sr)))
+        b = a + int(rng.integers(sr // 50, sr))
+        x[a:b] = 0 if k % 2 else (rng.integers(-2, 3, size=len(x[a:b]))).astype(np.int16)
+    return x
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seconds,seed,sr,win,off,margin", [
+    (20.0, 6, 16000, 250, 40.0, 100), (31.7, 7, 16000, 250, 40.0, 100), (12.3, 8, 16000, 100, 35.0, 30), (15.0, 9, 16000, 500, 40.0, 0),
+    (9.0, 10, 16000, 50, 30.0, 10), (14.0, 11, 8000, 250, 40.0, 100), (11.0, 12, 48000, 250, 40.0, 100), (10.0, 13, 16000, 250, 40.0, 200),
+    (6.0005, 14, 16000, 250, 40.0, 100), (7.00056, 15, 16000, 120, 38.0, 60)])
+def test_remove_silence_device_path_bit_exact(frontend, seconds, seed, sr, win, off, margin):
+    from modular_audio_pipeline_b200.silence import detect_silence_ms, remove_silence
+    from modular_audio_pipeline_b200._compat import TimestampMapping
+    pcm = _gappy(seconds, seed, sr=sr)
+    x = torch.from_numpy(pcm).to(frontend.device)
+    assert detect_silence_ms(frontend, x, sr, win, off) == O.detect_silence_ms(pcm, sr, win, off)
+    want = O.remove_silence(pcm, sr, win, off, margin)
+    got = remove_silence(frontend, x, sr, win, off, margin, True, TimestampMapping)
+    assert (want is None) == (got is None)
+    if want is not None:
+        assert len(want[1]) >= 2, "the case should exercise the cross-fade"
+        assert np.array_equal(got[0].cpu().numpy(), want[0])
+        assert [(m.processed_start, m.processed_end, m.original_start, m.original_end) for m in got[1]] == want[1]
+
+
+@pytest.mark.gpu
+def test_remove_silence_edge_cases(frontend):
+    from modular_audio_pipeline_b200.silence import detect_silence_ms, remove_silence
+    from modular_audio_pipeline_b200._compat import TimestampMapping
+    dev = frontend.device
+    # all silence -> the reference returns its input (:321-323)
+    z = torch.zeros(3 * SR, dtype=torch.int16, device=dev)
+    assert remove_silence(frontend, z, SR, 250, 40.0, 100, True, TimestampMapping) is None
+    assert detect_silence_ms(frontend, z, SR, 250, 40.0) == [[0, 3000]] == O.detect_silence_ms(np.zeros(3 * SR, dtype=np.int16), SR, 250, 40.0)
+    # no silence at all -> one chunk, the whole recording, one mapping
+    loud = speech_noise(4.0, 3, sigma=0.05).numpy()
+    got = remove_silence(frontend, torch.from_numpy(loud).to(dev), SR, 250, 40.0, 100, True, TimestampMapping)
+    want = O.remove_silence(loud, SR, 250, 40.0, 100)
+    assert np.array_equal(got[0].cpu().numpy(), want[0]) and len(got[1]) == len(want[1]) == 1
+    # shorter than the window: detect_silence returns [] -> everything is kept
+    short = speech_noise(0.2, 4).numpy()
+    got = remove_silence(frontend, torch.from_numpy(short).to(dev), SR, 250, 40.0, 100, False, TimestampMapping)
+    assert np.array_equal(got[0].cpu().numpy(), short) and got[1] == []
+    # silence at both ends, preserve_timestamps=False
+    pcm = _gappy(8.0, 21)
+    pcm[:SR] = 0; pcm[-SR:] = 0
+    got = remove_silence(frontend, torch.from_numpy(pcm).to(dev), SR, 250, 40.0, 100, False, TimestampMapping)
+    assert np.array_equal(got[0].cpu().numpy(), O.remove_silence(pcm, SR)[0]) and got[1] == []
+    # margin 0 with tiny kept ranges: chunks shorter than the next cross-fade; pydub raises when the cross-fade is longer than
+    # what has been accumulated -- both sides must agree on raise / no raise and on the samples
+    rng = np.random.default_rng(5)
+    for trial in range(6):
+        y = np.zeros(4 * SR, dtype=np.int16)
+        for k in range(8):
+            a = int(rng.integers(0, len(y) - 4000)); ln = int(rng.integers(16, 1500))
+            y[a:a + ln] = rng.integers(-9000, 9000, size=ln)
+        try:
+            want = O.remove_silence(y, SR, 40, 30.0, 0)
+            err = None
+        except ValueError as e:
+            want, err = None, e
+        if err is not None:
+            with pytest.raises(ValueError):
+                remove_silence(frontend, torch.from_numpy(y).to(dev), SR, 40, 30.0, 0, True, TimestampMapping)
+        else:
+            got = remove_silence(frontend, torch.from_numpy(y).to(dev), SR, 40, 30.0, 0, True, TimestampMapping)
+            assert (want is None) == (got is None)
+            if want is not None:
+                assert np.array_equal(got[0].cpu().numpy(), want[0])
+                assert [(m.processed_start, m.processed_end, m.original_start, m.original_end) for m in got[1]] == want[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_remove_silence_one_hour_properties(frontend):
+    """Full size (BASELINE config 2's recording): the oracle's per-millisecond Python loop needs minutes for an hour, so the device
+    path is checked through properties -- the mappings tile the output, every un-faded output sample is the input sample its
+    mapping names, and a one-minute excerpt equals the oracle bit for bit."""
+    from modular_audio_pipeline_b200.silence import remove_silence
+    from modular_audio_pipeline_b200._compat import TimestampMapping
+    pcm = speech_noise(3600.0, 1, sigma=0.0002)
+    x = pcm.to(frontend.device)
+    out, maps = remove_silence(frontend, x, SR, 250, 40.0, 100, True, TimestampMapping)
+    out = out.cpu().numpy()
+    src = pcm.numpy()
+    assert len(maps) > 1000 and out.size < src.size
+    ms = lambda t: int(round(t * 1000))
+    durs = [ms(m.processed_end) - ms(m.processed_start) for m in maps]
+    cfs = [0] + [min(20, d // 4) for d in durs[1:]]                  # cross-fade INTO chunk i (preprocessor.py:349-354)
+    for i, m in enumerate(maps):
+        assert ms(m.original_end) - ms(m.original_start) == durs[i]
+        nxt = cfs[i + 1] if i + 1 < len(maps) else 0
+        if i + 1 < len(maps):                                       # the reference records a position BEFORE it subtracts that chunk's cross-fade
+            assert ms(maps[i + 1].processed_start) == ms(m.processed_start) + durs[i] - cfs[i]
+        a = ms(m.processed_start) * 16                              # chunk i sits at processed_start - cf_i; its un-faded body is a verbatim copy
+        b = a + (durs[i] - cfs[i] - nxt) * 16
+        o = (ms(m.original_start) + cfs[i]) * 16
+        assert b > a and np.array_equal(out[a:b], src[o:o + (b - a)]), i
+    assert out.size == (ms(maps[-1].processed_start) + durs[-1] - cfs[-1]) * 16
+    one = src[: 60 * SR]
+    got = remove_silence(frontend, x[: 60 * SR].contiguous(), SR, 250, 40.0, 100, True, TimestampMapping)
+    want = O.remove_silence(one, SR)
+    assert np.array_equal(got[0].cpu().numpy(), want[0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("channels,sr,seconds", [(2, 16000, 12.0), (3, 16000, 5.0), (2, 48000, 6.0), (6, 8000, 9.0)])
+def test_loudness_multichannel_parity(frontend, channels, sr, seconds):
+    """normalize_loudness on interleaved multi-channel input (preprocessor.py:260-261: float32 channel mean)."""
+    chans = [speech_noise(seconds, 50 + c, sr=sr).numpy() for c in range(channels)]
+    inter = np.stack(chans, axis=1).reshape(-1)
+    out, lufs = frontend.loudness_interleaved(torch.from_numpy(inter).to(frontend.device), channels, sr)
+    want, want_lufs, applied = O.normalize_loudness(inter, sr, channels=channels)
+    assert applied and abs(lufs.item() - want_lufs) <= 1e-4
+    d = np.abs(out.cpu().numpy().astype(np.int32) - want.astype(np.int32))
+    assert out.numel() == len(chans[0]) and d.max() <= 1 and np.mean(d != 0) <= 5e-3
+    from modular_audio_pipeline_b200 import MafError
+    with pytest.raises(MafError):
+        frontend.loudness_interleaved(torch.zeros(2 * 1000, dtype=torch.int16, device=frontend.device), 2, sr)   # < 0.4 s
+
+
+@pytest.mark.gpu
+def test_protocol_path_reuses_plans_and_residents(tmp_path, frontend):
+    """The Protocol chain on the real FrontEnd: one plan for the three stage calls of a recording, stage outputs handed over on the
+    device (no file is re-read), deferred writes complete at remove_silence, prefetch() makes later calls start from HBM."""
+    from modular_audio_pipeline_b200.preprocessor import GpuAudioPreprocessor
+    paths = []
+    for i in range(3):
+        p = tmp_path / f"f{i}.wav"
+        _write_wav(p, speech_noise(6.0 + i, 30 + i, sigma=0.001).numpy())
+        paths.append(str(p))
+    sync = GpuAudioPreprocessor(SR, str(tmp_path / "s"), device=frontend.device)
+    lazy = GpuAudioPreprocessor(SR, str(tmp_path / "d"), device=frontend.device, write_mode="deferred")
+    sync._fe = lazy._fe = frontend
+    assert lazy.prefetch(paths) == 3 and all(lazy._lookup(p) is not None for p in paths)
+    for p in paths:
+        a = sync.remove_silence(sync.normalize_loudness(sync.normalize_audio(sync.reduce_stationary_noise(p))))
+        b = lazy.remove_silence(lazy.normalize_loudness(lazy.normalize_audio(lazy.reduce_stationary_noise(p))))
+        assert os.path.basename(a[0]) == os.path.basename(b[0]) and a[1] == b[1]
+        for suffix in ("_denoised", "_denoised_norm", "_denoised_norm_loudnorm", "_denoised_norm_loudnorm_nosilence"):
+            name = Path(p).stem + suffix + ".wav"
+            assert (tmp_path / "s" / name).read_bytes() == (tmp_path / "d" / name).read_bytes()
+    assert len(sync._plans) == 3                            # one stage plan per distinct length
+    sync.close(); lazy.close()

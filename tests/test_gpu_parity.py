@@ -351,10 +351,8 @@ def test_host_pipeline_device_handoff(frontend):
 @pytest.mark.parametrize("sr,seconds", [(8000, 40.0), (48000, 20.0), (22050, 15.0)])
 @pytest.mark.parametrize("stationary", [True, False])
 def test_denoise_parity_other_rates(frontend, sr, seconds, stationary):
-    if stationary and sr == 8000:
-        # documented limitation: below 10.24 kHz the detected noise clip can be shorter than n_fft
-        # (here 960 samples); scipy then shrinks nperseg to the clip length, the kernels keep the 1024 window
-        pytest.skip("noise clip shorter than n_fft: scipy's shrinking-nperseg semantics are not reproduced")
+    # 8 kHz stationary: the detected noise clip (960 samples here) is shorter than n_fft, so scipy shrinks nperseg to the clip
+    # length and the hop to nperseg - 768; noise_pass_kernel follows (maf_common.cuh clip_nperseg)
     pcm = gen(seconds, 11, sr=sr, meeting=not stationary)
     plan = frontend.plan([pcm.numel()], sample_rate=sr, stationary=stationary, n_mels=0)
     out16, outf, clip = plan.denoise(plan.pack([pcm]), want_float=True)
@@ -474,3 +472,108 @@ def test_full_size_cfg3_batch_equals_singles(frontend):
         ref = O.front_end(base[i].numpy(), SR, True, 80, 0)
         assert tuple(res.noise_clip[i].cpu().numpy()) == tuple(ref["noise_clip"])
         assert abs(res.lufs[i].item() - ref["lufs"]) <= 0.01
+
+
+# ---- noise clips shorter than n_fft (config.py:198 allows 8 kHz: 100 ms = 800 samples) --------------------------------------
+@pytest.mark.parametrize("clip_len", [769, 800, 880, 1001, 1023, 1024, 1025])
+def test_short_noise_clip_follows_scipy_shrunken_nperseg(frontend, clip_len):
+    """scipy.signal.stft(clip, nperseg=1024, noverlap=768) with len(clip) < 1024 uses nperseg = len(clip), hop = nperseg - 768
+    and an nperseg-point periodic Hann window (oracle: the real scipy call); the thresholds, hence the gate, must follow."""
+    import warnings
+    sr = 8000
+    pcm = gen(12.0, 31, sr=sr)
+    noise = gen(1.0, 77, sr=sr, sigma=0.02)[:clip_len].contiguous()
+    plan = frontend.plan([pcm.numel()], sample_rate=sr, external_noise=True, n_mels=0)
+    plan.set_noise_clips([0], [clip_len])
+    _, outf, clip = plan.denoise(plan.pack([pcm]), noise_pcm=noise.to(frontend.device), want_float=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                    # scipy: "nperseg = 1024 is greater than input length"
+        red = O.reduce_noise(pcm.numpy().astype(np.float32), sr, noise.numpy().astype(np.float32), 0.8, True)
+    assert snr_db(red, outf[0].cpu().numpy()) >= 80.0
+    assert tuple(clip.cpu().numpy()[0]) == (0, clip_len)   # an external clip reports its own range (never uninitialised memory)
+
+
+def test_noise_clip_not_longer_than_noverlap_is_an_error(frontend):
+    """scipy raises "noverlap must be less than nperseg" for clips of <= 768 samples; the reference wraps that into
+    AudioProcessingError (preprocessor.py:207-208).  The plan refuses such clips instead of producing numbers."""
+    from modular_audio_pipeline_b200 import MafError
+    pcm = gen(5.0, 1)
+    plan = frontend.plan([pcm.numel()], external_noise=True, n_mels=0)
+    with pytest.raises(MafError) as ei:
+        plan.set_noise_clips([0], [768])
+    assert ei.value.code == -1 and "768" in ei.value.message
+    def denoise_of(plan, n):
+        return plan.denoise(plan.pack([pcm[:n].contiguous()]))
+    with pytest.raises(MafError):                          # the fallback clip would be 0.04 s = 640 samples
+        denoise_of(frontend.plan([pcm.numel()], noise_sample_duration_s=0.04, n_mels=0), pcm.numel())
+    short = frontend.plan([700], n_mels=0)                 # a 700-sample recording: its only possible clip is itself
+    with pytest.raises(MafError):
+        denoise_of(short, 700)
+    assert short.peak_normalize(short.pack([pcm[:700].contiguous()]))[0].numel() == 700    # the other stages of that plan work
+    with pytest.raises(MafError) as ei:                    # 6 kHz: a detected 100 ms run is 600 samples
+        p6 = frontend.plan([60000], sample_rate=6000, n_mels=0)
+        p6.denoise(p6.pack([pcm[:60000].contiguous()]))
+    assert ei.value.code == -1 and "768" in ei.value.message
+
+
+# ---- non-stationary gate on an all-zero frequency row: documented deviation (silence instead of noisereduce's NaN) ---------
+def test_nonstationary_all_zero_chunk_guard(frontend):
+    """noisereduce divides by the smoothed magnitude: a chunk that is digital silence gives 0 / 0 = NaN for the WHOLE chunk
+    (SURVEY.md A.3).  The kernels take the relative excess as 0 there -- mask sigmoid(-20), output exactly 0 -- and every
+    other chunk must still match the oracle."""
+    pcm = gen(100.0, 4, meeting=True)
+    n = pcm.numel()
+    pcm[600000 - 30000: 2 * 600000 + 30000] = 0            # chunk 1 and both its 30 000-sample paddings: every row of its STFT is zero
+    plan = frontend.plan([n], stationary=False, n_mels=80)
+    out16, outf, _ = plan.denoise(plan.pack([pcm]), want_float=True)
+    got = outf[0].cpu().numpy()
+    assert np.isfinite(got).all()
+    assert not got[600000: 1200000].any() and not out16[0][600000: 1200000].any()
+    with np.errstate(all="ignore"):
+        red, _, _ = O.denoise_int16(pcm.numpy(), SR, stationary=False)
+    assert np.isnan(red[600000: 1200000]).all()            # the library behaviour the guard replaces
+    for a, b in ((0, 600000), (1200000, n)):
+        assert snr_db(red[a:b], got[a:b]) >= 80.0
+    res = plan.process(plan.pack([pcm]))                   # and the fused entry stays finite end to end
+    assert np.isfinite(res.lufs.item()) and torch.isfinite(res.log_mel[0]).all()
+
+
+# ---- error paths of the tensor-level entry points ----------------------------------------------------------------------------
+def test_front_door_and_mel_windows_error_paths(frontend):
+    from modular_audio_pipeline_b200 import MafError
+    x = torch.zeros(4800, dtype=torch.int16, device=frontend.device)
+    with pytest.raises(MafError) as ei:
+        frontend.front_door(x.float(), 1, 48000, 16000)                       # wrong dtype
+    assert ei.value.code == -1 and "int16" in ei.value.message
+    with pytest.raises(MafError):
+        frontend.front_door(x.cpu(), 1, 48000, 16000)                         # not on the device
+    with pytest.raises(MafError) as ei:
+        frontend.front_door(x, 3, 48000, 16000)                               # three channels
+    assert ei.value.code == -3
+    with pytest.raises(MafError):
+        frontend.front_door(x[:4799], 2, 48000, 16000)                        # odd number of interleaved stereo samples
+    with pytest.raises(MafError) as ei:
+        frontend.front_door(x, 1, 0, 16000)                                   # the library's own argument check
+    assert ei.value.code == -1 and "rate" in ei.value.message
+    mel = torch.zeros(80, 100, device=frontend.device)
+    seeks = torch.zeros(2, dtype=torch.int32, device=frontend.device)
+    out = torch.empty(2, 80, 3000, dtype=torch.float16, device=frontend.device)
+    with pytest.raises(MafError):
+        frontend.mel_windows(mel, seeks, torch.zeros(3, dtype=torch.int32, device=frontend.device), 3000, out)   # lens != seeks
+    with pytest.raises(MafError):
+        frontend.mel_windows(mel.double(), seeks, None, 3000, out)
+    with pytest.raises(MafError):
+        frontend.mel_windows(mel, seeks.long(), None, 3000, out)
+    with pytest.raises(MafError):
+        frontend.mel_windows(mel, seeks, None, 3000, out[:1])                 # output of the wrong size
+    with pytest.raises(MafError) as ei:
+        frontend.mel_windows(mel, seeks, None, 0, out[:0].reshape(2, 80, 0))  # the library's own shape check
+    assert ei.value.code == -1
+    assert frontend.mel_windows(mel, seeks, None, 3000, out).shape == (2, 80, 3000)
+
+
+def test_plan_rejects_oversized_batches(frontend):
+    from modular_audio_pipeline_b200 import MafError
+    with pytest.raises(MafError) as ei:
+        frontend.plan([16000] * 65536, n_mels=0)
+    assert ei.value.code == -3 and "65535" in ei.value.message
