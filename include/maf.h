@@ -135,16 +135,38 @@ int maf_sharded_logmel(maf_plan* plan, void* workspace_dev, const void* gate_dev
 int maf_mel_finalize(maf_plan* plan, void* workspace_dev, float* mel_dev, void* stream);
 /* byte offset / size of a named workspace buffer, so the host can view it as a tensor for a collective:
  * "peak" int32[n_items], "peak_norm" int32[n_items], "mel_max" int32[n_items] (ordered-int float),
- * "sub_energy" float64[tiles], "den16" int16 (own range preceded / followed by 2048 halo samples per item)      */
+ * "sub_energy" float64[tiles], "den16" int16 (own range preceded / followed by 2048 halo samples per item),
+ * "gates", "T2", "seg" int32[n_items][2] (noise-clip range), "mel_tmin" int32[n_items][max tiles] (ordered-int float: minimum
+ * log10 mel of every 32-frame tile -- the tiles below max - 8 are the ones maf_mel_finalize rewrites)             */
 int maf_plan_buffer(const maf_plan* plan, const char* name, int64_t* offset_bytes, int64_t* size_bytes);
 int64_t maf_plan_den_offset(const maf_plan* plan, int32_t item);   /* int16 index of own sample 0 inside "den16" */
 
 /* Sharded noise clip without a host round trip (seg_dev = the {start, end} maf_select_clip wrote, in global samples):
- * maf_sharded_clip_contrib fills clip_dev[600000] (int32) with the samples of the range this shard owns and zeros
- * elsewhere -- the all-reduce(SUM) over the ranks is the clip; maf_set_noise_clips_dev is maf_set_noise_clips for the
+ * maf_sharded_clip_contrib fills clip_dev[600000] (int16) with the samples of the range this shard owns and zeros
+ * elsewhere -- every sample is owned by exactly one rank, so the all-reduce(SUM) of the buffer viewed as 300000 int32
+ * words (pairs of samples; no carries) is the clip; maf_set_noise_clips_dev is maf_set_noise_clips for the
  * one item of a sharded plan with the length taken from seg_dev on the device (clip at offset 0 of noise_pcm_dev). */
-int maf_sharded_clip_contrib(maf_plan* plan, const int16_t* pcm_dev, const int32_t* seg_dev, int32_t* clip_dev, void* stream);
+int maf_sharded_clip_contrib(maf_plan* plan, const int16_t* pcm_dev, const int32_t* seg_dev, int16_t* clip_dev, void* stream);
 int maf_set_noise_clips_dev(maf_plan* plan, const int32_t* seg_dev, void* stream);
+
+/* Fused exchanges of the time-sharded mode (one all-gather per barrier instead of one collective per statistic; every buffer
+ * is caller-owned device memory, nothing here synchronises, so a whole sharded step can be captured in a CUDA graph):
+ *   maf_gather_compact      dst = concatenation over ranks r of src[r * stride + offset : ... + counts_dev[r]], elements of 4 or
+ *                           8 bytes -- un-pads an all-gather of per-rank arrays of different lengths (frame statistics)
+ *   maf_sharded_pack_edges  out[maf_sharded_edge_bytes()] = first 2048 own denoised samples | last 2048 | local peak
+ *   maf_sharded_unpack_edges  gathered[world][edge_bytes] -> global peak into the workspace, the left neighbour's tail / right
+ *                           neighbour's head into the 2048-sample halos of the denoised signal (K-weighting warm-up, STFT-400 halo)
+ *   maf_sharded_pack_energy out[1 + max_tiles] (float64) = local normalised peak | 100 ms sub-block energies, zero padded
+ *   maf_sharded_unpack_energy gathered[world][1 + max_tiles] -> global normalised peak into the workspace, sub_all_dev = the
+ *                           energies of the whole recording (counts_dev[r] tiles of rank r) for maf_gate                       */
+int maf_gather_compact(maf_ctx* ctx, const void* src_dev, int32_t elem_bytes, int32_t world, int64_t stride, int64_t offset,
+                       const int32_t* counts_dev, void* dst_dev, void* stream);
+int maf_sharded_edge_bytes(void);
+int maf_sharded_pack_edges(maf_plan* plan, void* workspace_dev, void* out_dev, void* stream);
+int maf_sharded_unpack_edges(maf_plan* plan, void* workspace_dev, const void* gathered_dev, int32_t world, int32_t rank, void* stream);
+int maf_sharded_pack_energy(maf_plan* plan, void* workspace_dev, double* out_dev, int32_t max_tiles, void* stream);
+int maf_sharded_unpack_energy(maf_plan* plan, void* workspace_dev, const double* gathered_dev, int32_t world, int32_t max_tiles,
+                              const int32_t* counts_dev, double* sub_all_dev, void* stream);
 
 /* ---- normalize_loudness on MULTI-CHANNEL 16-bit input (preprocessor.py:256-261: the reference averages the channels in float32,
  * `samples.reshape(-1, channels).mean(axis=1)`, meters the mean and writes the gained MONO signal, :271-282).  pcm_dev holds

@@ -69,6 +69,12 @@ SYMBOLS = {
     "maf_plan_buffer": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "maf_plan_den_offset": (C.c_int64, [_P, C.c_int32]),
     "maf_ms_energy": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int64, _P, _P, _P]),
+    "maf_gather_compact": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P]),
+    "maf_sharded_edge_bytes": (C.c_int, []),
+    "maf_sharded_pack_edges": (C.c_int, [_P, _P, _P, _P]),
+    "maf_sharded_unpack_edges": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "maf_sharded_pack_energy": (C.c_int, [_P, _P, _P, C.c_int32, _P]),
+    "maf_sharded_unpack_energy": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "maf_loudness_interleaved_ws": (C.c_int64, [C.c_int64, C.c_int32]),
     "maf_loudness_interleaved": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_float, _P, _P, _P, _P]),
     "maf_silence_layout": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),

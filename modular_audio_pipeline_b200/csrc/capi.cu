@@ -537,6 +537,7 @@ extern "C" int maf_plan_buffer(const maf_plan* pl, const char* name, int64_t* of
     else if (!strcmp(name, "mel_max")) b = &pl->mel_max; else if (!strcmp(name, "sub_energy")) b = &pl->sub;
     else if (!strcmp(name, "den16")) b = &pl->den16; else if (!strcmp(name, "gates")) b = &pl->gates;
     else if (!strcmp(name, "T2")) b = &pl->T2; else if (!strcmp(name, "seg")) b = &pl->seg;
+    else if (!strcmp(name, "mel_tmin")) b = &pl->mel_tmin;
     if (!b) return fail(MAF_ERR_INVALID, std::string("maf_plan_buffer: unknown buffer ") + name);
     *off = b->off; *size = b->bytes;
     return MAF_OK;
@@ -595,6 +596,15 @@ __global__ void abs_max_kernel(const int16_t* __restrict__ x, const Item* __rest
 }
 __global__ void gather_lufs_kernel(const Gate* __restrict__ g, int n, double* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = g[i].lufs;
+}
+
+// Small host structs reach the device as a KERNEL PARAMETER (copied at launch / captured by value in a CUDA graph) instead of a
+// cudaMemcpyAsync from a stack variable, which a graph would replay from a dead host address.
+struct PutBlob { unsigned char b[256]; };
+__global__ void put_blob_kernel(PutBlob v, unsigned char* dst, int n) { if ((int)threadIdx.x < n) dst[threadIdx.x] = v.b[threadIdx.x]; }
+static void launch_put(void* dst, const void* src, size_t n, cudaStream_t st) {
+    PutBlob v; memset(&v, 0, sizeof(v)); memcpy(v.b, src, n < sizeof(v.b) ? n : sizeof(v.b));
+    put_blob_kernel<<<1, 256, 0, st>>>(v, static_cast<unsigned char*>(dst), (int)n);
 }
 
 static const MelBank& pick_mel(const maf_plan* pl) { return pl->p.n_mels == 128 ? pl->ctx->mel128 : pl->ctx->mel80; }
@@ -941,7 +951,8 @@ extern "C" int maf_select_clip(maf_ctx* ctx, const float* energy, const int32_t*
     h.it.n_global = n_global; h.it.own_len = n_global; h.it.buf_len = n_global;
     h.foff = 0; h.fcount = (int)n_frames;
     unsigned char* d = (unsigned char*)ctx->scratch;
-    CU(cudaMemcpyAsync(d, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    static_assert(sizeof(h) <= 256, "selection header exceeds the put blob");
+    launch_put(d, &h, sizeof(h), st);
     const int frame_len = (int)(sr * 0.025), hop = (int)(sr * 0.010);
     if (n_frames > SEL_GRID_MIN_FRAMES)
         launch_select_clip_grid(energy, zc, (int)n_frames, h.it, frame_len, hop, sr, (int)(sr * (double)dur), d + 1024,
@@ -954,14 +965,14 @@ extern "C" int maf_select_clip(maf_ctx* ctx, const float* energy, const int32_t*
 }
 
 // Sharded noise clip without a host round trip: the selected range stays on the device (seg = {start, end} in global samples).
-__global__ void clip_contrib_kernel(const int16_t* __restrict__ pcm, Item it, const int* __restrict__ seg, int* __restrict__ clip) {
+__global__ void clip_contrib_kernel(const int16_t* __restrict__ pcm, Item it, const int* __restrict__ seg, int16_t* __restrict__ clip) {
     const long long gs = seg[0];
     long long len = (long long)seg[1] - gs; if (len > CHUNK) len = CHUNK;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < CHUNK; i += gridDim.x * blockDim.x) {
         const long long g = gs + i;
         int v = 0;
         if (i < len && g >= it.g0 && g < it.g0 + it.own_len) v = pcm[it.pcm_off + it.origin + (g - it.g0)];
-        clip[i] = v;
+        clip[i] = (int16_t)v;
     }
 }
 __global__ void set_clip_dev_kernel(const int* __restrict__ seg, Clip* __restrict__ clips) {
@@ -970,7 +981,7 @@ __global__ void set_clip_dev_kernel(const int* __restrict__ seg, Clip* __restric
     clips[0] = c;
 }
 
-extern "C" int maf_sharded_clip_contrib(maf_plan* pl, const int16_t* pcm, const int32_t* seg, int32_t* clip, void* stream) {
+extern "C" int maf_sharded_clip_contrib(maf_plan* pl, const int16_t* pcm, const int32_t* seg, int16_t* clip, void* stream) {
     if (!pl || !pcm || !seg || !clip || pl->n_items != 1) return fail(MAF_ERR_INVALID, "maf_sharded_clip_contrib: bad argument");
     CU(cudaSetDevice(pl->ctx->device));
     clip_contrib_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(pcm, pl->items[0], seg, clip);
@@ -983,6 +994,116 @@ extern "C" int maf_set_noise_clips_dev(maf_plan* pl, const int32_t* seg, void* s
     CU(cudaSetDevice(pl->ctx->device));
     set_clip_dev_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(seg, pl->d_clips_fixed);
     pl->have_noise_clips = true;
+    CU(cudaGetLastError());
+    return MAF_OK;
+}
+
+// ---- fused exchanges of the time-sharded mode: one all-gather per barrier instead of one collective per statistic -----------
+// generic: dst = concat over ranks r of src[r * stride + offset : ... + counts[r]] (elements of elem_bytes = 4 or 8)
+template <typename T>
+__global__ void gather_compact_kernel(const T* __restrict__ src, long long stride, long long offset, const int* __restrict__ counts, T* __restrict__ dst) {
+    const int r = blockIdx.y;
+    long long pre = 0;
+    for (int q = 0; q < r; ++q) pre += counts[q];
+    const int cnt = counts[r];
+    const T* s = src + (long long)r * stride + offset;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) dst[pre + i] = s[i];
+}
+
+extern "C" int maf_gather_compact(maf_ctx* ctx, const void* src, int32_t elem_bytes, int32_t world, int64_t stride, int64_t offset,
+                                  const int32_t* counts_dev, void* dst, void* stream) {
+    if (!ctx || !src || !dst || !counts_dev || world <= 0 || world > 65535 || (elem_bytes != 4 && elem_bytes != 8))
+        return fail(MAF_ERR_INVALID, "maf_gather_compact: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    dim3 grid(64, world);
+    if (elem_bytes == 4) gather_compact_kernel<uint32_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)src, stride, offset, counts_dev, (uint32_t*)dst);
+    else gather_compact_kernel<unsigned long long><<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned long long*)src, stride, offset, counts_dev, (unsigned long long*)dst);
+    CU(cudaGetLastError());
+    return MAF_OK;
+}
+
+// edges: [head KW_WARM int16 | tail KW_WARM int16 | peak int32 | pad] = MAF_EDGE_BYTES per rank
+constexpr int EDGE_BYTES = 4 * KW_WARM + 16;
+__global__ void pack_edges_kernel(const int16_t* __restrict__ den, long long own0, long long n, const int* __restrict__ peak, unsigned char* __restrict__ out) {
+    int16_t* o = reinterpret_cast<int16_t*>(out);
+    const long long k = n < KW_WARM ? n : KW_WARM;
+    for (int i = threadIdx.x; i < KW_WARM; i += blockDim.x) {
+        o[i] = i < k ? den[own0 + i] : (int16_t)0;                                   // first own samples
+        o[KW_WARM + i] = i >= KW_WARM - k ? den[own0 + n - KW_WARM + i] : (int16_t)0; // last own samples, right-aligned
+    }
+    if (threadIdx.x == 0) *reinterpret_cast<int*>(out + 4 * KW_WARM) = peak[0];
+}
+__global__ void unpack_edges_kernel(const unsigned char* __restrict__ gathered, int world, int rank, int16_t* __restrict__ den, long long own0, long long n,
+                                    int* __restrict__ peak) {
+    if (threadIdx.x == 0) {
+        int pk = 0;
+        for (int r = 0; r < world; ++r) pk = max(pk, *reinterpret_cast<const int*>(gathered + (size_t)r * EDGE_BYTES + 4 * KW_WARM));
+        peak[0] = pk;
+    }
+    if (rank > 0) {                                                                  // left neighbour's tail in front of own sample 0
+        const int16_t* t = reinterpret_cast<const int16_t*>(gathered + (size_t)(rank - 1) * EDGE_BYTES) + KW_WARM;
+        for (int i = threadIdx.x; i < KW_WARM; i += blockDim.x) den[own0 - KW_WARM + i] = t[i];
+    }
+    if (rank < world - 1) {                                                          // right neighbour's head behind the last own sample
+        const int16_t* h = reinterpret_cast<const int16_t*>(gathered + (size_t)(rank + 1) * EDGE_BYTES);
+        for (int i = threadIdx.x; i < KW_WARM; i += blockDim.x) den[own0 + n + i] = h[i];
+    }
+}
+
+extern "C" int maf_sharded_edge_bytes(void) { return EDGE_BYTES; }
+
+extern "C" int maf_sharded_pack_edges(maf_plan* pl, void* ws, void* out, void* stream) {
+    if (!pl || !ws || !out || pl->n_items != 1) return fail(MAF_ERR_INVALID, "maf_sharded_pack_edges: bad argument");
+    CU(cudaSetDevice(pl->ctx->device));
+    pack_edges_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ws_ptr<int16_t>(ws, pl->den16), pl->items[0].den_off, pl->items[0].own_len,
+                                                          ws_ptr<int>(ws, pl->peak), (unsigned char*)out);
+    pl->launches += 1;
+    CU(cudaGetLastError());
+    return MAF_OK;
+}
+
+extern "C" int maf_sharded_unpack_edges(maf_plan* pl, void* ws, const void* gathered, int32_t world, int32_t rank, void* stream) {
+    if (!pl || !ws || !gathered || pl->n_items != 1 || world <= 0 || rank < 0 || rank >= world)
+        return fail(MAF_ERR_INVALID, "maf_sharded_unpack_edges: bad argument");
+    CU(cudaSetDevice(pl->ctx->device));
+    unpack_edges_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>((const unsigned char*)gathered, world, rank, ws_ptr<int16_t>(ws, pl->den16),
+                                                            pl->items[0].den_off, pl->items[0].own_len, ws_ptr<int>(ws, pl->peak));
+    pl->launches += 1;
+    CU(cudaGetLastError());
+    return MAF_OK;
+}
+
+// energies: [peak_norm as double | sub-block energies padded to max_tiles] per rank
+__global__ void pack_energy_kernel(const double* __restrict__ sub, int n_tiles, int max_tiles, const int* __restrict__ peak_norm, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) out[0] = (double)peak_norm[0];
+    if (i < max_tiles) out[1 + i] = i < n_tiles ? sub[i] : 0.0;
+}
+__global__ void unpack_peak_norm_kernel(const double* __restrict__ gathered, int world, long long stride, int* __restrict__ peak_norm) {
+    int pk = 0;
+    for (int r = 0; r < world; ++r) pk = max(pk, (int)gathered[(long long)r * stride]);
+    peak_norm[0] = pk;
+}
+
+extern "C" int maf_sharded_pack_energy(maf_plan* pl, void* ws, double* out, int32_t max_tiles, void* stream) {
+    if (!pl || !ws || !out || pl->n_items != 1 || max_tiles < pl->items[0].n_ktiles) return fail(MAF_ERR_INVALID, "maf_sharded_pack_energy: bad argument");
+    CU(cudaSetDevice(pl->ctx->device));
+    pack_energy_kernel<<<(max_tiles + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ws_ptr<double>(ws, pl->sub), pl->items[0].n_ktiles, max_tiles,
+                                                                                 ws_ptr<int>(ws, pl->peak_norm), out);
+    pl->launches += 1;
+    CU(cudaGetLastError());
+    return MAF_OK;
+}
+
+extern "C" int maf_sharded_unpack_energy(maf_plan* pl, void* ws, const double* gathered, int32_t world, int32_t max_tiles, const int32_t* counts_dev,
+                                         double* sub_all, void* stream) {
+    if (!pl || !ws || !gathered || !counts_dev || !sub_all || world <= 0) return fail(MAF_ERR_INVALID, "maf_sharded_unpack_energy: bad argument");
+    CU(cudaSetDevice(pl->ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    unpack_peak_norm_kernel<<<1, 1, 0, st>>>(gathered, world, 1LL + max_tiles, ws_ptr<int>(ws, pl->peak_norm));
+    dim3 grid(64, world);
+    gather_compact_kernel<double><<<grid, 256, 0, st>>>(gathered, 1LL + max_tiles, 1, counts_dev, sub_all);
+    pl->launches += 2;
     CU(cudaGetLastError());
     return MAF_OK;
 }
@@ -1007,7 +1128,8 @@ extern "C" int maf_gate(maf_ctx* ctx, const double* sub_energy, int64_t n_tiles,
     Item it{};
     it.ktile_first = 0; it.n_ktiles = (int)n_tiles; it.n_blocks = (int)n_blocks;
     unsigned char* d = (unsigned char*)ctx->scratch + 512;
-    CU(cudaMemcpyAsync(d, &it, sizeof(it), cudaMemcpyHostToDevice, st));
+    static_assert(sizeof(Item) <= 256, "Item exceeds the put blob");
+    launch_put(d, &it, sizeof(it), st);
     launch_gate(sub_energy, (const Item*)d, 1, 1.0 / (0.4 * (double)sr), (double)target_lufs, peak_norm, (Gate*)gate, st);
     CU(cudaGetLastError());
     return MAF_OK;

@@ -401,9 +401,13 @@ class HostPipeline:
     (final int16 PCM, float32 log-mel, float64 LUFS) in the plan's layouts.
     """
 
-    def __init__(self, fe: FrontEnd, lengths: Sequence[int], depth: int = 2, mel_to_host: bool = True, **plan_kw):
+    def __init__(self, fe: FrontEnd, lengths: Sequence[int], depth: int = 2, mel_to_host: bool = True, encoder_windows: bool = False,
+                 **plan_kw):
         self.fe = fe
         self.depth = depth
+        # encoder_windows=True additionally cuts every item's log-mel into the 30 s float16 windows a Whisper encoder on the same
+        # GPU consumes (maf_mel_windows; whisper's seek loop at full-window stride): ``d_win[slot][item]`` = [windows, n_mels, 3000]
+        self.encoder_windows = encoder_windows
         # mel_to_host=False keeps the log-mel on the device (``d_mel[slot]``) for the hand-off into a Whisper encoder on the
         # same GPU (transcriber.py adapters); only the final PCM and the LUFS travel back over PCIe
         self.mel_to_host = mel_to_host
@@ -421,6 +425,13 @@ class HostPipeline:
         self.h_mel = [torch.empty(max(p0.total_mel, 4), dtype=torch.float32).pin_memory() for _ in range(depth)]
         self.h_lufs = [torch.empty(p0.n_items, dtype=torch.float64).pin_memory() for _ in range(depth)]
         self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.d_win: List[List[torch.Tensor]] = [[] for _ in range(depth)]
+        self._seeks: List[torch.Tensor] = []
+        if encoder_windows and p0.params.n_mels:
+            for lay in p0.layout:
+                self._seeks.append(torch.arange(0, max(lay.mel_frames, 1), 3000, dtype=torch.int32, device=dev))
+            for s in range(depth):
+                self.d_win[s] = [torch.empty(int(sk.numel()), p0.params.n_mels, 3000, dtype=torch.float16, device=dev) for sk in self._seeks]
         self._n = 0
         for p in self.plans:
             _ = p.workspace
@@ -446,6 +457,9 @@ class HostPipeline:
         self.s_k.wait_event(self.ev_in[slot])
         with torch.cuda.stream(self.s_k):
             res = plan.process(self.d_in[slot], out_pcm=self.d_out[slot], mel=self.d_mel[slot] if plan.params.n_mels else None)
+            if self._seeks:
+                for m, sk, w in zip(res.log_mel, self._seeks, self.d_win[slot]):
+                    self.fe.mel_windows(m, sk, None, 3000, w)
             self.ev_k[slot].record(self.s_k)
         res.lufs.record_stream(self.s_out)
         self.s_out.wait_event(self.ev_k[slot])

@@ -3,14 +3,20 @@
 Shards are whole 600 000-sample denoise chunks, so every chunk keeps the frame grid noisereduce gives it; a boundary
 is at the same time a multiple of the Whisper hop (160), of the loudness block hop (1 600) and of the noise-detector
 hop (160).  Each rank holds its samples plus a 30 000-sample halo per side (the denoise padding, which the algorithm
-defines) and the data path needs only latency-class collectives over NCCL / NVLink:
+defines) and the data path needs only latency-class collectives over NCCL / NVLink -- ONE per barrier of the algorithm, the
+statistics that become available together travel together:
 
-  1. all-gather of the per-frame (energy, zero-crossing) statistics  -> every rank selects the same noise clip
-  2. all-reduce(SUM) of the clip's samples (each rank fills the part it owns)      -> per-bin thresholds everywhere
-  3. all-reduce(MAX) of the denoised peak                                         -> peak normalise
-  4. all-gather of 2 x 2 048 denoised edge samples                                -> K-weighting warm-up / STFT-400 halo
-  5. all-gather of the 100 ms sub-block energies + all-reduce(MAX) of the normalised peak -> gating, gain, limiter
-  6. all-reduce(MAX) of the log-mel maximum                                       -> the global max - 8 clamp
+  1. all-gather  per-frame (energy, zero-crossing) statistics, packed            -> every rank selects the same noise clip
+  2. all-reduce  (SUM) the clip's samples: every sample is owned by one rank, the buffer travels as int32 words holding
+                 two int16 samples each                                           -> per-bin thresholds everywhere
+  3. all-gather  [first 2 048 | last 2 048 denoised samples | local peak]         -> peak normalise, K-weighting warm-up /
+                                                                                     STFT-400 halo
+  4. all-gather  [local normalised peak | 100 ms sub-block energies]              -> gating, gain, limiter
+  5. all-reduce  (MAX) the log-mel maximum                                        -> the global max - 8 clamp
+
+(non-stationary mode needs no noise clip: exchanges 3-5 only).  The device side of every exchange is a pack / unpack kernel of
+libmaf_b200.so on preallocated buffers; nothing in a step allocates or synchronises with the host, so a whole step can be
+replayed as one CUDA graph (``CudaShardBackend.capture``).
 
 ``ShardGeometry`` is pure Python.  ``run_sharded`` drives a *backend* (the CUDA plan in production,
 ``CudaShardBackend``; tests drive the same logic with a CPU stand-in over gloo) and a ``torch.distributed`` group.
@@ -99,8 +105,10 @@ class Comm:
 
     def __init__(self, group=None, via_cpu: bool = False):
         self.group, self.via_cpu = group, via_cpu
+        self.calls = 0
 
     def all_reduce(self, t: torch.Tensor, op) -> None:
+        self.calls += 1
         if self.via_cpu and t.is_cuda:
             h = t.cpu()
             dist.all_reduce(h, op=op, group=self.group)
@@ -109,6 +117,7 @@ class Comm:
             dist.all_reduce(t, op=op, group=self.group)
 
     def all_gather(self, out: torch.Tensor, inp: torch.Tensor) -> None:
+        self.calls += 1
         if self.via_cpu and inp.is_cuda:
             ho, hi = torch.empty(out.shape, dtype=out.dtype), inp.cpu()
             dist.all_gather_into_tensor(ho, hi, group=self.group)
@@ -117,67 +126,43 @@ class Comm:
             dist.all_gather_into_tensor(out, inp, group=self.group)
 
 
-def _gather_var(x: torch.Tensor, counts: List[int], comm: Comm) -> torch.Tensor:
-    """all-gather of per-rank 1-D tensors of different lengths (padded to the maximum), concatenated in rank order."""
-    world = len(counts)
-    m = max(max(counts), 1)
-    buf = torch.zeros(m, dtype=x.dtype, device=x.device)
-    buf[: x.numel()] = x
-    out = torch.empty(world * m, dtype=x.dtype, device=x.device)
-    comm.all_gather(out, buf)
-    return torch.cat([out[r * m: r * m + counts[r]] for r in range(world)])
+class NullComm(Comm):
+    """Times a step WITHOUT its collectives (bench.py: collective cost = step - this).  Results are meaningless."""
+
+    def all_reduce(self, t, op) -> None:
+        self.calls += 1
+
+    def all_gather(self, out, inp) -> None:
+        self.calls += 1
 
 
 def run_sharded(backend, geo: ShardGeometry, group=None, stationary: bool = True, comm: Optional[Comm] = None):
-    """Drive one shard through the pipeline.  Returns (own int16 PCM, own log-mel [n_mels, frames], LUFS)."""
-    world, rank = geo.world, geo.rank
+    """Drive one shard through the pipeline.  Returns (own int16 PCM, own log-mel [n_mels, frames], LUFS).
+
+    The backend packs what it contributes to an exchange into a flat buffer of a length that is the same on every rank and
+    unpacks the gathered buffer itself: ``*_contrib()`` -> (send, recv) tensors, ``apply_*()`` consumes recv."""
     comm = comm or Comm(group)
     if stationary:
-        # 1. noise clip: gather frame statistics, select identically on every rank
-        e, z = backend.frame_stats()
-        e_all = _gather_var(e, geo.frame_counts, comm)
-        z_all = _gather_var(z, geo.frame_counts, comm)
-        if hasattr(backend, "clip_contrib"):
-            # device path: the selected range never visits the host (no stream sync in the whole step)
-            seg = backend.select_clip_dev(e_all, z_all)
-            clip = backend.clip_contrib(seg)                       # int32 [CHUNK]: own samples of the range, zeros elsewhere
-            comm.all_reduce(clip, dist.ReduceOp.SUM)
-            backend.set_noise_dev(clip.to(torch.int16), seg)
-        else:
-            gs, ge = backend.select_clip(e_all, z_all)             # global sample range (host ints, one sync)
-            clip_len = min(ge - gs, CHUNK)
-            # 2. every rank contributes the clip samples it owns; the sum is the clip
-            clip = torch.zeros(clip_len, dtype=torch.int32, device=e.device)
-            lo, hi = max(gs, geo.own_start), min(gs + clip_len, geo.own_end)
-            if hi > lo:
-                clip[lo - gs: hi - gs] = backend.own_samples(lo - geo.own_start, hi - geo.own_start).to(torch.int32)
-            comm.all_reduce(clip, dist.ReduceOp.SUM)
-            backend.set_noise(clip.to(torch.int16))
-    # 3. denoise the own chunks; global peak
+        send, recv = backend.stats_contrib()                       # 1. frame statistics of the own frames
+        comm.all_gather(recv, send)
+        backend.select_clip()                                      #    identical selection on every rank
+        clip = backend.clip_contrib()                              # 2. own samples of the selected range, zeros elsewhere
+        comm.all_reduce(clip, dist.ReduceOp.SUM)
+        backend.set_noise()
     backend.denoise()
-    comm.all_reduce(backend.peak(), dist.ReduceOp.MAX)
-    # 4. exchange 2 x HALO denoised edge samples with the neighbours
-    edges = backend.den_edges()                                     # [2, HALO] int16: first / last own samples
-    all_edges = torch.empty(world * 2 * HALO, dtype=torch.int16, device=edges.device)
-    # neither NCCL nor gloo has an int16 type: move the edges as bytes
-    comm.all_gather(all_edges.view(torch.uint8), edges.reshape(-1).contiguous().view(torch.uint8))
-    all_edges = all_edges.view(world, 2, HALO)
-    left = all_edges[rank - 1, 1] if rank > 0 else None             # left neighbour's tail
-    right = all_edges[rank + 1, 0] if rank < world - 1 else None    # right neighbour's head
-    backend.set_den_halo(left, right)
-    # 5. loudness: local sub-block energies -> gathered, gated identically everywhere
-    sub = backend.energy()
-    comm.all_reduce(backend.peak_norm(), dist.ReduceOp.MAX)
-    sub_all = _gather_var(sub, geo.tile_counts, comm)
-    backend.gate(sub_all, geo.n_blocks)
-    # 6. gain + log-mel of the own frames, global maximum, clamp
-    backend.logmel()
+    send, recv = backend.edge_contrib()                            # 3. denoised edges + local peak
+    comm.all_gather(recv, send)
+    backend.apply_edges()
+    send, recv = backend.energy_contrib()                          # 4. K-weighted sub-block energies + normalised peak
+    comm.all_gather(recv, send)
+    backend.gate()
+    backend.logmel()                                               # 5. gain + log-mel of the own frames, global maximum, clamp
     comm.all_reduce(backend.mel_max(), dist.ReduceOp.MAX)
     return backend.finalize()
 
 
 class CudaShardBackend:
-    """The CUDA plan of one shard behind the interface ``run_sharded`` drives."""
+    """The CUDA plan of one shard behind the interface ``run_sharded`` drives.  Every buffer is allocated here, once."""
 
     def __init__(self, fe, geo: ShardGeometry, pcm_local: torch.Tensor, stationary: bool = True, n_mels: int = 80,
                  mel_padding: int = 0, target_lufs: float = -16.0, peak_normalize: bool = True,
@@ -186,16 +171,41 @@ class CudaShardBackend:
         self.fe, self.geo = fe, geo
         self.stationary, self.n_mels, self.padding = stationary, n_mels, mel_padding
         self.target_lufs, self.dur = target_lufs, noise_sample_duration_s
+        dev = fe.device
+        world = geo.world
         desc = ItemDesc(geo.buf_end - geo.buf_start, geo.origin, geo.own_len, geo.own_start, geo.n_global, geo.lo_avail, geo.hi_avail)
         self.plan = fe.plan([], sample_rate=geo.sample_rate, stationary=stationary, external_noise=stationary,
                             peak_normalize=peak_normalize, target_lufs=target_lufs, n_mels=n_mels, mel_padding=mel_padding,
                             shards=[desc])
-        self.pcm = self.plan.pack([pcm_local.to(fe.device)])
-        self.noise: Optional[torch.Tensor] = None
-        self.gate_buf = torch.zeros(32, dtype=torch.uint8, device=fe.device)
-        self.out = torch.empty(max(self.plan.total_out, 8), dtype=torch.int16, device=fe.device)
-        self.mel = torch.empty(max(self.plan.total_mel, 4), dtype=torch.float32, device=fe.device)
+        self.pcm = self.plan.pack([pcm_local.to(dev)])
+        self.gate_buf = torch.zeros(32, dtype=torch.uint8, device=dev)
+        self.out = torch.empty(max(self.plan.total_out, 8), dtype=torch.int16, device=dev)
+        self.mel = torch.empty(max(self.plan.total_mel, 4), dtype=torch.float32, device=dev)
         _ = self.plan.workspace
+        lib = fe._lib
+        # 1. frame statistics: [energy bits | zero crossings] padded to the largest shard
+        self.m_frames = max(max(geo.frame_counts), 1)
+        self.stats_send = torch.zeros(2 * self.m_frames, dtype=torch.int32, device=dev)
+        self.stats_recv = torch.empty(world * 2 * self.m_frames, dtype=torch.int32, device=dev)
+        self.frame_counts = torch.tensor(geo.frame_counts, dtype=torch.int32, device=dev)
+        self.n_frames_all = int(sum(geo.frame_counts))
+        self.e_all = torch.empty(max(self.n_frames_all, 1), dtype=torch.float32, device=dev)
+        self.z_all = torch.empty(max(self.n_frames_all, 1), dtype=torch.int32, device=dev)
+        self.seg = torch.zeros(2, dtype=torch.int32, device=dev)
+        # 2. noise clip: CHUNK int16 samples = CHUNK / 2 int32 words on the wire
+        self.clip = torch.zeros(CHUNK, dtype=torch.int16, device=dev)
+        # 3. edges
+        self.edge_bytes = int(lib.maf_sharded_edge_bytes())
+        self.edge_send = torch.zeros(self.edge_bytes, dtype=torch.uint8, device=dev)
+        self.edge_recv = torch.empty(world * self.edge_bytes, dtype=torch.uint8, device=dev)
+        # 4. energies
+        self.m_tiles = max(max(geo.tile_counts), 1)
+        self.en_send = torch.zeros(1 + self.m_tiles, dtype=torch.float64, device=dev)
+        self.en_recv = torch.empty(world * (1 + self.m_tiles), dtype=torch.float64, device=dev)
+        self.tile_counts = torch.tensor(geo.tile_counts, dtype=torch.int32, device=dev)
+        self.sub_all = torch.empty(max(int(sum(geo.tile_counts)), 1), dtype=torch.float64, device=dev)
+        self._mel_max = self.plan.buffer("mel_max", torch.int32)
+        self._graph = None
 
     def _st(self):
         return torch.cuda.current_stream(self.fe.device).cuda_stream
@@ -205,88 +215,93 @@ class CudaShardBackend:
         with torch.cuda.device(self.fe.device):
             check(fn(*args))
 
-    def frame_stats(self):
-        return self.plan.frame_stats(self.pcm)
-
-    def select_clip_dev(self, e_all, z_all):
-        seg = torch.zeros(2, dtype=torch.int32, device=self.fe.device)
+    # 1 -------------------------------------------------------------------------------------------------------------
+    def stats_contrib(self):
         lib = self.fe._lib
-        self._e_all, self._z_all = e_all, z_all                 # keep alive until the kernel has run
-        self._call(lib.maf_select_clip, self.fe._h, e_all.data_ptr(), z_all.data_ptr(), e_all.numel(), self.geo.n_global,
-                   self.geo.sample_rate, self.dur, seg.data_ptr(), self._st())
-        return seg
+        send = self.stats_send                                     # maf_frame_stats writes the two arrays straight into the send buffer
+        self._call(lib.maf_frame_stats, self.plan._h, self.pcm.data_ptr(), send.data_ptr(), send.data_ptr() + 4 * self.m_frames, self._st())
+        return send, self.stats_recv
 
-    def select_clip(self, e_all, z_all):
-        s = self.select_clip_dev(e_all, z_all).cpu()
-        return int(s[0]), int(s[1])
+    def select_clip(self):
+        lib, fe, g = self.fe._lib, self.fe, self.geo
+        m = self.m_frames
+        self._call(lib.maf_gather_compact, fe._h, self.stats_recv.data_ptr(), 4, g.world, 2 * m, 0, self.frame_counts.data_ptr(),
+                   self.e_all.data_ptr(), self._st())
+        self._call(lib.maf_gather_compact, fe._h, self.stats_recv.data_ptr(), 4, g.world, 2 * m, m, self.frame_counts.data_ptr(),
+                   self.z_all.data_ptr(), self._st())
+        self._call(lib.maf_select_clip, fe._h, self.e_all.data_ptr(), self.z_all.data_ptr(), self.n_frames_all, g.n_global,
+                   g.sample_rate, self.dur, self.seg.data_ptr(), self._st())
 
-    def clip_contrib(self, seg: torch.Tensor) -> torch.Tensor:
-        clip = torch.empty(CHUNK, dtype=torch.int32, device=self.fe.device)
-        self._call(self.fe._lib.maf_sharded_clip_contrib, self.plan._h, self.pcm.data_ptr(), seg.data_ptr(), clip.data_ptr(), self._st())
-        return clip
+    # 2 -------------------------------------------------------------------------------------------------------------
+    def clip_contrib(self) -> torch.Tensor:
+        self._call(self.fe._lib.maf_sharded_clip_contrib, self.plan._h, self.pcm.data_ptr(), self.seg.data_ptr(), self.clip.data_ptr(), self._st())
+        return self.clip.view(torch.int32)
 
-    def set_noise_dev(self, clip: torch.Tensor, seg: torch.Tensor):
-        self.noise, self._seg = clip.contiguous(), seg
-        self._call(self.fe._lib.maf_set_noise_clips_dev, self.plan._h, seg.data_ptr(), self._st())
-
-    def own_samples(self, a: int, b: int) -> torch.Tensor:
-        o = self.plan.layout[0].pcm_off + self.geo.origin
-        return self.pcm[o + a: o + b]
-
-    def set_noise(self, clip: torch.Tensor):
-        self.noise = clip.contiguous()
-        self.plan.set_noise_clips([0], [clip.numel()])
+    def set_noise(self):
+        self._call(self.fe._lib.maf_set_noise_clips_dev, self.plan._h, self.seg.data_ptr(), self._st())
 
     def denoise(self):
         lib = self.fe._lib
-        self._call(lib.maf_sharded_denoise, self.plan._h, self.pcm.data_ptr(), None if self.noise is None else self.noise.data_ptr(),
+        self._call(lib.maf_sharded_denoise, self.plan._h, self.pcm.data_ptr(), self.clip.data_ptr() if self.stationary else None,
                    self.plan.workspace.data_ptr(), self._st())
 
-    def peak(self):
-        return self.plan.buffer("peak", torch.int32)
+    # 3 -------------------------------------------------------------------------------------------------------------
+    def edge_contrib(self):
+        self._call(self.fe._lib.maf_sharded_pack_edges, self.plan._h, self.plan.workspace.data_ptr(), self.edge_send.data_ptr(), self._st())
+        return self.edge_send, self.edge_recv
 
-    def peak_norm(self):
-        return self.plan.buffer("peak_norm", torch.int32)
+    def apply_edges(self):
+        self._call(self.fe._lib.maf_sharded_unpack_edges, self.plan._h, self.plan.workspace.data_ptr(), self.edge_recv.data_ptr(),
+                   self.geo.world, self.geo.rank, self._st())
 
-    def mel_max(self):
-        return self.plan.buffer("mel_max", torch.int32)
-
-    def den_edges(self):
-        den = self.plan.buffer("den16", torch.int16)
-        o, n = self.plan.den_offset(0), self.geo.own_len
-        head = torch.zeros(HALO, dtype=torch.int16, device=den.device)
-        tail = torch.zeros(HALO, dtype=torch.int16, device=den.device)
-        k = min(HALO, n)
-        head[:k] = den[o: o + k]
-        tail[HALO - k:] = den[o + n - k: o + n]
-        return torch.stack([head, tail])
-
-    def set_den_halo(self, left, right):
-        den = self.plan.buffer("den16", torch.int16)
-        o, n = self.plan.den_offset(0), self.geo.own_len
-        if left is not None:
-            den[o - HALO: o] = left
-        if right is not None:
-            den[o + n: o + n + HALO] = right
-
-    def energy(self):
+    # 4 -------------------------------------------------------------------------------------------------------------
+    def energy_contrib(self):
         lib = self.fe._lib
         self._call(lib.maf_sharded_energy, self.plan._h, self.plan.workspace.data_ptr(), self._st())
-        return self.plan.buffer("sub_energy", torch.float64)[: self.geo.tile_counts[self.geo.rank]]
+        self._call(lib.maf_sharded_pack_energy, self.plan._h, self.plan.workspace.data_ptr(), self.en_send.data_ptr(), self.m_tiles, self._st())
+        return self.en_send, self.en_recv
 
-    def gate(self, sub_all: torch.Tensor, n_blocks: int):
-        lib = self.fe._lib
-        self.sub_all = sub_all.contiguous()
-        self._call(lib.maf_gate, self.fe._h, self.sub_all.data_ptr(), self.sub_all.numel(), n_blocks, self.geo.sample_rate,
-                   self.target_lufs, self.peak_norm().data_ptr(), self.gate_buf.data_ptr(), self._st())
+    def gate(self):
+        lib, g = self.fe._lib, self.geo
+        self._call(lib.maf_sharded_unpack_energy, self.plan._h, self.plan.workspace.data_ptr(), self.en_recv.data_ptr(), g.world, self.m_tiles,
+                   self.tile_counts.data_ptr(), self.sub_all.data_ptr(), self._st())
+        self._call(lib.maf_gate, self.fe._h, self.sub_all.data_ptr(), self.sub_all.numel(), g.n_blocks, g.sample_rate,
+                   self.target_lufs, self.plan.buffer("peak_norm", torch.int32).data_ptr(), self.gate_buf.data_ptr(), self._st())
 
+    # 5 -------------------------------------------------------------------------------------------------------------
     def logmel(self):
         lib = self.fe._lib
         self._call(lib.maf_sharded_logmel, self.plan._h, self.plan.workspace.data_ptr(), self.gate_buf.data_ptr(), self.out.data_ptr(),
                    self.mel.data_ptr(), self._st())
+
+    def mel_max(self):
+        return self._mel_max
 
     def finalize(self):
         lib = self.fe._lib
         self._call(lib.maf_mel_finalize, self.plan._h, self.plan.workspace.data_ptr(), self.mel.data_ptr(), self._st())
         lufs = self.gate_buf[:8].view(torch.float64)
         return self.plan.split_out(self.out)[0], self.plan.split_mel(self.mel)[0], lufs
+
+    # whole-step CUDA graph -------------------------------------------------------------------------------------------
+    def capture(self, comm: Optional[Comm] = None):
+        """Capture one whole sharded step -- kernels AND collectives -- into a CUDA graph (NCCL operations are capturable; the
+        step allocates nothing and never touches the host).  Returns a callable that replays it and returns finalize()'s tensors."""
+        comm = comm or Comm(None)
+        dev = self.fe.device
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):                                     # warm-up outside capture (lazy function attributes, NCCL channels)
+                run_sharded(self, self.geo, stationary=self.stationary, comm=comm)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            ret = run_sharded(self, self.geo, stationary=self.stationary, comm=comm)
+        self._graph = graph
+
+        def replay():
+            graph.replay()
+            return ret
+        return replay

@@ -213,6 +213,33 @@ def reduce_noise(y: np.ndarray, sr: int, y_noise: Optional[np.ndarray] = None, p
     return result.astype(y.dtype if y.dtype.kind == "f" else np.float32)
 
 
+def stationary_tie_samples(y: np.ndarray, sr: int, y_noise: np.ndarray, band_db: float = 1e-4) -> np.ndarray:
+    """Boolean mask over the samples of y that a HARD-threshold tie can reach.  The stationary gate is `dB > thresh`, a step
+    function: a cell whose dB value lies within `band_db` of its threshold is decided by the last bits of the FFT, which differ
+    between any two implementations (scipy's float32 pocketfft in the real library, the float64 here, the float32 kernels).  A
+    flipped cell moves the smoothed mask of its (2 nf + 1) x (2 nt + 1) neighbourhood, i.e. the output of the frames t - nt ..
+    t + nt.  Test infrastructure for the parity tests: those samples are compared at a looser bound, everything else at the
+    north-star 80 dB."""
+    y = np.asarray(y, dtype=np.float64)
+    n = len(y)
+    thresh = stationary_threshold(y_noise)
+    vf, vt = smoothing_taps(sr)
+    nt = len(vt) // 2
+    tied = np.zeros(n, dtype=bool)
+    for (s, keep, L) in chunk_table(n):
+        c = np.zeros(L)
+        lo = max(s - PAD, 0)
+        hi = min(s + (L - 2 * PAD) + PAD, n)
+        c[lo - (s - PAD): hi - (s - PAD)] = y[lo:hi]
+        D = amp_to_db(np.abs(_stft(c)))
+        frames = np.nonzero((np.abs(D - thresh[:, None]) <= band_db).any(axis=0))[0]
+        for t in frames:                                               # frame t is centred on padded sample t * HOP
+            a = (t - nt) * HOP - N_FFT // 2 - PAD + s
+            b = (t + nt) * HOP + N_FFT // 2 - PAD + s
+            tied[max(a, s): max(min(b, s + keep), s)] = True
+    return tied
+
+
 def to_int16_trunc(x: np.ndarray) -> np.ndarray:
     """``reduced.astype(np.int16)`` of preprocessor.py:211: truncation toward zero, low 16 bits on overflow."""
     return np.asarray(x, dtype=np.float32).astype(np.int64).astype(np.int16)

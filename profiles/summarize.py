@@ -46,11 +46,18 @@ def main():
     lines.append("|---|---|" + "---|" * (len(METRICS) + 1))
     seen = set()
     traffic = {}
+    warp_inst = {}
+    per_step = {}
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("maf::", "")
+        per_step[name.split("<")[0]] = per_step.get(name.split("<")[0], 0) + 1
         if name in seen:
             continue
         seen.add(name)
+        try:
+            warp_inst[name.split("<")[0]] = float(r[hdr.index("smsp__inst_executed.sum")])
+        except ValueError:
+            pass
         cells = []
         for m, _ in METRICS:
             i = hdr.index(m)
@@ -71,7 +78,7 @@ def main():
         wl = a
     with open(os.path.join(ROOT, "profiles", f"traffic_{wl}.json"), "w") as f:
         json.dump({"tag": tag, "workload": wl, "source": "ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch",
-                   "bytes_per_launch": traffic}, f, indent=1)
+                   "bytes_per_launch": traffic, "warp_inst_per_launch": warp_inst, "launches_per_step": per_step}, f, indent=1)
     lpath = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
     if os.path.exists(lpath):
         lr = list(csv.DictReader(l for l in open(lpath) if l.startswith('"')))

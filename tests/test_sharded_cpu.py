@@ -30,25 +30,44 @@ class OracleShardBackend:
         self._mel_max = torch.zeros(1, dtype=torch.float32)
         self.left = self.right = None
 
-    def frame_stats(self):
+    # 1. frame statistics: [energy bits | zero crossings], padded to the largest shard, gathered, un-padded
+    def stats_contrib(self):
         g = self.geo
         hop, flen = 160, 400
         cnt = g.frame_counts[g.rank]
         seg = self.x[g.origin: g.origin + (cnt - 1) * hop + flen].astype(np.float32)
         e, z = O.frame_stats(seg, SR)
-        return torch.from_numpy(e[:cnt].astype(np.float32)), torch.from_numpy(np.round(z[:cnt] * flen).astype(np.int32))
+        m = max(g.frame_counts)
+        send = torch.zeros(2 * m, dtype=torch.int32)
+        send[:cnt] = torch.from_numpy(e[:cnt].astype(np.float32)).view(torch.int32)
+        send[m: m + cnt] = torch.from_numpy(np.round(z[:cnt] * flen).astype(np.int32))
+        self._stats = torch.empty(g.world * 2 * m, dtype=torch.int32)
+        return send, self._stats
 
-    def select_clip(self, e_all, z_all):
+    def select_clip(self):
+        g = self.geo
+        m = max(g.frame_counts)
+        rows = self._stats.view(g.world, 2, m)
+        e_all = torch.cat([rows[r, 0, :g.frame_counts[r]] for r in range(g.world)]).view(torch.float32)
+        z_all = torch.cat([rows[r, 1, :g.frame_counts[r]] for r in range(g.world)])
         segs = O.segments_from_stats(e_all.numpy().astype(np.float64), z_all.numpy() / 400.0, 160, SR)
-        if segs:
-            return max(segs, key=lambda s: s[1] - s[0])
-        return (0, min(int(SR * 0.5), self.geo.n_global))
+        self.seg = max(segs, key=lambda s: s[1] - s[0]) if segs else (0, min(int(SR * 0.5), g.n_global))
 
-    def own_samples(self, a, b):
-        return torch.from_numpy(self.x[self.geo.origin + a: self.geo.origin + b].copy())
+    # 2. the clip: own samples of the range as int16 (zeros elsewhere), summed as int32 words of two samples
+    def clip_contrib(self):
+        g = self.geo
+        gs, ge = self.seg
+        n = min(ge - gs, CHUNK)
+        clip = np.zeros(CHUNK, dtype=np.int16)
+        lo, hi = max(gs, g.own_start), min(gs + n, g.own_end)
+        if hi > lo:
+            clip[lo - gs: hi - gs] = self.x[g.origin + lo - g.own_start: g.origin + hi - g.own_start]
+        self._clip = torch.from_numpy(clip)
+        return self._clip.view(torch.int32)
 
-    def set_noise(self, clip):
-        self.thresh = O.stationary_threshold(clip.numpy().astype(np.float32))
+    def set_noise(self):
+        gs, ge = self.seg
+        self.thresh = O.stationary_threshold(self._clip.numpy()[: min(ge - gs, CHUNK)].astype(np.float32))
 
     def denoise(self):
         g = self.geo
@@ -65,16 +84,24 @@ class OracleShardBackend:
         self.den = O.to_int16_trunc(out.astype(np.float32))
         self._peak[0] = int(np.abs(self.den.astype(np.int32)).max())
 
-    def peak(self): return self._peak
-    def peak_norm(self): return self._peak_norm
     def mel_max(self): return self._mel_max
 
-    def den_edges(self):
-        return torch.from_numpy(np.stack([self.den[:HALO], self.den[-HALO:]]).copy())
+    # 3. edges: [first HALO | last HALO denoised samples | local peak]
+    def edge_contrib(self):
+        g = self.geo
+        send = torch.zeros(2 * HALO + 2, dtype=torch.int32)
+        send[:HALO] = torch.from_numpy(self.den[:HALO].astype(np.int32))
+        send[HALO: 2 * HALO] = torch.from_numpy(self.den[-HALO:].astype(np.int32))
+        send[2 * HALO] = int(self._peak[0])
+        self._edges = torch.empty(g.world * (2 * HALO + 2), dtype=torch.int32)
+        return send, self._edges
 
-    def set_den_halo(self, left, right):
-        self.left = None if left is None else left.numpy()
-        self.right = None if right is None else right.numpy()
+    def apply_edges(self):
+        g = self.geo
+        rows = self._edges.view(g.world, 2 * HALO + 2)
+        self._peak[0] = int(rows[:, 2 * HALO].max())
+        self.left = rows[g.rank - 1, HALO: 2 * HALO].numpy().astype(np.int16) if g.rank > 0 else None
+        self.right = rows[g.rank + 1, :HALO].numpy().astype(np.int16) if g.rank < g.world - 1 else None
 
     def _norm_with_halo(self):
         parts = [p for p in (self.left, self.den, self.right) if p is not None]
@@ -83,21 +110,31 @@ class OracleShardBackend:
         v = np.floor(np.clip(full.astype(np.float64) * f, -32768.0, 32767.0)).astype(np.int16)
         return v, (0 if self.left is None else len(self.left))
 
-    def energy(self):
+    # 4. [local normalised peak | sub-block energies]
+    def energy_contrib(self):
+        g = self.geo
         v, off = self._norm_with_halo()
         x = v.astype(np.float32) / np.float32(32768.0)
         d = x.copy()
         for (b, a) in O.k_weighting_coeffs(SR):
             d[:] = sps.lfilter(b, a, d)                  # starts from zero state HALO samples early: the warm-up
-        own = d[off: off + self.geo.own_len]
-        nt = self.geo.tile_counts[self.geo.rank]
+        own = d[off: off + g.own_len]
+        nt = g.tile_counts[g.rank]
         sub = np.array([np.sum(np.square(own[t * 1600:(t + 1) * 1600]).astype(np.float64)) for t in range(nt)])
-        self._peak_norm[0] = int(np.abs(v[off: off + self.geo.own_len].astype(np.int32)).max())
-        return torch.from_numpy(sub)
+        m = max(g.tile_counts)
+        send = torch.zeros(1 + m, dtype=torch.float64)
+        send[0] = float(np.abs(v[off: off + g.own_len].astype(np.int32)).max())
+        send[1: 1 + nt] = torch.from_numpy(sub)
+        self._en = torch.empty(g.world * (1 + m), dtype=torch.float64)
+        return send, self._en
 
-    def gate(self, sub_all, n_blocks):
-        sb = sub_all.numpy()
-        z = np.array([sb[j:j + 4].sum() / 6400.0 for j in range(n_blocks)])
+    def gate(self):
+        g = self.geo
+        m = max(g.tile_counts)
+        rows = self._en.view(g.world, 1 + m)
+        self._peak_norm[0] = int(rows[:, 0].max())
+        sb = torch.cat([rows[r, 1: 1 + g.tile_counts[r]] for r in range(g.world)]).numpy()
+        z = np.array([sb[j:j + 4].sum() / 6400.0 for j in range(g.n_blocks)])
         self.lufs = O.gate_loudness(z)
         self.gain = np.float32(10.0 ** ((-16.0 - self.lufs) / 20.0))
         p = self.gain * np.float32(int(self._peak_norm[0]) / 32768.0)
