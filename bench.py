@@ -423,6 +423,7 @@ def measure_time_sharded(args, dev, world, rank, steps, warmup):
         graph_ms = timed(replay, steps)
     except Exception as e:                                    # the eager figure stands
         graph_err = f"{type(e).__name__}: {e}"[:300]
+    backend.release_graph()                                   # before destroy_process_group: a live graph pins the NCCL communicator
     out, mel, lufs = run_sharded(backend, geo, stationary=True, comm=comm)
     torch.cuda.synchronize()
     best = min(ms_eager, graph_ms) if graph_ms else ms_eager
@@ -578,6 +579,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        import faulthandler
+        faulthandler.dump_traceback_later(1500, exit=True)     # a stuck collective must not hold N GPUs until the driver's limit
         dist.init_process_group("nccl", device_id=dev)
     desc, seconds, per_gpu, stationary, n_mels, padding, meeting = WORKLOADS[args.workload]
     n = int(round(seconds * SR))

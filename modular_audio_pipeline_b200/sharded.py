@@ -300,8 +300,21 @@ class CudaShardBackend:
         with torch.cuda.graph(graph):
             ret = run_sharded(self, self.geo, stationary=self.stationary, comm=comm)
         self._graph = graph
+        del graph
 
         def replay():
-            graph.replay()
+            self._graph.replay()
             return ret
         return replay
+
+    def release_graph(self) -> None:
+        """Destroy the captured step.  A live CUDA graph that holds NCCL operations keeps the communicator referenced:
+        ``dist.destroy_process_group()`` blocks until the graph is gone, so call this (or ``close``) first."""
+        if self._graph is not None:
+            torch.cuda.synchronize(self.fe.device)
+            self._graph.reset()
+            self._graph = None
+
+    def close(self) -> None:
+        self.release_graph()
+        self.plan.close()

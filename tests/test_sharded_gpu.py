@@ -24,6 +24,8 @@ EXPECT = int(os.environ.get("MAF_EXPECT_GPUS", "0"))
 
 
 def _worker(rank, world, port, pcm, stationary, n_mels, padding, results):
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("MAF_RANK_TIMEOUT", "240")), exit=True)   # a stuck collective must not hold the box
     from modular_audio_pipeline_b200 import FrontEnd
     from modular_audio_pipeline_b200.sharded import Comm, CudaShardBackend, ShardGeometry, run_sharded
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -47,8 +49,10 @@ def _worker(rank, world, port, pcm, stationary, n_mels, padding, results):
             o2, m2, l2 = replay()
             torch.cuda.synchronize()
             res[5] = bool(np.array_equal(o2.cpu().numpy(), res[0]) and np.array_equal(m2.cpu().numpy(), res[1]) and float(l2.cpu().item()) == res[2])
+            backend.release_graph()                        # a live graph with NCCL nodes would block destroy_process_group
         results[rank] = tuple(res)
     finally:
+        faulthandler.cancel_dump_traceback_later()
         dist.destroy_process_group()
 
 
@@ -61,9 +65,9 @@ def _free_port():
 @pytest.mark.timeout(900)
 @pytest.mark.parametrize("world,stationary,n_mels,padding,n_samples", [
     (2, True, 80, 0, 1500000), (2, False, 128, 480000, 1500000), (2, False, 80, 480000, 12345678),
-    (4, True, 80, 480000, 12345678), (4, False, 128, 0, 2400001)])
+    (4, True, 80, 480000, 12345678), (4, False, 128, 0, 2403001)])
 def test_ranks_equal_one_gpu(frontend, world, stationary, n_mels, padding, n_samples):
-    # 3 chunks (ranks own 2 + 1), a 12.9 min recording (21 chunks, ragged last chunk), and 5 chunks over 4 ranks with a 1-sample tail
+    # 3 chunks (ranks own 2 + 1), a 12.9 min recording (21 chunks, ragged last chunk), and 5 chunks over 4 ranks with a 3001-sample last shard
     pcm = speech_noise(n_samples / SR, 8, meeting=not stationary).numpy()
     mgr = mp.Manager()
     results = mgr.dict()
