@@ -202,7 +202,7 @@ struct maf_plan {
     NsParams ns{}; void* d_ns = nullptr;
     KwGeom kgeo{}; KwScan kscan{}; void* d_kscan = nullptr; int max_kgroups = 0;
     long long total_tiles = 0;
-    WsBuf S, M, P, Q, Yend, Zend, bits, rowflag, T2, T2hi, nmax, partial, E, ZC, clips, seg, den16, peak, pnorm, peak_norm, mel_max, mel_tmin, sub, gates, selws;
+    WsBuf S, M, P, Q, Yend, Zend, bits, rowflag, T2, T2hi, nmax, partial, E, ZC, clips, seg, den16, norm16, peak, pnorm, peak_norm, mel_max, mel_tmin, sub, gates, selws;
     long long ws_bytes = 0;
     long long launches = 0;
     // optional per-stage CUDA-event timing (maf_plan_profile): ring of event sets, one per maf_process call
@@ -476,6 +476,7 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
     pl->clips = carve(cur, (long long)n_items * sizeof(Clip));
     pl->seg = carve(cur, (long long)n_items * 2 * 4);
     pl->den16 = carve(cur, pl->total_den * 2);
+    pl->norm16 = carve(cur, pl->total_den * 2);       // peak-normalised samples (den16 layout), written by kweight_energy_kernel for logmel_kernel
     pl->peak = carve(cur, (long long)n_items * 4);
     pl->pnorm = carve(cur, (long long)n_items * sizeof(PeakNorm));
     pl->peak_norm = carve(cur, (long long)n_items * 4);
@@ -717,14 +718,15 @@ static int run_denoise(maf_plan* pl, const int16_t* pcm, const int16_t* noise_pc
     return MAF_OK;
 }
 
-static int run_loudness_stats(maf_plan* pl, const int16_t* src, const Item* items, int peak_normalize, void* ws, cudaStream_t st) {
+static int run_loudness_stats(maf_plan* pl, const int16_t* src, const Item* items, int peak_normalize, void* ws, cudaStream_t st,
+                              int16_t* norm16 = nullptr) {
     if (pl->too_short) return fail(MAF_ERR_TOO_SHORT, "Audio must have length greater than the block size");
     const int n = pl->n_items;
     launch_zero_bytes(ws_ptr<int>(ws, pl->peak_norm), 4LL * n, st);
     pl->launches += 1;
     if (peak_normalize) { launch_peak_factor(ws_ptr<int>(ws, pl->peak), n, pl->target_peak, ws_ptr<PeakNorm>(ws, pl->pnorm), st); pl->launches += 1; }
     launch_kweight_energy(src, items, n, pl->max_kgroups, pl->tile_len, pl->kgeo, pl->kw, (const KwScan*)pl->d_kscan, peak_normalize, ws_ptr<PeakNorm>(ws, pl->pnorm),
-                          ws_ptr<double>(ws, pl->sub), ws_ptr<int>(ws, pl->peak_norm), st);
+                          ws_ptr<double>(ws, pl->sub), ws_ptr<int>(ws, pl->peak_norm), peak_normalize ? norm16 : nullptr, st);
     pl->launches += 1;
     mark(pl, ST_KWEIGHT, st);
     CU(cudaGetLastError());
@@ -741,7 +743,7 @@ static int run_gate(maf_plan* pl, const Item* items, void* ws, cudaStream_t st) 
 }
 
 static int run_logmel(maf_plan* pl, const int16_t* src, const Item* items, int peak_normalize, const Gate* gates, void* ws, int16_t* out16,
-                      float* mel, bool finalize, cudaStream_t st) {
+                      float* mel, bool finalize, cudaStream_t st, const int16_t* norm16 = nullptr) {
     const int n = pl->n_items;
     fill_int_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws_ptr<int>(ws, pl->mel_max), n, (int)0x80000001);
     {
@@ -749,7 +751,7 @@ static int run_logmel(maf_plan* pl, const int16_t* src, const Item* items, int p
         fill_int_kernel<<<(nt + 255) / 256, 256, 0, st>>>(ws_ptr<int>(ws, pl->mel_tmin), nt, (int)0x7fffffff);
     }
     if (launch_logmel(src, items, n, pl->max_mel_tiles, pl->ctx->c, pick_mel(pl), pl->p.mel_padding, peak_normalize,
-                      ws_ptr<PeakNorm>(ws, pl->pnorm), gates, out16, mel, ws_ptr<int>(ws, pl->mel_max), ws_ptr<int>(ws, pl->mel_tmin), st))
+                      ws_ptr<PeakNorm>(ws, pl->pnorm), peak_normalize ? norm16 : nullptr, gates, out16, mel, ws_ptr<int>(ws, pl->mel_max), ws_ptr<int>(ws, pl->mel_tmin), st))
         return fail(MAF_ERR_UNSUPPORTED, "log-mel tile count exceeds 2^31");
     pl->launches += 3;
     mark(pl, ST_LOGMEL, st);
@@ -772,13 +774,13 @@ extern "C" int maf_process(maf_plan* pl, const int16_t* pcm, const int16_t* nois
     int16_t* den16 = ws_ptr<int16_t>(ws, pl->den16);
     int rc = run_denoise(pl, pcm, noise_pcm, ws, den16, 0, nullptr, st);
     if (rc) return rc;
-    rc = run_loudness_stats(pl, den16, pl->d_items, pl->p.peak_normalize, ws, st);
+    rc = run_loudness_stats(pl, den16, pl->d_items, pl->p.peak_normalize, ws, st, ws_ptr<int16_t>(ws, pl->norm16));
     if (rc) return rc;
     rc = run_gate(pl, pl->d_items, ws, st);
     if (rc) return rc;
     const Gate* gates = ws_ptr<Gate>(ws, pl->gates);
     if (pl->p.n_mels) {
-        rc = run_logmel(pl, den16, pl->d_items, pl->p.peak_normalize, gates, ws, out_pcm, mel, true, st);
+        rc = run_logmel(pl, den16, pl->d_items, pl->p.peak_normalize, gates, ws, out_pcm, mel, true, st, ws_ptr<int16_t>(ws, pl->norm16));
         if (rc) return rc;
     } else {
         launch_apply_gain(den16, pl->d_items, pl->n_items, pl->max_own, pl->p.peak_normalize, ws_ptr<PeakNorm>(ws, pl->pnorm), gates, 1,
@@ -1117,7 +1119,8 @@ extern "C" int maf_sharded_denoise(maf_plan* pl, const int16_t* pcm, const int16
 extern "C" int maf_sharded_energy(maf_plan* pl, void* ws, void* stream) {
     if (!pl || !ws) return fail(MAF_ERR_INVALID, "maf_sharded_energy: NULL argument");
     CU(cudaSetDevice(pl->ctx->device));
-    return run_loudness_stats(pl, ws_ptr<int16_t>(ws, pl->den16), pl->d_items, pl->p.peak_normalize, ws, (cudaStream_t)stream);
+    return run_loudness_stats(pl, ws_ptr<int16_t>(ws, pl->den16), pl->d_items, pl->p.peak_normalize, ws, (cudaStream_t)stream,
+                              ws_ptr<int16_t>(ws, pl->norm16));
 }
 
 extern "C" int maf_gate(maf_ctx* ctx, const double* sub_energy, int64_t n_tiles, int64_t n_blocks, int32_t sr, float target_lufs,
@@ -1140,7 +1143,7 @@ extern "C" int maf_sharded_logmel(maf_plan* pl, void* ws, const void* gate, int1
     if (pl->n_items != 1) return fail(MAF_ERR_INVALID, "maf_sharded_logmel: one shard per plan");
     CU(cudaSetDevice(pl->ctx->device));
     return run_logmel(pl, ws_ptr<int16_t>(ws, pl->den16), pl->d_items, pl->p.peak_normalize, (const Gate*)gate, ws, out_pcm, mel, false,
-                      (cudaStream_t)stream);
+                      (cudaStream_t)stream, ws_ptr<int16_t>(ws, pl->norm16));
 }
 
 extern "C" int maf_mel_finalize(maf_plan* pl, void* ws, float* mel, void* stream) {

@@ -30,8 +30,8 @@ struct MelTile {            // geometry of one (item, 32-frame tile) unit
 // the NEXT tile are fetched into registers before the current tile's FFT phases, so no global-load latency is exposed.
 __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__ den16, const Item* __restrict__ items, int n_items,
                                                      int max_tiles, Consts cs, MelBank mel, int padding, int peak_normalize,
-                                                     const PeakNorm* __restrict__ pnorm, const Gate* __restrict__ gates,
-                                                     int16_t* __restrict__ out16, float* __restrict__ mel_out,
+                                                     const PeakNorm* __restrict__ pnorm, const int16_t* __restrict__ norm16,
+                                                     const Gate* __restrict__ gates, int16_t* __restrict__ out16, float* __restrict__ mel_out,
                                                      int* __restrict__ mel_max, int* __restrict__ tile_min) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* span = reinterpret_cast<float*>(smem_raw);
@@ -58,8 +58,9 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
         g.own_lo = g.i0 + W_NFFT / 2;
         g.own_hi = g.last_tile ? it.g0 + it.own_len : g.own_lo + (long long)MEL_TILE * W_HOP;
         g.l0 = g.i0 - it.g0;                                        // item-relative index of span[0]
-        g.interior = g.i0 >= 0 && g.i0 + MEL_SPAN <= it.n_global && g.l0 >= -(long long)it.lo_avail &&
-                     g.l0 + MEL_SPAN <= it.own_len + it.hi_avail && ((it.den_off + g.l0) & 7) == 0 && !g.last_tile &&
+        // (norm16, the peak-normalised copy kweight_energy_kernel leaves behind, covers the own range only: no halos)
+        g.interior = g.i0 >= 0 && g.i0 + MEL_SPAN <= it.n_global && g.l0 >= (norm16 ? 0LL : -(long long)it.lo_avail) &&
+                     g.l0 + MEL_SPAN <= it.own_len + (norm16 ? 0 : it.hi_avail) && ((it.den_off + g.l0) & 7) == 0 && !g.last_tile &&
                      (!out16 || (((it.out_off + g.l0) & 7) == 0 && g.l0 + W_NFFT / 2 >= 0 && g.l0 + W_NFFT / 2 + MEL_TILE * W_HOP <= it.own_len));
         return true;
     };
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     uint4 pre[PRE];
     auto fetch = [&](const MelTile& g) {                            // interior fast path only: raw samples -> registers
         if (!g.interior) return;
-        const int16_t* x = den16 + items[g.item].den_off + g.l0;
+        const int16_t* x = (norm16 ? norm16 : den16) + items[g.item].den_off + g.l0;
 #pragma unroll
         for (int u = 0; u < PRE; ++u) {
             const int gq = tid + 256 * u;
@@ -113,23 +114,44 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
                 const int gq = tid + 256 * u;
                 if (gq >= MEL_SPAN / 8) break;
                 const uint4 v = pre[u];
-                int sv[8];
-                sv[0] = (short)(v.x & 0xffff); sv[1] = (short)(v.x >> 16); sv[2] = (short)(v.y & 0xffff); sv[3] = (short)(v.y >> 16);
-                sv[4] = (short)(v.z & 0xffff); sv[5] = (short)(v.z >> 16); sv[6] = (short)(v.w & 0xffff); sv[7] = (short)(v.w >> 16);
+                const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
                 float a[8];
+                uint32_t ow[4];
+                if (norm16 || !pn) {
+                    // the samples are final up to the loudness gain (peak normalisation done by kweight_energy_kernel, or off):
+                    // int16 -> float by byte permutation (0x4B00'0000 | (s ^ 0x8000) = 2^23 + 32768 + s), gain, limiter, clamp,
+                    // truncation; the low 16 bits of (q + 1.5 * 2^23) are q's two's complement, so the int16 pair is one permute
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    float qf;
-                    sv[e] = norm_gain_sample(sv[e], pn, pnv, gt, dv, qf);
-                    a[e] = qf * (1.0f / 32768.0f);
+                    for (int h = 0; h < 4; ++h) {
+                        const uint32_t b = wv[h] ^ 0x80008000u;
+                        float t0 = __fadd_rn(__uint_as_float(__byte_perm(b, 0x4B000000u, 0x7410)), -8421376.0f);
+                        float t1 = __fadd_rn(__uint_as_float(__byte_perm(b, 0x4B000000u, 0x7432)), -8421376.0f);
+                        if (gt.applied) {
+                            t0 = __fmul_rn(gt.gain, t0); t1 = __fmul_rn(gt.gain, t1);
+                            if (gt.lim) { t0 = div_by(t0, dv); t1 = div_by(t1, dv); }
+                            t0 = truncf(fminf(fmaxf(t0, -32768.0f), 32767.0f));
+                            t1 = truncf(fminf(fmaxf(t1, -32768.0f), 32767.0f));
+                            ow[h] = __byte_perm(__float_as_uint(__fadd_rn(t0, MAGIC_F)), __float_as_uint(__fadd_rn(t1, MAGIC_F)), 0x5410);
+                        } else {
+                            ow[h] = wv[h];
+                        }
+                        a[2 * h] = t0 * (1.0f / 32768.0f); a[2 * h + 1] = t1 * (1.0f / 32768.0f);
+                    }
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        float q0, q1;
+                        const int s0 = norm_gain_sample((int)(short)(wv[h] & 0xffffu), pn, pnv, gt, dv, q0);
+                        const int s1 = norm_gain_sample((int)wv[h] >> 16, pn, pnv, gt, dv, q1);
+                        a[2 * h] = q0 * (1.0f / 32768.0f); a[2 * h + 1] = q1 * (1.0f / 32768.0f);
+                        ow[h] = ((uint32_t)s0 & 0xffffu) | ((uint32_t)s1 << 16);
+                    }
                 }
                 *reinterpret_cast<float4*>(span + 8 * gq) = make_float4(a[0], a[1], a[2], a[3]);
                 *reinterpret_cast<float4*>(span + 8 * gq + 4) = make_float4(a[4], a[5], a[6], a[7]);
                 const int e0 = 8 * gq;
                 if (out16 && e0 >= W_NFFT / 2 && e0 < W_NFFT / 2 + MEL_TILE * W_HOP) {
-                    uint4 o;
-                    o.x = (uint32_t)(sv[0] & 0xffff) | ((uint32_t)sv[1] << 16); o.y = (uint32_t)(sv[2] & 0xffff) | ((uint32_t)sv[3] << 16);
-                    o.z = (uint32_t)(sv[4] & 0xffff) | ((uint32_t)sv[5] << 16); o.w = (uint32_t)(sv[6] & 0xffff) | ((uint32_t)sv[7] << 16);
+                    const uint4 o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                     *reinterpret_cast<uint4*>(out16 + it.out_off + l0 + e0) = o;
                 }
             }
@@ -167,8 +189,9 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
             const int n = j + 25 * m;
-            const float* s = span + lf * W_HOP + 2 * n;
-            v[m] = mk(s[0] * win[2 * n], s[1] * win[2 * n + 1]);
+            const float2 sp = *reinterpret_cast<const float2*>(span + lf * W_HOP + 2 * n);        // 8-byte aligned: every term is even
+            const float2 wn = *reinterpret_cast<const float2*>(win + 2 * n);
+            v[m] = mk(sp.x * wn.x, sp.y * wn.y);
         }
         fft200_stepA(v, zb + lf * Z_PITCH, twA, j);
     }
@@ -249,7 +272,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
 }
 
 int launch_logmel(const int16_t* den16, const Item* items, int n_items, int max_tiles, const Consts& c,
-                   const MelBank& mel, int padding, int peak_normalize, const PeakNorm* pnorm,
+                   const MelBank& mel, int padding, int peak_normalize, const PeakNorm* pnorm, const int16_t* norm16,
                    const Gate* gates, int16_t* out16, float* mel_out, int* mel_max, int* tile_min, cudaStream_t st) {
     if (n_items <= 0) return 0;
     cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOGMEL_SMEM);
@@ -259,7 +282,7 @@ int launch_logmel(const int16_t* den16, const Item* items, int n_items, int max_
     const long long total = (long long)n_items * max_tiles;
     if (total >= (1LL << 31) - 4096) return -1;                    // maf_plan_create rejects such plans; never skip work silently
     const int grid = (int)(total < 2LL * n_sm ? total : 2LL * n_sm);
-    logmel_kernel<<<grid, 256, LOGMEL_SMEM, st>>>(den16, items, n_items, max_tiles, c, mel, padding, peak_normalize, pnorm, gates, out16,
+    logmel_kernel<<<grid, 256, LOGMEL_SMEM, st>>>(den16, items, n_items, max_tiles, c, mel, padding, peak_normalize, pnorm, norm16, gates, out16,
                                                   mel_out, mel_max, tile_min);
     return 0;
 }

@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
                                                                         int tile_len, int seg_rt, int lpt, int tpc, KWeight kw,
                                                                         const KwScan* __restrict__ tab, int peak_normalize,
                                                                         const PeakNorm* __restrict__ pnorm,
-                                                                        double* __restrict__ sub_energy, int* __restrict__ peak_norm) {
+                                                                        double* __restrict__ sub_energy, int* __restrict__ peak_norm,
+                                                                        int16_t* __restrict__ norm16) {
     extern __shared__ __align__(16) unsigned char kw_smem[];
     double* e_lane = reinterpret_cast<double*>(kw_smem);                         // [blockDim.x] lane energies
     double* e_warp = e_lane + blockDim.x;                                        // [32][4] zero-state end state of each warp
@@ -102,12 +103,26 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
             wv[h] = ((uint32_t)s0 & 0xffffu) | ((uint32_t)s1 << 16);
         }
         if (pn) *reinterpret_cast<uint4*>(xs + 8 * g8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        {
+            // the peak-normalised samples of the sub-blocks this CTA OWNS (everything past the warm-up sub-block) also go to
+            // global memory: logmel_kernel applies the loudness gain to them instead of redoing the audioop.mul floor
+            if (norm16 && 8 * g8 + 8 > tile_len && li + 8 > 0 && li < it.own_len) {
+                if (8 * g8 >= tile_len && li >= 0 && li + 8 <= it.own_len && ((it.den_off + li) & 7) == 0) {
+                    *reinterpret_cast<uint4*>(norm16 + it.den_off + li) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (8 * g8 + e >= tile_len && li + e >= 0 && li + e < it.own_len) norm16[it.den_off + li + e] = xs[8 * g8 + e];
+                }
+            }
+        }
     }
     for (int i = (span / 8) * 8 + tid; i < span; i += blockDim.x) {
         int sv = xs[i];
         if (pn) sv = peak_norm_sample_fast(sv, pnv);
         if (c0 + i >= 0) pk = max(pk, abs(sv));
         xs[i] = (int16_t)sv;
+        if (norm16 && i >= tile_len && c0 + i >= 0 && c0 + i < it.own_len) norm16[it.den_off + c0 + i] = (int16_t)sv;
     }
     __syncthreads();
 
@@ -205,7 +220,7 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
 
 void launch_kweight_energy(const int16_t* den16, const Item* items, int n_items, int max_groups, int tile_len, const KwGeom& geo,
                            const KWeight& kw, const KwScan* tab, int peak_normalize, const PeakNorm* pnorm,
-                           double* sub_energy, int* peak_norm, cudaStream_t st) {
+                           double* sub_energy, int* peak_norm, int16_t* norm16, cudaStream_t st) {
     if (n_items <= 0 || max_groups <= 0) return;
     const size_t smem = sizeof(double) * (geo.threads + 128 + 6 * 16 + 16 * 32) + sizeof(float4) * KW_MAX_SEG + sizeof(int16_t) * (size_t)(geo.tpc + 1) * tile_len + 16;
     auto kern = geo.seg == 50 ? kweight_energy_kernel<50> : kweight_energy_kernel<0>;
@@ -214,7 +229,7 @@ void launch_kweight_energy(const int16_t* den16, const Item* items, int n_items,
         const int ny = n_items - y0 < 32768 ? n_items - y0 : 32768;
         dim3 grid(max_groups, ny);
         kern<<<grid, geo.threads, smem, st>>>(den16, items + y0, tile_len, geo.seg, geo.lpt, geo.tpc, kw, tab, peak_normalize,
-                                                               pnorm ? pnorm + y0 : nullptr, sub_energy, peak_norm + y0);
+                                                               pnorm ? pnorm + y0 : nullptr, sub_energy, peak_norm + y0, norm16);
     }
 }
 
