@@ -239,19 +239,24 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
                 const float4 w = wts[i];
                 a0 = fmaf(w.x, pv, a0); a1 = fmaf(w.y, pv, a1); a2 = fmaf(w.z, pv, a2); a3 = fmaf(w.w, pv, a3);
             }
-            // lg2.approx: |err| < 3e-6 in log10 units
-            const float l0 = __log2f(fmaxf(a0, 1e-10f)) * 0.30102999566398120f, l1 = __log2f(fmaxf(a1, 1e-10f)) * 0.30102999566398120f;
-            const float l2 = __log2f(fmaxf(a2, 1e-10f)) * 0.30102999566398120f, l3 = __log2f(fmaxf(a3, 1e-10f)) * 0.30102999566398120f;
+            // lg2.approx (|err| < 3e-6 in log10 units; the clamp keeps the argument normal, so the .ftz form needs no denormal
+            // fix-up) and (log10 + 4) / 4 as ONE fused multiply-add: 1 + lg2 * (log10(2) / 4)
+            auto sc = [](float a) {
+                float l;
+                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fmaxf(a, 1e-10f)));
+                return fmaf(l, 0.30102999566398120f * 0.25f, 1.0f);
+            };
+            const float l0 = sc(a0), l1 = sc(a1), l2 = sc(a2), l3 = sc(a3);
             if (valid) {
                 float* o = orow + (long long)(4 * q) * it.mel_frames;
-                // written already scaled, (L + 4) / 4; the max - 8 clamp is applied afterwards only to tiles that need it
-                // (division by 4 is exact in binary floating point: multiply by 0.25)
-                o[0] = __fmul_rn(__fadd_rn(l0, 4.0f), 0.25f); o[it.mel_frames] = __fmul_rn(__fadd_rn(l1, 4.0f), 0.25f);
-                o[2LL * it.mel_frames] = __fmul_rn(__fadd_rn(l2, 4.0f), 0.25f); o[3LL * it.mel_frames] = __fmul_rn(__fadd_rn(l3, 4.0f), 0.25f);
+                // written already scaled; the max - 8 clamp is applied afterwards only to tiles that need it
+                o[0] = l0; o[it.mel_frames] = l1; o[2LL * it.mel_frames] = l2; o[3LL * it.mel_frames] = l3;
                 bmax = fmaxf(fmaxf(bmax, fmaxf(l0, l1)), fmaxf(l2, l3));
                 bmin = fminf(fminf(bmin, fminf(l0, l1)), fminf(l2, l3));
             }
         }
+        // back to log10 units for the recording-wide maximum and the tile minimum (scaling is monotonic)
+        bmax = fmaf(bmax, 4.0f, -4.0f); bmin = fmaf(bmin, 4.0f, -4.0f);
         bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, 16));
         bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, 8));
         bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, 4));

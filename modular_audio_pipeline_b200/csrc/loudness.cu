@@ -88,21 +88,56 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
         xs[i] = (li >= -(long long)it.lo_avail && li < it.own_len) ? x[li] : (int16_t)0;
     }
     asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
-    // stage 2 (same thread <-> same groups, so no barrier in between): peak normalisation in place, peak of the result
+    // stage 2 (same thread <-> same groups, so no barrier in between): peak normalisation in place, peak of the result.
+    // Eight samples at a time, branch-free: int16 -> float by byte permutation (0x4B00'0000 | (s ^ 0x8000) = 2^23 + 32768 + s),
+    // the two-float audioop.mul floor of peak_norm_sample_fastf, ONE test per group for "some sample is too close to an
+    // integer to decide in float32" (about two samples per million: that group is redone through the float64 path), the
+    // int16 pair rebuilt with one permute from the low halves of (q + 1.5 * 2^23), per-halfword |.| / max for the peak.
     int pk = 0;
+    uint32_t pk2 = 0;
     for (int g8 = tid; g8 < span / 8; g8 += blockDim.x) {
         const long long li = c0 + 8 * g8;
         uint4 o = *reinterpret_cast<const uint4*>(xs + 8 * g8);
         uint32_t wv[4] = {o.x, o.y, o.z, o.w};
+        if (pn) {
+            float tf[8];
+            bool undecided = false;
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            int s0 = (int)(short)(wv[h] & 0xffffu), s1 = (int)wv[h] >> 16;
-            if (pn) { s0 = peak_norm_sample_fast(s0, pnv); s1 = peak_norm_sample_fast(s1, pnv); }
-            if (li + 2 * h >= 0) pk = max(pk, abs(s0));
-            if (li + 2 * h + 1 >= 0) pk = max(pk, abs(s1));
-            wv[h] = ((uint32_t)s0 & 0xffffu) | ((uint32_t)s1 << 16);
+            for (int h = 0; h < 4; ++h) {
+                const uint32_t bw = wv[h] ^ 0x80008000u;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float sf = __fadd_rn(__uint_as_float(__byte_perm(bw, 0x4B000000u, e ? 0x7432 : 0x7410)), -8421376.0f);
+                    const float p = __fmul_rn(sf, pnv.fh);
+                    const float lo = fmaf(sf, pnv.fl, fmaf(sf, pnv.fh, -p));
+                    const float t = floorf(p);
+                    const float fr = __fadd_rn(__fadd_rn(p, -t), lo);
+                    undecided |= !(fabsf(fr - 0.5f) < 0.499999f) && sf != 0.0f;
+                    tf[2 * h + e] = t;
+                }
+            }
+            if (__builtin_expect(undecided, 0)) {
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    tf[2 * h] = peak_norm_sample_fastf((int)(short)(wv[h] & 0xffffu), pnv);
+                    tf[2 * h + 1] = peak_norm_sample_fastf((int)wv[h] >> 16, pnv);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+                wv[h] = __byte_perm(__float_as_uint(__fadd_rn(tf[2 * h], MAGIC_F)), __float_as_uint(__fadd_rn(tf[2 * h + 1], MAGIC_F)), 0x5410);
+            *reinterpret_cast<uint4*>(xs + 8 * g8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
         }
-        if (pn) *reinterpret_cast<uint4*>(xs + 8 * g8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        if (li >= 0) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) pk2 = __vmaxu2(pk2, __vabs2(wv[h]));          // |-32768| = 0x8000 compares as 32768 unsigned
+        } else {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                if (li + 2 * h >= 0) pk = max(pk, abs((int)(short)(wv[h] & 0xffffu)));
+                if (li + 2 * h + 1 >= 0) pk = max(pk, abs((int)wv[h] >> 16));
+            }
+        }
         {
             // the peak-normalised samples of the sub-blocks this CTA OWNS (everything past the warm-up sub-block) also go to
             // global memory: logmel_kernel applies the loudness gain to them instead of redoing the audioop.mul floor
@@ -112,11 +147,13 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
                 } else {
 #pragma unroll
                     for (int e = 0; e < 8; ++e)
-                        if (8 * g8 + e >= tile_len && li + e >= 0 && li + e < it.own_len) norm16[it.den_off + li + e] = xs[8 * g8 + e];
+                        if (8 * g8 + e >= tile_len && li + e >= 0 && li + e < it.own_len)
+                            norm16[it.den_off + li + e] = (int16_t)((wv[e >> 1] >> (16 * (e & 1))) & 0xffffu);
                 }
             }
         }
     }
+    pk = max(pk, max((int)(pk2 & 0xffffu), (int)(pk2 >> 16)));
     for (int i = (span / 8) * 8 + tid; i < span; i += blockDim.x) {
         int sv = xs[i];
         if (pn) sv = peak_norm_sample_fast(sv, pnv);
@@ -134,11 +171,25 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
     double e[4] = {0.0, 0.0, 0.0, 0.0};
     if (live) {
         float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+        if constexpr (SEG > 0 && SEG % 2 == 0) {
+            // two samples per 32-bit shared-memory word; int16 -> float by byte permutation (see stage 2)
+            const uint32_t* xw = reinterpret_cast<const uint32_t*>(xl);
+#pragma unroll 5
+            for (int i = 0; i < SEG / 2; ++i) {
+                const uint32_t bw = xw[i] ^ 0x80008000u;
+                const float x0 = __fadd_rn(__uint_as_float(__byte_perm(bw, 0x4B000000u, 0x7410)), -8421376.0f);
+                const float x1 = __fadd_rn(__uint_as_float(__byte_perm(bw, 0x4B000000u, 0x7432)), -8421376.0f);
+                const float4 h0 = hs[2 * i], h1 = hs[2 * i + 1];
+                f0 = fmaf(h0.x, x0, f0); f1 = fmaf(h0.y, x0, f1); f2 = fmaf(h0.z, x0, f2); f3 = fmaf(h0.w, x0, f3);
+                f0 = fmaf(h1.x, x1, f0); f1 = fmaf(h1.y, x1, f1); f2 = fmaf(h1.z, x1, f2); f3 = fmaf(h1.w, x1, f3);
+            }
+        } else {
 #pragma unroll 10
-        for (int i = 0; i < seg; ++i) {
-            const float xv = int_to_float_exact((int)xl[i]);
-            const float4 h = hs[i];
-            f0 = fmaf(h.x, xv, f0); f1 = fmaf(h.y, xv, f1); f2 = fmaf(h.z, xv, f2); f3 = fmaf(h.w, xv, f3);
+            for (int i = 0; i < seg; ++i) {
+                const float xv = int_to_float_exact((int)xl[i]);
+                const float4 h = hs[i];
+                f0 = fmaf(h.x, xv, f0); f1 = fmaf(h.y, xv, f1); f2 = fmaf(h.z, xv, f2); f3 = fmaf(h.w, xv, f3);
+            }
         }
         e[0] = (double)f0; e[1] = (double)f1; e[2] = (double)f2; e[3] = (double)f3;
     }
@@ -186,17 +237,33 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
         const long long li0 = c0 + (long long)tid * seg;
         const int n_own = (int)max(0LL, min((long long)seg, it.own_len - li0));      // samples of this segment inside the recording
         const int n_run = SEG ? SEG : n_own;
-#pragma unroll 10
-        for (int i = 0; i < n_run; ++i) {
-            const float xv = int_to_float_exact((int)xl[i]) * (1.0f / 32768.0f);
-            const float y1 = fmaf(b10, xv, s0);
-            s0 = fmaf(-a11, y1, fmaf(b11, xv, s1));
-            s1 = fmaf(-a12, y1, b12 * xv);
+        // (x / 32768 is an exact scaling, so it is folded into the three shelf numerator coefficients: b (x 2^-15) == (b 2^-15) x)
+        const float c10 = b10 * (1.0f / 32768.0f), c11 = b11 * (1.0f / 32768.0f), c12 = b12 * (1.0f / 32768.0f);
+        auto step = [&](float xr, bool own) {
+            const float y1 = fmaf(c10, xr, s0);
+            s0 = fmaf(-a11, y1, fmaf(c11, xr, s1));
+            s1 = fmaf(-a12, y1, c12 * xr);
             const float y2 = fmaf(hb0, y1, h1);
             const float nh1 = fmaf(-d1, y2, fmaf(2.0f, h1, h2));
             h2 = fmaf(d2, y2, -h1);
             h1 = nh1;
-            if (!SEG || i < n_own) acc = fmaf(y2, y2, acc);
+            if (own) acc = fmaf(y2, y2, acc);
+        };
+        if constexpr (SEG > 0 && SEG % 2 == 0) {
+            const uint32_t* xw = reinterpret_cast<const uint32_t*>(xl);
+            if (n_own >= SEG) {                                                      // the whole segment lies inside the recording
+#pragma unroll 5
+                for (int i = 0; i < SEG / 2; ++i) {
+                    const uint32_t bw = xw[i] ^ 0x80008000u;
+                    step(__fadd_rn(__uint_as_float(__byte_perm(bw, 0x4B000000u, 0x7410)), -8421376.0f), true);
+                    step(__fadd_rn(__uint_as_float(__byte_perm(bw, 0x4B000000u, 0x7432)), -8421376.0f), true);
+                }
+            } else {
+                for (int i = 0; i < n_own; ++i) step(int_to_float_exact((int)xl[i]), true);
+            }
+        } else {
+#pragma unroll 10
+            for (int i = 0; i < n_run; ++i) step(int_to_float_exact((int)xl[i]), !SEG || i < n_own);
         }
     }
     e_lane[tid] = (double)acc;
