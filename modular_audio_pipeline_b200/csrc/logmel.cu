@@ -22,7 +22,7 @@ constexpr size_t LOGMEL_SMEM = sizeof(float) * MEL_SPAN + sizeof(c32) * MEL_TILE
 
 struct MelTile {            // geometry of one (item, 32-frame tile) unit
     int item, lf0;
-    long long i0, l0, own_lo, own_hi;
+    long long i0, l0, own_lo, own_hi, den_off;
     bool last_tile, interior;
 };
 
@@ -46,12 +46,19 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     int* m_qoff = m_qcount + MEL_SLOTS_MAX;
     int* m_qrow = m_qoff + MEL_SLOTS_MAX;
     const int tid = threadIdx.x;
+    // descriptor / peak factor / gate of the item the CTA is working on, fetched once per ITEM instead of once per tile (a long
+    // recording is thousands of tiles of the same item: the global-load latency of the descriptor sat at the top of every tile)
+    __shared__ Item s_item;
+    __shared__ PeakNorm s_pn;
+    __shared__ Gate s_gt;
+    int cached = -1;
 
     const unsigned total = (unsigned)n_items * (unsigned)max_tiles;            // < 2^31 (checked by the launcher): 32-bit index math
     auto geom = [&](unsigned t, MelTile& g) {
         g.item = (int)(t / (unsigned)max_tiles);
         g.lf0 = (int)(t - (unsigned)g.item * (unsigned)max_tiles) * MEL_TILE;
-        const Item& it = items[g.item];
+        const Item& it = g.item == cached ? s_item : items[g.item];
+        g.den_off = it.den_off;
         if (g.lf0 >= it.mel_frames) return false;
         g.i0 = ((long long)it.mel_f0 + g.lf0) * W_HOP - W_NFFT / 2;
         g.last_tile = g.lf0 + MEL_TILE >= it.mel_frames;
@@ -68,7 +75,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     uint4 pre[PRE];
     auto fetch = [&](const MelTile& g) {                            // interior fast path only: raw samples -> registers
         if (!g.interior) return;
-        const int16_t* x = (norm16 ? norm16 : den16) + items[g.item].den_off + g.l0;
+        const int16_t* x = (norm16 ? norm16 : den16) + g.den_off + g.l0;
 #pragma unroll
         for (int u = 0; u < PRE; ++u) {
             const int gq = tid + 256 * u;
@@ -90,13 +97,19 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
 
   while (t < total) {
     const int item = cur.item;
-    const Item it = items[item];
+    if (item != cached) {                                           // CTA-uniform
+        __syncthreads();                                            // nobody still reads the previous item's copy
+        if (tid < (int)(sizeof(Item) / 4)) reinterpret_cast<int*>(&s_item)[tid] = reinterpret_cast<const int*>(items + item)[tid];
+        if (tid == 64) { PeakNorm v; v.factor = 1.0; v.fh = 1.0f; v.fl = 0.f; v.active = 0; v.pad_ = 0; if (peak_normalize) v = pnorm[item]; s_pn = v; }
+        if (tid == 96) { Gate v; v.lufs = 0.0; v.gain = 1.0f; v.limp = 1.0f; v.applied = 0; v.lim = 0; if (gates) v = gates[item]; s_gt = v; }
+        cached = item;
+        __syncthreads();
+    }
+    const Item& it = s_item;
     const int lf0 = cur.lf0;
-    PeakNorm pnv; pnv.active = 0;
-    if (peak_normalize) pnv = pnorm[item];
+    const PeakNorm pnv = s_pn;
     const bool pn = pnv.active != 0;
-    Gate gt; gt.applied = 0; gt.lim = 0; gt.limp = 1.0f;
-    if (gates) gt = gates[item];
+    const Gate gt = s_gt;
     const DivConst dv = limiter_div(gt);
     const int16_t* x = den16 + it.den_off;
     const long long np_global = it.n_global + padding;            // length of the zero-padded recording
@@ -182,18 +195,33 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     if (tn < total) fetch(nxt);
     __syncthreads();
 
-    // stage A: (frame, j) -> 8-point FFT over m of z[j + 25 m], twiddle, store
-    for (int w = tid; w < MEL_TILE * 25; w += 256) {
-        const int lf = w / 25, j = w - lf * 25;
-        c32 v[8];
+    // stage A: (frame, j) -> 8-point FFT over m of z[j + 25 m], twiddle, store.  Thread = (j, frame group): j is FIXED per
+    // thread, so its 16 window values and 7 twiddles are read once per tile instead of once per transform, and the four
+    // transforms of a thread (frames fg, fg + 8, fg + 16, fg + 24) need only their 8 sample pairs from shared memory.
+    if (tid < 200) {
+        const int j = tid % 25, fg = tid / 25;
+        float2 wn[8];
+        c32 twj[8];
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int n = j + 25 * m;
-            const float2 sp = *reinterpret_cast<const float2*>(span + lf * W_HOP + 2 * n);        // 8-byte aligned: every term is even
-            const float2 wn = *reinterpret_cast<const float2*>(win + 2 * n);
-            v[m] = mk(sp.x * wn.x, sp.y * wn.y);
+        for (int m = 0; m < 8; ++m) wn[m] = *reinterpret_cast<const float2*>(win + 2 * (j + 25 * m));
+#pragma unroll
+        for (int p = 1; p < 8; ++p) twj[p] = twA[p * 25 + j];
+#pragma unroll 2
+        for (int r = 0; r < MEL_TILE / 8; ++r) {
+            const int lf = fg + 8 * r;
+            const float* sp0 = span + lf * W_HOP + 2 * j;
+            c32 v[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const float2 sp = *reinterpret_cast<const float2*>(sp0 + 50 * m);        // 8-byte aligned: every term is even
+                v[m] = mk(sp.x * wn[m].x, sp.y * wn[m].y);
+            }
+            fft8(v);
+            c32* zo = zb + lf * Z_PITCH + j;
+            zo[0] = v[0];
+#pragma unroll
+            for (int p = 1; p < 8; ++p) zo[p * 25] = cmul(v[p], twj[p]);
         }
-        fft200_stepA(v, zb + lf * Z_PITCH, twA, j);
     }
     __syncthreads();
     // stage B: (frame, p) -> 25-point DFT in registers; exactly one round, so the in-place write is safe after a barrier
@@ -206,16 +234,25 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
         for (int q = 0; q < 25; ++q) zb[lf * Z_PITCH + p + 8 * q] = o[q];
     }
     __syncthreads();
-    // real split + power: one work item = (frame, k <= 100) produces bins k and 200 - k from the same two loads
-    for (int idx = tid; idx < MEL_TILE * 101; idx += 256) {
-        const int lf = idx / 101, k = idx - lf * 101;
-        const c32* z = zb + lf * Z_PITCH;
-        const c32 za = z[k], zn = z[k == 0 ? 0 : 200 - k];
+    // real split + power: one work item = (frame, k <= 100) produces bins k and 200 - k from the same two loads.  Thread =
+    // (k, frame parity): k, its twiddle and every address offset are fixed per thread; the 16 frames of a thread are a
+    // constant stride apart (no division, no per-item twiddle load).
+    if (tid < 202) {
+        const int k = tid % 101, fg = tid / 101;
         const c32 tw = tw400[k];
-        const c32 Xa = rfft400_bin(za, zn, tw);
-        const c32 Xb = rfft400_bin(zn, za, mk(-tw.x, tw.y));            // e^{-2 pi i (200 - k) / 400} = -conj(e^{-2 pi i k / 400})
-        pw[lf * P_PITCH + k] = Xa.x * Xa.x + Xa.y * Xa.y;
-        pw[lf * P_PITCH + 200 - k] = Xb.x * Xb.x + Xb.y * Xb.y;
+        const c32 twn = mk(-tw.x, tw.y);                                // e^{-2 pi i (200 - k) / 400} = -conj(e^{-2 pi i k / 400})
+        const int kn = k == 0 ? 0 : 200 - k;
+        const c32* z = zb + fg * Z_PITCH;
+        float* po = pw + fg * P_PITCH;
+#pragma unroll 4
+        for (int r = 0; r < MEL_TILE / 2; ++r) {
+            const c32 za = z[k], zn = z[kn];
+            const c32 Xa = rfft400_bin(za, zn, tw);
+            const c32 Xb = rfft400_bin(zn, za, twn);
+            po[k] = Xa.x * Xa.x + Xa.y * Xa.y;
+            po[200 - k] = Xb.x * Xb.x + Xb.y * Xb.y;
+            z += 2 * Z_PITCH; po += 2 * P_PITCH;
+        }
     }
     __syncthreads();
     // mel projection: warp-uniform quad of four adjacent mel rows, lane = frame (coalesced 128 B row segments of the
