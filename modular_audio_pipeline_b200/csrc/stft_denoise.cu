@@ -75,6 +75,13 @@ __device__ __forceinline__ void stft_stage_span(int16_t* span, const int16_t* __
     const long long j0 = (long long)f0 * HOP - NFFT / 2;              // padded-chunk coordinate of span[0]
     const long long li0 = ch.s_local - PADS + j0;                     // local buffer index of span[0]
     const int16_t* base = pcm + it.pcm_off;
+    if (j0 >= 0 && j0 + STFT_SPAN <= ch.L && li0 >= 0 && li0 + STFT_SPAN <= it.buf_len && ((it.pcm_off + li0) & 7) == 0) {
+        // the whole span lies inside the padded chunk and the recording (all but a chunk's first / last tiles): no per-group tests
+        const int16_t* src = base + li0;
+#pragma unroll
+        for (int g = tid; g < STFT_SPAN / 8; g += 32 * STFT_WARPS) cp_async16(&span[8 * g], src + 8 * g);
+        return;
+    }
     for (int g = tid; g < STFT_SPAN / 8; g += 32 * STFT_WARPS) {
         const long long j = j0 + 8 * g, li = li0 + 8 * g;
         if (j >= 0 && j + 8 <= ch.L && li >= 0 && li + 8 <= it.buf_len && ((it.pcm_off + li) & 7) == 0) {
@@ -248,15 +255,23 @@ __global__ void __launch_bounds__(32 * STFT_WARPS, 2) stft1024_kernel(const int1
             for (int k1 = 0; k1 < 16; ++k1) { gp[32 * k1 + lane] = accP[k1]; gp[T_PITCH + 32 * k1 + lane] = accQ[k1]; }
             if (lane == 0) { gp[512] = accP[16]; gp[T_PITCH + 512] = accQ[16]; }
             __syncthreads();
+            // threads 0..127 add the P rows, 128..255 the Q rows, four bins each (16-byte shared loads, one 16-byte store;
+            // same warp order as a scalar loop, so the sums are bit-identical); bin 512 by the first thread of each half
             const long long trow = (ch.tile0 + tile) * T_PITCH;
-            for (int k = tid; k < NBIN; k += 32 * STFT_WARPS) {
-                float p = 0.f, q = 0.f;
+            {
+                const int half = tid >> 7, k4 = 4 * (tid & 127);
+                float* dst = (half ? Q : P) + trow;
+                float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                float a512 = 0.f;
 #pragma unroll
                 for (int w = 0; w < STFT_WARPS; ++w) {
-                    const float* g = reinterpret_cast<const float*>(scratch + w * FFT1024_SMEM);
-                    p += g[k]; q += g[T_PITCH + k];
+                    const float* g = reinterpret_cast<const float*>(scratch + w * FFT1024_SMEM) + half * T_PITCH;
+                    const float4 x = *reinterpret_cast<const float4*>(g + k4);
+                    acc4.x += x.x; acc4.y += x.y; acc4.z += x.z; acc4.w += x.w;
+                    if (k4 == 0) a512 += g[512];
                 }
-                P[trow + k] = p; Q[trow + k] = q;
+                *reinterpret_cast<float4*>(dst + k4) = acc4;
+                if (k4 == 0) dst[512] = a512;
             }
         }
         if (STATIONARY) __syncthreads();                              // every warp is done with this span before it is refilled
