@@ -139,6 +139,10 @@ int maf_mel_finalize(maf_plan* plan, void* workspace_dev, float* mel_dev, void* 
  * "gates", "T2", "seg" int32[n_items][2] (noise-clip range), "mel_tmin" int32[n_items][max tiles] (ordered-int float: minimum
  * log10 mel of every 32-frame tile -- the tiles below max - 8 are the ones maf_mel_finalize rewrites)             */
 int maf_plan_buffer(const maf_plan* plan, const char* name, int64_t* offset_bytes, int64_t* size_bytes);
+/* (offset, size) of EVERY buffer carved out of the workspace, in order; returns their number (fills at most `cap` entries).
+ * With MAF_DEBUG_REDZONE=<bytes> in the environment at plan creation the buffers are that far apart: the bounds-check run of
+ * the parity suite verifies that the gaps are never written and never influence a result.                              */
+int maf_plan_ws_layout(const maf_plan* plan, int64_t* offsets_bytes, int64_t* sizes_bytes, int32_t cap);
 int64_t maf_plan_den_offset(const maf_plan* plan, int32_t item);   /* int16 index of own sample 0 inside "den16" */
 
 /* Sharded noise clip without a host round trip (seg_dev = the {start, end} maf_select_clip wrote, in global samples):

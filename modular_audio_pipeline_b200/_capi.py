@@ -67,6 +67,7 @@ SYMBOLS = {
     "maf_sharded_logmel": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "maf_mel_finalize": (C.c_int, [_P, _P, _P, _P]),
     "maf_plan_buffer": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "maf_plan_ws_layout": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32]),
     "maf_plan_den_offset": (C.c_int64, [_P, C.c_int32]),
     "maf_ms_energy": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int64, _P, _P, _P]),
     "maf_gather_compact": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P]),

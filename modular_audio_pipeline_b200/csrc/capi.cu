@@ -202,6 +202,7 @@ struct maf_plan {
     NsParams ns{}; void* d_ns = nullptr;
     KwGeom kgeo{}; KwScan kscan{}; void* d_kscan = nullptr; int max_kgroups = 0;
     long long total_tiles = 0;
+    std::vector<WsBuf> ws_layout;        // every carved buffer in order (maf_plan_ws_layout)
     WsBuf S, M, P, Q, Yend, Zend, bits, rowflag, T2, T2hi, nmax, partial, E, ZC, clips, seg, den16, norm16, peak, pnorm, peak_norm, mel_max, mel_tmin, sub, gates, selws;
     long long ws_bytes = 0;
     long long launches = 0;
@@ -298,8 +299,16 @@ static int design_taps(int sr, SmoothTaps& t) {
     return 0;
 }
 
+// Workspace carving.  MAF_DEBUG_REDZONE=<bytes> (read at plan creation) leaves that many unused bytes after every buffer: the
+// bounds-check build of the parity suite fills the workspace with 0xFF, runs a step and verifies that every gap is intact and
+// that the outputs do not depend on what the gaps hold (tests/test_gpu_parity.py::test_workspace_red_zones) -- compute-sanitizer
+// is not available on the GPU pool.  `g_layout` collects the carved (offset, bytes) pairs of the plan being built.
+static long long g_redzone = 0;
+static std::vector<WsBuf>* g_layout = nullptr;
 static WsBuf carve(long long& cursor, long long bytes) {
-    WsBuf b; b.off = align_up(cursor, 256); b.bytes = bytes; cursor = b.off + bytes; return b;
+    WsBuf b; b.off = align_up(cursor, 256); b.bytes = bytes; cursor = b.off + bytes + g_redzone;
+    if (g_layout) g_layout->push_back(b);
+    return b;
 }
 
 extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf_item_desc* descs, int32_t n_items, maf_plan** out) {
@@ -459,6 +468,11 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
     pl->n_slices = std::max(1, std::min(32, (592 + n_items - 1) / n_items));
     // workspace layout
     long long cur = 0;
+    {
+        const char* rz = getenv("MAF_DEBUG_REDZONE");
+        g_redzone = rz ? std::max<long long>(0, atoll(rz)) / 256 * 256 : 0;
+        g_layout = &pl->ws_layout;
+    }
     pl->S = carve(cur, pl->total_rows * S_PITCH * (long long)sizeof(c32));
     pl->M = carve(cur, pl->total_rows * M_PITCH * 4LL);
     {
@@ -486,6 +500,7 @@ extern "C" int maf_plan_create(maf_ctx* ctx, const maf_params* params, const maf
     pl->gates = carve(cur, (long long)n_items * sizeof(Gate));
     pl->selws = carve(cur, SEL_SCRATCH_BYTES);
     pl->ws_bytes = align_up(cur, 256);
+    g_layout = nullptr; g_redzone = 0;
     // device tables
     std::vector<Item> io = pl->items;
     for (int i = 0; i < n_items; ++i) { io[i].den_off = io[i].pcm_off + io[i].origin; io[i].lo_avail = 0; io[i].hi_avail = 0; }
@@ -542,6 +557,13 @@ extern "C" int maf_plan_buffer(const maf_plan* pl, const char* name, int64_t* of
     if (!b) return fail(MAF_ERR_INVALID, std::string("maf_plan_buffer: unknown buffer ") + name);
     *off = b->off; *size = b->bytes;
     return MAF_OK;
+}
+
+extern "C" int maf_plan_ws_layout(const maf_plan* pl, int64_t* offsets, int64_t* sizes, int32_t cap) {
+    if (!pl) return 0;
+    const int n = (int)pl->ws_layout.size();
+    for (int i = 0; i < n && i < cap; ++i) { if (offsets) offsets[i] = pl->ws_layout[i].off; if (sizes) sizes[i] = pl->ws_layout[i].bytes; }
+    return n;
 }
 
 extern "C" int maf_set_noise_clips(maf_plan* pl, const int64_t* offsets, const int32_t* lengths) {

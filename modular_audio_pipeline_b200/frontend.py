@@ -252,6 +252,14 @@ class Plan:
         check(self._lib.maf_plan_buffer(self._h, name.encode(), C.byref(off), C.byref(size)))
         return self.workspace[off.value: off.value + size.value].view(dtype)
 
+    def workspace_layout(self):
+        """[(offset, size)] of every buffer carved out of the workspace (``maf_plan_ws_layout``); the bounds-check test reads the
+        gaps between them (MAF_DEBUG_REDZONE)."""
+        n = int(self._lib.maf_plan_ws_layout(self._h, None, None, 0))
+        offs, sizes = (C.c_int64 * n)(), (C.c_int64 * n)()
+        self._lib.maf_plan_ws_layout(self._h, offs, sizes, n)
+        return [(int(offs[i]), int(sizes[i])) for i in range(n)]
+
     def den_offset(self, item: int = 0) -> int:
         return int(self._lib.maf_plan_den_offset(self._h, item))
 

@@ -590,3 +590,59 @@ def test_plan_rejects_oversized_batches(frontend):
     with pytest.raises(MafError) as ei:
         frontend.plan([16000] * 65536, n_mels=0)
     assert ei.value.code == -3 and "65535" in ei.value.message
+
+
+# ---- bounds check without compute-sanitizer (closed on the GPU pool): red zones between the workspace buffers ---------------
+@pytest.mark.parametrize("stationary,n_mels,padding,lengths", [
+    (True, 80, 0, [16000 * 7 + 13, 600000, 600001, 1234567]),          # ragged batch, single- and multi-chunk items
+    (False, 128, 480000, [2400000 + 777]),                             # 5 chunks, 30 s Whisper pad
+    (True, 0, 0, [48000, 30001]),                                      # no log-mel: the standalone gain kernel
+])
+def test_workspace_red_zones(frontend, monkeypatch, stationary, n_mels, padding, lengths):
+    """MAF_DEBUG_REDZONE puts 4 KB of unused bytes after EVERY workspace buffer.  The workspace, and guard bands around the
+    caller's input / output buffers, are filled with 0xFF before the step: afterwards every gap and guard band must be
+    untouched (no out-of-bounds write), and PCM, log-mel and LUFS must equal the run on the packed layout bit for bit (no
+    result depends on bytes outside a buffer: 0xFF reads back as NaN / -1, which would not go unnoticed)."""
+    clips = [gen(n / SR, 40 + i, meeting=not stationary)[:n].contiguous() for i, n in enumerate(lengths)]
+    kw = dict(stationary=stationary, n_mels=n_mels, mel_padding=padding)
+    plain = frontend.plan(lengths, **kw)
+    want = plain.process(plain.pack(clips))
+    monkeypatch.setenv("MAF_DEBUG_REDZONE", "4096")
+    plan = frontend.plan(lengths, **kw)
+    monkeypatch.delenv("MAF_DEBUG_REDZONE")
+    lay = plan.workspace_layout()
+    assert len(lay) > 20 and plan.workspace_bytes >= plain.workspace_bytes + 4096 * (len(lay) - 1)
+    G = 4096                                                           # guard band (bytes) on both sides of the caller's buffers
+    def guarded(n_elems, dtype):
+        item = torch.empty((), dtype=dtype).element_size()
+        raw = torch.full((2 * G + max(n_elems, 8) * item,), 255, dtype=torch.uint8, device=frontend.device)
+        return raw, raw[G: G + max(n_elems, 8) * item].view(dtype)
+    ws_raw = torch.full((plan.workspace_bytes,), 255, dtype=torch.uint8, device=frontend.device)
+    plan._ws = ws_raw
+    in_raw, pcm = guarded(plan.total_pcm, torch.int16)
+    pcm.zero_()
+    plan.pack(clips, out=pcm)
+    out_raw, out = guarded(plan.total_out, torch.int16)
+    mel_raw, mel = guarded(plan.total_mel, torch.float32)
+    got = plan.process(pcm, out_pcm=out, mel=mel if n_mels else None)
+    torch.cuda.synchronize()
+    # 1. results identical to the packed layout
+    for a, b in zip(got.pcm, want.pcm):
+        assert torch.equal(a, b)
+    assert torch.equal(got.lufs, want.lufs)
+    if n_mels:
+        for a, b in zip(got.log_mel, want.log_mel):
+            assert torch.equal(a, b)
+    # 2. every gap between (and after) the workspace buffers still holds the fill pattern
+    ends = sorted((o + sz) for o, sz in lay)
+    starts = sorted(o for o, _ in lay) + [plan.workspace_bytes]
+    touched = []
+    for e in ends:
+        nxt = min(s for s in starts if s >= e)
+        if nxt > e and not bool((ws_raw[e:nxt] == 255).all()):
+            touched.append((e, nxt))
+    assert not touched, f"workspace red zones written: {touched[:4]}"
+    # 3. and so do the guard bands around the caller's buffers
+    for name, raw, n_bytes in (("pcm in", in_raw, max(plan.total_pcm, 8) * 2), ("pcm out", out_raw, max(plan.total_out, 8) * 2),
+                               ("mel", mel_raw, max(plan.total_mel, 8) * 4)):
+        assert bool((raw[:G] == 255).all()) and bool((raw[G + n_bytes:] == 255).all()), f"guard band of {name} written"

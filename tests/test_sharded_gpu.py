@@ -38,11 +38,24 @@ def _worker(rank, world, port, pcm, stationary, n_mels, padding, results):
     try:
         fe = FrontEnd(dev)
         geo = ShardGeometry(len(pcm), rank, world)
+        redzone = world == 2 and n_mels == 128               # one case doubles as the bounds check of the sharded stages
+        if redzone:
+            os.environ["MAF_DEBUG_REDZONE"] = "4096"
         backend = CudaShardBackend(fe, geo, torch.from_numpy(pcm[geo.local_slice()].copy()), stationary=stationary, n_mels=n_mels,
                                    mel_padding=padding)
+        os.environ.pop("MAF_DEBUG_REDZONE", None)
+        if redzone:                                          # workspace = 0xFF everywhere; the gaps must survive the step
+            backend.plan._ws = torch.full((backend.plan.workspace_bytes,), 255, dtype=torch.uint8, device=dev)
+            backend._mel_max = backend.plan.buffer("mel_max", torch.int32)
         comm = Comm(None, via_cpu=not multi)
         out, mel, lufs = run_sharded(backend, geo, stationary=stationary, comm=comm)
         torch.cuda.synchronize()
+        if redzone:
+            ws, lay = backend.plan._ws, backend.plan.workspace_layout()
+            starts = sorted(o for o, _ in lay) + [backend.plan.workspace_bytes]
+            for e in sorted(o + sz for o, sz in lay):
+                nxt = min(x for x in starts if x >= e)
+                assert nxt == e or bool((ws[e:nxt] == 255).all()), f"rank {rank}: workspace red zone [{e}, {nxt}) written"
         res = [out.cpu().numpy().copy(), mel.cpu().numpy().copy(), float(lufs.cpu().item()), "nccl" if multi else "gloo", comm.calls, None]
         if multi:                                          # the same step as one CUDA graph (kernels + NCCL collectives)
             replay = backend.capture(Comm(None))
