@@ -71,11 +71,12 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 // Stage the contiguous int16 span of tile (chunk c, frames f0 ..) into `span`: 16-byte cp.async where the group lies
 // inside the padded chunk and the recording (asynchronous: no register staging, no stall), plain stores of the zero-
 // filled samples at the edges.
-__device__ __forceinline__ void stft_stage_span(int16_t* span, const int16_t* __restrict__ pcm, const Item& it, const Chunk& ch, int f0, int tid) {
+__device__ __forceinline__ void stft_stage_span(int16_t* span, const int16_t* __restrict__ pcm, long long it_pcm_off, long long it_buf_len,
+                                                const Chunk& ch, int f0, int tid) {
     const long long j0 = (long long)f0 * HOP - NFFT / 2;              // padded-chunk coordinate of span[0]
     const long long li0 = ch.s_local - PADS + j0;                     // local buffer index of span[0]
-    const int16_t* base = pcm + it.pcm_off;
-    if (j0 >= 0 && j0 + STFT_SPAN <= ch.L && li0 >= 0 && li0 + STFT_SPAN <= it.buf_len && ((it.pcm_off + li0) & 7) == 0) {
+    const int16_t* base = pcm + it_pcm_off;
+    if (j0 >= 0 && j0 + STFT_SPAN <= ch.L && li0 >= 0 && li0 + STFT_SPAN <= it_buf_len && ((it_pcm_off + li0) & 7) == 0) {
         // the whole span lies inside the padded chunk and the recording (all but a chunk's first / last tiles): no per-group tests
         const int16_t* src = base + li0;
 #pragma unroll
@@ -84,14 +85,14 @@ __device__ __forceinline__ void stft_stage_span(int16_t* span, const int16_t* __
     }
     for (int g = tid; g < STFT_SPAN / 8; g += 32 * STFT_WARPS) {
         const long long j = j0 + 8 * g, li = li0 + 8 * g;
-        if (j >= 0 && j + 8 <= ch.L && li >= 0 && li + 8 <= it.buf_len && ((it.pcm_off + li) & 7) == 0) {
+        if (j >= 0 && j + 8 <= ch.L && li >= 0 && li + 8 <= it_buf_len && ((it_pcm_off + li) & 7) == 0) {
             cp_async16(&span[8 * g], base + li);
         } else {
             int16_t tmp[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const long long jj = j + e, ll = li + e;
-                tmp[e] = (jj >= 0 && jj < ch.L && ll >= 0 && ll < it.buf_len) ? base[ll] : (int16_t)0;
+                tmp[e] = (jj >= 0 && jj < ch.L && ll >= 0 && ll < it_buf_len) ? base[ll] : (int16_t)0;
             }
             *reinterpret_cast<uint4*>(&span[8 * g]) = *reinterpret_cast<uint4*>(tmp);
         }
@@ -130,27 +131,43 @@ __global__ void __launch_bounds__(32 * STFT_WARPS, 2) stft1024_kernel(const int1
     }
 
     const unsigned total = (unsigned)n_chunks * (unsigned)tiles_per_chunk;    // < 2^31 (checked by the launcher): 32-bit index math
-    auto tile_valid = [&](unsigned t, Chunk& ch, int& f0) {
+    // The descriptors of this CTA's first STFT_DESC tiles (grid-strided walk: a different chunk almost every step) are fetched
+    // ONCE, all loads in flight together, instead of two dependent global loads at the top of every tile.
+    constexpr int STFT_DESC = 32;
+    __shared__ Chunk s_ch[STFT_DESC];
+    __shared__ long long s_io[STFT_DESC][2];                              // the item's pcm_off, buf_len
+    for (int i = tid; i < STFT_DESC; i += 32 * STFT_WARPS) {
+        const unsigned tt = blockIdx.x + (unsigned)i * gridDim.x;
+        if (tt < total) {
+            const Chunk v = chunks[tt / (unsigned)tiles_per_chunk];
+            s_ch[i] = v;
+            s_io[i][0] = items[v.item].pcm_off; s_io[i][1] = items[v.item].buf_len;
+        }
+    }
+    __syncthreads();
+    auto tile_valid = [&](unsigned t, Chunk& ch, int& f0, long long& po, long long& bl) {
         const unsigned c = t / (unsigned)tiles_per_chunk;
-        ch = chunks[c];
+        const unsigned i = (t - blockIdx.x) / gridDim.x;
+        if (i < (unsigned)STFT_DESC) { ch = s_ch[i]; po = s_io[i][0]; bl = s_io[i][1]; }
+        else { ch = chunks[c]; po = items[ch.item].pcm_off; bl = items[ch.item].buf_len; }
         f0 = (int)(t - c * (unsigned)tiles_per_chunk) * STFT_TILE;
         return f0 < ch.n_frames;
     };
     // first valid tile of this CTA
     unsigned t = blockIdx.x;
-    Chunk ch; int f0 = 0;
-    while (t < total && !tile_valid(t, ch, f0)) t += gridDim.x;
+    Chunk ch; int f0 = 0; long long po = 0, bl = 0;
+    while (t < total && !tile_valid(t, ch, f0, po, bl)) t += gridDim.x;
     if (t >= total) return;
     int buf = 0;
-    stft_stage_span(span0, pcm, items[ch.item], ch, f0, tid);
+    stft_stage_span(span0, pcm, po, bl, ch, f0, tid);
     asm volatile("cp.async.commit_group;" ::: "memory");
 
     while (t < total) {
         // next valid tile: start its span load into the other buffer
         unsigned tn = t + gridDim.x;
         Chunk chn; int f0n = 0;
-        while (tn < total && !tile_valid(tn, chn, f0n)) tn += gridDim.x;
-        if (tn < total) stft_stage_span(span0 + (buf ^ 1) * STFT_SPAN, pcm, items[chn.item], chn, f0n, tid);
+        while (tn < total && !tile_valid(tn, chn, f0n, po, bl)) tn += gridDim.x;
+        if (tn < total) stft_stage_span(span0 + (buf ^ 1) * STFT_SPAN, pcm, po, bl, chn, f0n, tid);
         asm volatile("cp.async.commit_group;\n cp.async.wait_group 1;" ::: "memory");
         __syncthreads();                                              // current span landed; everyone is done with the previous tile's scratch
 
