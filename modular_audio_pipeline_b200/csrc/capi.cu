@@ -78,11 +78,12 @@ static MelHost build_mel(int n_mels) {
             if (h.count[m] > 0) { lo = std::min(lo, h.start[m]); hi = std::max(hi, h.start[m] + h.count[m]); }
         }
         if (hi <= lo) { lo = 0; hi = 0; }
-        h.qstart.push_back(lo); h.qcount.push_back(hi - lo); h.qoff.push_back((int)h.wq.size() / 4);
-        for (int k = lo; k < hi; ++k)
+        const int padded = (hi - lo + 3) / 4 * 4;                // whole groups of four bins (zero weights past the run: the
+        h.qstart.push_back(lo); h.qcount.push_back(padded); h.qoff.push_back((int)h.wq.size() / 4);   // kernel has no remainder loop)
+        for (int k = lo; k < lo + padded; ++k)
             for (int j = 0; j < 4; ++j) {
                 const int m = 4 * q + j;
-                const bool in = k >= h.start[m] && k < h.start[m] + h.count[m];
+                const bool in = k < hi && k >= h.start[m] && k < h.start[m] + h.count[m];
                 h.wq.push_back(in ? h.w[h.woff[m] + k - h.start[m]] : 0.0f);
             }
     }

@@ -17,7 +17,7 @@ namespace maf {
 constexpr int MEL_SPAN = (MEL_TILE - 1) * W_HOP + W_NFFT;            // 5360 samples per tile
 constexpr int Z_PITCH = 200;
 constexpr int P_PITCH = 201;
-constexpr size_t LOGMEL_SMEM = sizeof(float) * MEL_SPAN + sizeof(c32) * MEL_TILE * Z_PITCH + sizeof(float) * MEL_TILE * P_PITCH +
+constexpr size_t LOGMEL_SMEM = sizeof(float) * MEL_SPAN + sizeof(c32) * MEL_TILE * Z_PITCH + sizeof(float) * (MEL_TILE * P_PITCH + 4) +
                                sizeof(float) * W_NFFT + sizeof(c32) * 200 + sizeof(c32) * 208 + sizeof(int) * 4 * MEL_SLOTS_MAX + sizeof(float4) * MEL_WQ_MAX;
 
 struct MelTile {            // geometry of one (item, 32-frame tile) unit
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     float* span = reinterpret_cast<float*>(smem_raw);
     c32* zb = reinterpret_cast<c32*>(span + MEL_SPAN);
     float* pw = reinterpret_cast<float*>(zb + MEL_TILE * Z_PITCH);
-    float* win = pw + MEL_TILE * P_PITCH;
+    float* win = pw + MEL_TILE * P_PITCH + 4;                            // four floats of slack: padded mel runs may read past bin 200
     c32* twA = reinterpret_cast<c32*>(win + W_NFFT);
     c32* tw400 = twA + 200;
     float4* m_wq = reinterpret_cast<float4*>(tw400 + 208);               // 16-byte aligned: every array before it is a multiple of 16 bytes
@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
         g.own_hi = g.last_tile ? it.g0 + it.own_len : g.own_lo + (long long)MEL_TILE * W_HOP;
         g.l0 = g.i0 - it.g0;                                        // item-relative index of span[0]
         // (norm16, the peak-normalised copy kweight_energy_kernel leaves behind, covers the own range only: no halos)
-        g.interior = g.i0 >= 0 && g.i0 + MEL_SPAN <= it.n_global && g.l0 >= (norm16 ? 0LL : -(long long)it.lo_avail) &&
+        // (peak normalisation requested but no norm16 -- a stage-wise call without the loudness pass -- takes the generic path)
+        g.interior = (norm16 || !peak_normalize) && g.i0 >= 0 && g.i0 + MEL_SPAN <= it.n_global && g.l0 >= (norm16 ? 0LL : -(long long)it.lo_avail) &&
                      g.l0 + MEL_SPAN <= it.own_len + (norm16 ? 0 : it.hi_avail) && ((it.den_off + g.l0) & 7) == 0 && !g.last_tile &&
                      (!out16 || (((it.out_off + g.l0) & 7) == 0 && g.l0 + W_NFFT / 2 >= 0 && g.l0 + W_NFFT / 2 + MEL_TILE * W_HOP <= it.own_len));
         return true;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     if (tid < mel.n_slots) { m_qstart[tid] = mel.qstart[tid]; m_qcount[tid] = mel.qcount[tid]; m_qoff[tid] = mel.qoff[tid]; m_qrow[tid] = mel.qrow[tid]; }
     for (int i = tid; i < mel.n_wq; i += 256) m_wq[i] = mel.wq[i];
     for (int i = tid; i < 201; i += 256) tw400[i] = cs.tw400[i];
+    if (tid < 4) pw[MEL_TILE * P_PITCH + tid] = 0.f;              // slack read (times a zero weight) by the last frame's padded mel runs
 
   while (t < total) {
     const int item = cur.item;
@@ -130,35 +132,24 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
                 const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
                 float a[8];
                 uint32_t ow[4];
-                if (norm16 || !pn) {
-                    // the samples are final up to the loudness gain (peak normalisation done by kweight_energy_kernel, or off):
-                    // int16 -> float by byte permutation (0x4B00'0000 | (s ^ 0x8000) = 2^23 + 32768 + s), gain, limiter, clamp,
-                    // truncation; the low 16 bits of (q + 1.5 * 2^23) are q's two's complement, so the int16 pair is one permute
+                // the samples are final up to the loudness gain (peak normalisation done by kweight_energy_kernel, or off):
+                // int16 -> float by byte permutation (0x4B00'0000 | (s ^ 0x8000) = 2^23 + 32768 + s), gain, limiter, clamp,
+                // truncation; the low 16 bits of (q + 1.5 * 2^23) are q's two's complement, so the int16 pair is one permute
 #pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        const uint32_t b = wv[h] ^ 0x80008000u;
-                        float t0 = __fadd_rn(__uint_as_float(__byte_perm(b, 0x4B000000u, 0x7410)), -8421376.0f);
-                        float t1 = __fadd_rn(__uint_as_float(__byte_perm(b, 0x4B000000u, 0x7432)), -8421376.0f);
-                        if (gt.applied) {
-                            t0 = __fmul_rn(gt.gain, t0); t1 = __fmul_rn(gt.gain, t1);
-                            if (gt.lim) { t0 = div_by(t0, dv); t1 = div_by(t1, dv); }
-                            t0 = truncf(fminf(fmaxf(t0, -32768.0f), 32767.0f));
-                            t1 = truncf(fminf(fmaxf(t1, -32768.0f), 32767.0f));
-                            ow[h] = __byte_perm(__float_as_uint(__fadd_rn(t0, MAGIC_F)), __float_as_uint(__fadd_rn(t1, MAGIC_F)), 0x5410);
-                        } else {
-                            ow[h] = wv[h];
-                        }
-                        a[2 * h] = t0 * (1.0f / 32768.0f); a[2 * h + 1] = t1 * (1.0f / 32768.0f);
+                for (int h = 0; h < 4; ++h) {
+                    const uint32_t b = wv[h] ^ 0x80008000u;
+                    float t0 = __fadd_rn(__uint_as_float(__byte_perm(b, 0x4B000000u, 0x7410)), -8421376.0f);
+                    float t1 = __fadd_rn(__uint_as_float(__byte_perm(b, 0x4B000000u, 0x7432)), -8421376.0f);
+                    if (gt.applied) {
+                        t0 = __fmul_rn(gt.gain, t0); t1 = __fmul_rn(gt.gain, t1);
+                        if (gt.lim) { t0 = div_by(t0, dv); t1 = div_by(t1, dv); }
+                        t0 = truncf(fminf(fmaxf(t0, -32768.0f), 32767.0f));
+                        t1 = truncf(fminf(fmaxf(t1, -32768.0f), 32767.0f));
+                        ow[h] = __byte_perm(__float_as_uint(__fadd_rn(t0, MAGIC_F)), __float_as_uint(__fadd_rn(t1, MAGIC_F)), 0x5410);
+                    } else {
+                        ow[h] = wv[h];
                     }
-                } else {
-#pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        float q0, q1;
-                        const int s0 = norm_gain_sample((int)(short)(wv[h] & 0xffffu), pn, pnv, gt, dv, q0);
-                        const int s1 = norm_gain_sample((int)wv[h] >> 16, pn, pnv, gt, dv, q1);
-                        a[2 * h] = q0 * (1.0f / 32768.0f); a[2 * h + 1] = q1 * (1.0f / 32768.0f);
-                        ow[h] = ((uint32_t)s0 & 0xffffu) | ((uint32_t)s1 << 16);
-                    }
+                    a[2 * h] = t0 * (1.0f / 32768.0f); a[2 * h + 1] = t1 * (1.0f / 32768.0f);
                 }
                 *reinterpret_cast<float4*>(span + 8 * gq) = make_float4(a[0], a[1], a[2], a[3]);
                 *reinterpret_cast<float4*>(span + 8 * gq + 4) = make_float4(a[4], a[5], a[6], a[7]);
@@ -270,11 +261,16 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
             const float4* wts = m_wq + m_qoff[sl];
             const float* pr = pw + lf * P_PITCH + m_qstart[sl];
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-            for (int i = 0; i < cnt; ++i) {
-                const float pv = pr[i];
-                const float4 w = wts[i];
-                a0 = fmaf(w.x, pv, a0); a1 = fmaf(w.y, pv, a1); a2 = fmaf(w.z, pv, a2); a3 = fmaf(w.w, pv, a3);
+            // the host pads every run to a multiple of four bins with zero weights (the power rows have four floats of slack):
+            // whole groups of four, all eight loads of a group issued before its sixteen FMAs, no remainder loop
+#pragma unroll 1
+            for (int i = 0; i < cnt; i += 4) {
+                const float p0 = pr[i], p1 = pr[i + 1], p2 = pr[i + 2], p3 = pr[i + 3];
+                const float4 w0 = wts[i], w1 = wts[i + 1], w2 = wts[i + 2], w3 = wts[i + 3];
+                a0 = fmaf(w0.x, p0, a0); a1 = fmaf(w0.y, p0, a1); a2 = fmaf(w0.z, p0, a2); a3 = fmaf(w0.w, p0, a3);
+                a0 = fmaf(w1.x, p1, a0); a1 = fmaf(w1.y, p1, a1); a2 = fmaf(w1.z, p1, a2); a3 = fmaf(w1.w, p1, a3);
+                a0 = fmaf(w2.x, p2, a0); a1 = fmaf(w2.y, p2, a1); a2 = fmaf(w2.z, p2, a2); a3 = fmaf(w2.w, p2, a3);
+                a0 = fmaf(w3.x, p3, a0); a1 = fmaf(w3.y, p3, a1); a2 = fmaf(w3.z, p3, a2); a3 = fmaf(w3.w, p3, a3);
             }
             // lg2.approx (|err| < 3e-6 in log10 units; the clamp keeps the argument normal, so the .ftz form needs no denormal
             // fix-up) and (log10 + 4) / 4 as ONE fused multiply-add: 1 + lg2 * (log10(2) / 4)

@@ -64,14 +64,6 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
     const int tid = threadIdx.x;
     const long long c0 = (first_tile - 1) * tile_len;                            // item-relative index of the first staged sample
     const int span = (tpc + 1) * tile_len;
-    if (tid < seg) hs[tid] = make_float4(tab->H[tid][0], tab->H[tid][1], tab->H[tid][2], tab->H[tid][3]);
-    // scan matrices into shared memory (the scan steps are a dependent chain: global-load latency would sit in every link)
-    for (int i = tid; i < 6 * 16; i += blockDim.x) mats[i] = i < 80 ? tab->Mstep[i >> 4][i & 15] : tab->Mwarp[i - 80];
-    for (int i = tid; i < 16 * 32; i += blockDim.x) mlane[i] = tab->Mlane[i & 31][i >> 5];
-
-    PeakNorm pnv; pnv.active = 0;
-    if (peak_normalize) pnv = pnorm[item];
-    const bool pn = pnv.active != 0;
     const int16_t* x = den16 + it.den_off;
     // stage 1: raw samples -> shared memory; interior 16-byte groups by cp.async (all loads of the CTA in flight at once)
     for (int g8 = tid; g8 < span / 8; g8 += blockDim.x) {
@@ -87,7 +79,16 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
         const long long li = c0 + i;
         xs[i] = (li >= -(long long)it.lo_avail && li < it.own_len) ? x[li] : (int16_t)0;
     }
-    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // the tables and the peak factor are fetched AFTER the sample copies are in flight (their global-load latency used to sit in
+    // front of the staging loop); scan matrices go to shared memory: the scan steps are a dependent chain
+    if (tid < seg) hs[tid] = make_float4(tab->H[tid][0], tab->H[tid][1], tab->H[tid][2], tab->H[tid][3]);
+    for (int i = tid; i < 6 * 16; i += blockDim.x) mats[i] = i < 80 ? tab->Mstep[i >> 4][i & 15] : tab->Mwarp[i - 80];
+    for (int i = tid; i < 16 * 32; i += blockDim.x) mlane[i] = tab->Mlane[i & 31][i >> 5];
+    PeakNorm pnv; pnv.active = 0;
+    if (peak_normalize) pnv = pnorm[item];
+    const bool pn = pnv.active != 0;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     // stage 2 (same thread <-> same groups, so no barrier in between): peak normalisation in place, peak of the result.
     // Eight samples at a time, branch-free: int16 -> float by byte permutation (0x4B00'0000 | (s ^ 0x8000) = 2^23 + 32768 + s),
     // the two-float audioop.mul floor of peak_norm_sample_fastf, ONE test per group for "some sample is too close to an
