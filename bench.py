@@ -580,7 +580,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import faulthandler
-        faulthandler.dump_traceback_later(1500, exit=True)     # a stuck collective must not hold N GPUs until the driver's limit
+        faulthandler.dump_traceback_later(900, exit=True)      # a stuck collective must not hold N GPUs until the driver's limit
         dist.init_process_group("nccl", device_id=dev)
     desc, seconds, per_gpu, stationary, n_mels, padding, meeting = WORKLOADS[args.workload]
     n = int(round(seconds * SR))

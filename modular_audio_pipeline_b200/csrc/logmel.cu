@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
     const bool pn = pnv.active != 0;
     const Gate gt = s_gt;
     const DivConst dv = limiter_div(gt);
+    const float gain = gt.applied ? gt.gain : 1.0f;
     const int16_t* x = den16 + it.den_off;
     const long long np_global = it.n_global + padding;            // length of the zero-padded recording
     const long long i0 = cur.i0, l0 = cur.l0, own_lo = cur.own_lo, own_hi = cur.own_hi;
@@ -140,15 +141,13 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
                     const uint32_t b = wv[h] ^ 0x80008000u;
                     float t0 = __fadd_rn(__uint_as_float(__byte_perm(b, 0x4B000000u, 0x7410)), -8421376.0f);
                     float t1 = __fadd_rn(__uint_as_float(__byte_perm(b, 0x4B000000u, 0x7432)), -8421376.0f);
-                    if (gt.applied) {
-                        t0 = __fmul_rn(gt.gain, t0); t1 = __fmul_rn(gt.gain, t1);
-                        if (gt.lim) { t0 = div_by(t0, dv); t1 = div_by(t1, dv); }
-                        t0 = truncf(fminf(fmaxf(t0, -32768.0f), 32767.0f));
-                        t1 = truncf(fminf(fmaxf(t1, -32768.0f), 32767.0f));
-                        ow[h] = __byte_perm(__float_as_uint(__fadd_rn(t0, MAGIC_F)), __float_as_uint(__fadd_rn(t1, MAGIC_F)), 0x5410);
-                    } else {
-                        ow[h] = wv[h];
-                    }
+                    // (a pass-through gate runs the same chain with gain 1: 1 * t, the clamp and the truncation leave an int16-valued
+                    // float unchanged, so no second code path -- the loop body has to stay small for the instruction cache)
+                    t0 = __fmul_rn(gain, t0); t1 = __fmul_rn(gain, t1);
+                    if (gt.lim) { t0 = div_by(t0, dv); t1 = div_by(t1, dv); }
+                    t0 = truncf(fminf(fmaxf(t0, -32768.0f), 32767.0f));
+                    t1 = truncf(fminf(fmaxf(t1, -32768.0f), 32767.0f));
+                    ow[h] = __byte_perm(__float_as_uint(__fadd_rn(t0, MAGIC_F)), __float_as_uint(__fadd_rn(t1, MAGIC_F)), 0x5410);
                     a[2 * h] = t0 * (1.0f / 32768.0f); a[2 * h + 1] = t1 * (1.0f / 32768.0f);
                 }
                 *reinterpret_cast<float4*>(span + 8 * gq) = make_float4(a[0], a[1], a[2], a[3]);
@@ -197,7 +196,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
         for (int m = 0; m < 8; ++m) wn[m] = *reinterpret_cast<const float2*>(win + 2 * (j + 25 * m));
 #pragma unroll
         for (int p = 1; p < 8; ++p) twj[p] = twA[p * 25 + j];
-#pragma unroll 2
+#pragma unroll 1
         for (int r = 0; r < MEL_TILE / 8; ++r) {
             const int lf = fg + 8 * r;
             const float* sp0 = span + lf * W_HOP + 2 * j;
@@ -235,7 +234,7 @@ __global__ void __launch_bounds__(256) logmel_kernel(const int16_t* __restrict__
         const int kn = k == 0 ? 0 : 200 - k;
         const c32* z = zb + fg * Z_PITCH;
         float* po = pw + fg * P_PITCH;
-#pragma unroll 4
+#pragma unroll 2
         for (int r = 0; r < MEL_TILE / 2; ++r) {
             const c32 za = z[k], zn = z[kn];
             const c32 Xa = rfft400_bin(za, zn, tw);
