@@ -757,8 +757,10 @@ static int run_loudness_stats(maf_plan* pl, const int16_t* src, const Item* item
 }
 
 static int run_gate(maf_plan* pl, const Item* items, void* ws, cudaStream_t st) {
+    int max_blocks = 0;
+    for (const Item& it : pl->items) max_blocks = std::max(max_blocks, it.n_blocks);
     launch_gate(ws_ptr<double>(ws, pl->sub), items, pl->n_items, pl->inv_block, (double)pl->p.target_lufs, ws_ptr<int>(ws, pl->peak_norm),
-                ws_ptr<Gate>(ws, pl->gates), st);
+                ws_ptr<Gate>(ws, pl->gates), max_blocks, ws_ptr<void>(ws, pl->selws), st);
     pl->launches += 1;
     mark(pl, ST_GATE, st);
     CU(cudaGetLastError());
@@ -1156,7 +1158,8 @@ extern "C" int maf_gate(maf_ctx* ctx, const double* sub_energy, int64_t n_tiles,
     unsigned char* d = (unsigned char*)ctx->scratch + 512;
     static_assert(sizeof(Item) <= 256, "Item exceeds the put blob");
     launch_put(d, &it, sizeof(it), st);
-    launch_gate(sub_energy, (const Item*)d, 1, 1.0 / (0.4 * (double)sr), (double)target_lufs, peak_norm, (Gate*)gate, st);
+    launch_gate(sub_energy, (const Item*)d, 1, 1.0 / (0.4 * (double)sr), (double)target_lufs, peak_norm, (Gate*)gate, (int)n_blocks,
+                (unsigned char*)ctx->scratch + 1024, st);
     CU(cudaGetLastError());
     return MAF_OK;
 }

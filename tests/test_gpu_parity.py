@@ -646,3 +646,38 @@ def test_workspace_red_zones(frontend, monkeypatch, stationary, n_mels, padding,
     for name, raw, n_bytes in (("pcm in", in_raw, max(plan.total_pcm, 8) * 2), ("pcm out", out_raw, max(plan.total_out, 8) * 2),
                                ("mel", mel_raw, max(plan.total_mel, 8) * 4)):
         assert bool((raw[:G] == 255).all()) and bool((raw[G + n_bytes:] == 255).all()), f"guard band of {name} written"
+
+
+# ---- gating of a LONG recording: the co-operative grid kernel (>= 16 384 blocks) against numpy and against the one-CTA kernel ----
+@pytest.mark.parametrize("n_tiles", [9000, 16387, 36000, 288003])
+def test_gate_long_recordings(frontend, n_tiles):
+    """pyloudnorm's two gates over the 400 ms blocks (= 4 consecutive 100 ms sub-blocks) of a recording of up to 8 h; the
+    grid kernel that takes over at 16 384 blocks must give the LUFS of a float64 numpy evaluation (and the gain derived from it)."""
+    import ctypes as C
+    from modular_audio_pipeline_b200._capi import check
+    rng = np.random.default_rng(n_tiles)
+    sub = rng.random(n_tiles) * 1e-3 * (rng.random(n_tiles) > 0.3)          # 30 % silent sub-blocks: both gates bite
+    sub[: n_tiles // 7] *= 1e-9                                             # a stretch below the absolute gate
+    nb = n_tiles - 3
+    inv_block = 1.0 / (0.4 * SR)
+    z = inv_block * (sub[:-3] + sub[1:-2] + sub[2:-1] + sub[3:])
+    zabs = 10.0 ** ((-70.0 + 0.691) / 10.0)
+    keep = z >= zabs
+    zrel = z[keep].mean() * 0.1
+    keep2 = (z > zrel) & (z > zabs)
+    want = -0.691 + 10.0 * np.log10(z[keep2].mean())
+    d_sub = torch.from_numpy(sub).to(frontend.device)
+    pk = torch.full((1,), 20000, dtype=torch.int32, device=frontend.device)
+    gate = torch.zeros(32, dtype=torch.uint8, device=frontend.device)
+    st = torch.cuda.current_stream().cuda_stream
+    check(frontend._lib.maf_gate(frontend._h, d_sub.data_ptr(), n_tiles, nb, SR, C.c_float(-16.0), pk.data_ptr(), gate.data_ptr(), st))
+    torch.cuda.synchronize()
+    lufs = float(gate[:8].view(torch.float64).item())
+    gain = float(gate[8:12].view(torch.float32).item())
+    assert abs(lufs - want) <= 1e-9
+    assert gain == np.float32(10.0 ** ((-16.0 - lufs) / 20.0))
+    # twice the same input: bit-identical (fixed partition, fixed summation order)
+    gate2 = torch.zeros(32, dtype=torch.uint8, device=frontend.device)
+    check(frontend._lib.maf_gate(frontend._h, d_sub.data_ptr(), n_tiles, nb, SR, C.c_float(-16.0), pk.data_ptr(), gate2.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert torch.equal(gate, gate2)
