@@ -39,6 +39,22 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
 }
 
+// One bulk asynchronous copy (TMA, 1-D: SASS UBLKCP) global -> shared, completion counted in bytes on an mbarrier (SYNCS):
+// ONE thread moves a CTA's whole 51 KB sample span; dst / src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar), d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n .reg .pred p;\n MBAR_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra MBAR_DONE;\n bra MBAR_WAIT;\n MBAR_DONE:\n}" ::"r"(b), "r"(phase) : "memory");
+}
+
 // SEG > 0: compile-time segment length (the loops unroll and the compiler hoists the shared-memory loads); 0 = `seg_rt`.
 template <int SEG>
 __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const int16_t* __restrict__ den16, const Item* __restrict__ items,
@@ -66,21 +82,29 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
     const long long c0 = (first_tile - 1) * tile_len;                            // item-relative index of the first staged sample
     const int span = (tpc + 1) * tile_len;
     const int16_t* x = den16 + it.den_off;
-    // stage 1: raw samples -> shared memory; interior 16-byte groups by cp.async (all loads of the CTA in flight at once)
-    for (int g8 = tid; g8 < span / 8; g8 += blockDim.x) {
-        const long long li = c0 + 8 * g8;
-        if (li >= -(long long)it.lo_avail && li + 8 <= it.own_len && ((it.den_off + li) & 7) == 0) {
-            cp_async16(xs + 8 * g8, x + li);
-        } else {
+    // stage 1: raw samples -> shared memory.  A span that lies inside the item and is 16-byte aligned (all but an item's first /
+    // last CTA) travels as ONE bulk asynchronous copy issued by thread 0 and counted on an mbarrier; the edge CTAs stage
+    // 16-byte groups by cp.async and zero-fill what lies outside the recording.
+    __shared__ __align__(8) unsigned long long span_bar;
+    const bool bulk = c0 >= -(long long)it.lo_avail && c0 + span <= it.own_len && ((it.den_off + c0) & 7) == 0 && (span & 7) == 0;
+    if (bulk) {
+        if (tid == 0) { mbar_init(&span_bar, 1); bulk_load(xs, x + c0, 2u * (unsigned)span, &span_bar); }
+    } else {
+        for (int g8 = tid; g8 < span / 8; g8 += blockDim.x) {
+            const long long li = c0 + 8 * g8;
+            if (li >= -(long long)it.lo_avail && li + 8 <= it.own_len && ((it.den_off + li) & 7) == 0) {
+                cp_async16(xs + 8 * g8, x + li);
+            } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) xs[8 * g8 + e] = (li + e >= -(long long)it.lo_avail && li + e < it.own_len) ? x[li + e] : (int16_t)0;
+                for (int e = 0; e < 8; ++e) xs[8 * g8 + e] = (li + e >= -(long long)it.lo_avail && li + e < it.own_len) ? x[li + e] : (int16_t)0;
+            }
         }
+        for (int i = (span / 8) * 8 + tid; i < span; i += blockDim.x) {              // tail when tile_len is not a multiple of 8
+            const long long li = c0 + i;
+            xs[i] = (li >= -(long long)it.lo_avail && li < it.own_len) ? x[li] : (int16_t)0;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    for (int i = (span / 8) * 8 + tid; i < span; i += blockDim.x) {              // tail when tile_len is not a multiple of 8
-        const long long li = c0 + i;
-        xs[i] = (li >= -(long long)it.lo_avail && li < it.own_len) ? x[li] : (int16_t)0;
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
     // the tables and the peak factor are fetched AFTER the sample copies are in flight (their global-load latency used to sit in
     // front of the staging loop); scan matrices go to shared memory: the scan steps are a dependent chain
     if (tid < seg) hs[tid] = make_float4(tab->H[tid][0], tab->H[tid][1], tab->H[tid][2], tab->H[tid][3]);
@@ -89,7 +113,12 @@ __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const in
     PeakNorm pnv; pnv.active = 0;
     if (peak_normalize) pnv = pnorm[item];
     const bool pn = pnv.active != 0;
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (bulk) {
+        __syncthreads();                                                             // the barrier's initialisation is visible to every waiter
+        mbar_wait(&span_bar, 0);
+    } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     // stage 2 (same thread <-> same groups, so no barrier in between): peak normalisation in place, peak of the result.
     // Eight samples at a time, branch-free: int16 -> float by byte permutation (0x4B00'0000 | (s ^ 0x8000) = 2^23 + 32768 + s),
     // the two-float audioop.mul floor of peak_norm_sample_fastf, ONE test per group for "some sample is too close to an
