@@ -39,22 +39,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
 }
 
-// One bulk asynchronous copy (TMA, 1-D: SASS UBLKCP) global -> shared, completion counted in bytes on an mbarrier (SYNCS):
-// ONE thread moves a CTA's whole 51 KB sample span; dst / src 16-byte aligned, bytes a multiple of 16.
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
-    const unsigned b = (unsigned)__cvta_generic_to_shared(bar), d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(b) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
-    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("{\n .reg .pred p;\n MBAR_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra MBAR_DONE;\n bra MBAR_WAIT;\n MBAR_DONE:\n}" ::"r"(b), "r"(phase) : "memory");
-}
-
 // SEG > 0: compile-time segment length (the loops unroll and the compiler hoists the shared-memory loads); 0 = `seg_rt`.
 template <int SEG>
 __global__ void __launch_bounds__(KW_MAX_THREADS) kweight_energy_kernel(const int16_t* __restrict__ den16, const Item* __restrict__ items,
