@@ -644,7 +644,7 @@ __device__ __forceinline__ void freq_taps8(const float* row, int k0, int nf, con
 // Recurrence phase of one bin: walks W = 32 + 2 NT frames downwards from frame base + 31, writes the time-smoothed raw
 // mask of the 32 output frames into column k of `rows`.  INTERIOR = every walked frame lies inside the chunk.
 template <int NT, bool INTERIOR>
-__device__ __forceinline__ void ns_walk(const c32* __restrict__ sp, int k, int base, int F, double y, double z, const NsParams& ns,
+__device__ __forceinline__ void ns_walk(const c32* __restrict__ sp, int k, int base, int F, float yend, float zend, const NsParams& ns,
                                         const SmoothTaps& taps, float* __restrict__ rows) {
     constexpr int W = NS_TILE + 2 * NT;
     constexpr int NB = 4;                                     // frames per load batch (double-buffered)
@@ -652,8 +652,6 @@ __device__ __forceinline__ void ns_walk(const c32* __restrict__ sp, int k, int b
     // from float32-rounded states, so float32 arithmetic adds ~4e-7 relative to Sm (mask error < 3e-6, -110 dB) and keeps
     // the quarter-rate conversion unit (F2F) off the per-bin path.
     const float a = (float)ns.a, ia = (float)ns.inv_a, b2ia = (float)(ns.b * ns.b * ns.inv_a);
-    float u = (float)(ns.b * y);
-    float zf = (float)z;
     // sigmoid(((A - sm) / sm - thresh) * slope) = 1 / (1 + 2^(c0 - c1 A / sm))
     const float c1 = ns.slope * 1.4426950408889634f, c0 = ns.slope * (1.0f + ns.thresh) * 1.4426950408889634f;
     // bins 0 and 512 share slot 0 as (re X_0, re X_512): select the component, zero the other one
@@ -683,6 +681,10 @@ __device__ __forceinline__ void ns_walk(const c32* __restrict__ sp, int k, int b
         }
     }
     load(cur, 0);
+    // first use of the tile-end states: only now, with the L2 prefetches and the first batch of S loads already in flight (the
+    // Yend / Zend loads of the caller used to be waited for before anything else was issued)
+    float u = (float)(ns.b * (double)yend);
+    float zf = zend;
 #pragma unroll
     for (int b0 = 0; b0 < W; b0 += NB) {
         if (b0 + NB < W) load(nxt, b0 + NB);
@@ -742,7 +744,7 @@ __global__ void __launch_bounds__(NSM_THREADS, 2) ns_mask_smooth_kernel(const c3
         const int k = tid;
         const int e = min(base + NS_TILE, F);                    // the walk starts at frame e - 1; states are known at tile ends
         const long long srow = (ch.tile0 + (e + STFT_TILE - 1) / STFT_TILE - 1) * T_PITCH + k;
-        const double y = (double)Yend[srow], z = (double)Zend[srow];
+        const float y = Yend[srow], z = Zend[srow];                // (converted at their first use inside the walk, after its loads are issued)
         const c32* sp = S + ch.row0 * S_PITCH + (k & 511);
         if (base - 2 * NT >= 0 && base + NS_TILE <= F) ns_walk<NT, true>(sp, k, base, F, y, z, ns, taps, rows);
         else ns_walk<NT, false>(sp, k, base, F, y, z, ns, taps, rows);
