@@ -217,10 +217,21 @@ MAF_HD void fft32(c32 (&v)[32]) {
 constexpr int FFT1024_PITCH = 33;
 constexpr int FFT1024_SMEM = 32 * FFT1024_PITCH;
 
-MAF_HD void fft1024w_pass1(c32 (&v)[32], c32* sm, const c32* tww, int lane) {
+MAF_HD void fft1024w_pass1(c32 (&v)[32], c32* __restrict__ sm, const c32* __restrict__ tww, int lane) {
     fft32(v);                                                         // over n2 (registers) -> k2
+    // the 31 twiddle loads are software-pipelined TW_AHEAD deep: with the kernel at its register cap the compiler otherwise
+    // funnels all of them through one register pair (load -> multiply -> store -> next load: every shared-memory latency exposed)
+    constexpr int TW_AHEAD = 4;
+    c32 tq[TW_AHEAD];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) sm[j * FFT1024_PITCH + lane] = (j == 0) ? v[0] : cmul(v[j], tww[j * 32 + lane]);
+    for (int a = 0; a < TW_AHEAD; ++a) tq[a] = tww[(1 + a) * 32 + lane];
+    sm[lane] = v[0];
+#pragma unroll
+    for (int j = 1; j < 32; ++j) {
+        const c32 t = tq[(j - 1) % TW_AHEAD];
+        if (j + TW_AHEAD < 32) tq[(j - 1) % TW_AHEAD] = tww[(j + TW_AHEAD) * 32 + lane];
+        sm[j * FFT1024_PITCH + lane] = cmul(v[j], t);
+    }
 }
 // (warp barrier)
 MAF_HD void fft1024w_pass2(c32 (&v)[32], const c32* sm, int lane) {
