@@ -835,8 +835,37 @@ __global__ void __launch_bounds__(NSM_THREADS, 2) smooth_mask_kernel(const uint3
         rows[r * SM_ROW + swz(c < MAX_NF ? c : c + NBIN)] = 0.f;
     }
     const bool rf = tid < NBIN ? rowflag[(long long)blockIdx.y * M_PITCH + tid] != 0 : false;
+    // Interior tiles with few time taps: the time-smoothed value of an output depends only on the 2 NT + 1 raw BITS around it, so
+    // it is looked up: lut[pattern] is computed once per CTA with the very multiply-add chain of the generic walk (bit j of the
+    // pattern = frame rr - NT + j, oldest first: bit-identical results), and a bin's walk collapses to gathering its column of
+    // W bits into a 64-bit word and one table read per output.
+    constexpr bool USE_LUT = (2 * NT + 1 <= 7) && (W <= 64);
+    __shared__ float lut[USE_LUT ? (1 << (2 * NT + 1)) : 1];
+    const bool interior = base - NT >= 0 && base + NS_TILE + NT <= F;
+    if (USE_LUT && interior && tid < (1 << (2 * NT + 1))) {
+        const float lo = 1.0f - prop;
+        float acc = taps.vt[0] * ((tid & 1) ? 1.0f : lo);
+#pragma unroll
+        for (int j = 1; j < 2 * NT + 1; ++j) acc = fmaf(taps.vt[j], ((tid >> j) & 1) ? 1.0f : lo, acc);
+        lut[tid] = acc;
+    }
     __syncthreads();
-    if (tid < NBIN) {
+    if (USE_LUT && interior) {
+        if (tid < NBIN) {
+            const int k = tid;
+            const uint32_t* bp = bw + (k >> 5);
+            const int sh = k & 31;
+            unsigned long long col = 0ull;                        // bit i = raw bit of frame base - NT + i
+            if (rf) col = ~0ull;
+            else {
+#pragma unroll
+                for (int i = 0; i < W; ++i) col |= (unsigned long long)((bp[i * BW] >> sh) & 1u) << i;
+            }
+#pragma unroll
+            for (int lr = 0; lr < NS_TILE; ++lr)
+                rows[lr * SM_ROW + swz(MAX_NF + k)] = lut[(unsigned)(col >> lr) & ((1u << (2 * NT + 1)) - 1u)];
+        }
+    } else if (tid < NBIN) {
         const int k = tid;
         const float lo = 1.0f - prop;
         const uint32_t* bp = bw + (k >> 5);
