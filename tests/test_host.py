@@ -222,3 +222,29 @@ def test_property_wavio_roundtrip_and_wave_module_interop(tmp_path):
         assert torch.equal(out, x)
 
     check()
+
+
+# ---- the bench line contract, checked on the committed record of the last full run ---------------------------------------------
+def test_committed_bench_line_has_the_contract_keys():
+    """`python bench.py` prints ONE JSON line; the driver and the judge read these keys.  The committed record of the round's last
+    full run (profiles/r02_final_bench_cfg2_n1.json) must carry every one of them with sane values."""
+    import json
+    rec = json.load(open(os.path.join(ROOT, "profiles", "r02_final_bench_cfg2_n1.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in rec, k
+    assert rec["metric"] == "audio_seconds_per_second" and rec["unit"] == "audio-s/s" and rec["higher_is_better"] is True
+    assert rec["scaling"] == "weak" and rec["vs_baseline"] is None and rec["data"] == "synthetic" and "workload" in rec["config"]
+    assert abs(rec["value"] - 3600.0 * rec["n_gpus"] / (rec["ms_per_step"] * 1e-3)) / rec["value"] < 1e-6
+    rf = rec["roofline"]
+    for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "traffic", "near_dominant"):
+        assert k in rf, k
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and 0 < rf["frac"] < 1
+    assert all(0 < s["GBps"] / rf["peak"] < 1.0 for s in rf["stages"].values() if s["GBps"])      # no stage above the measured peak
+    cb = rec["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] > 0 and cb["sample"]
+    e = rec["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 2 * 57_600_000 and e["d2h_bytes_per_step"] >= 2 * 57_600_000
+    assert e["value"] < rec["value"]                                    # the host round trip cannot be faster than the resident step
+    assert rec["gpu_launches"] >= 10 * rec["steps"]
+    assert not set(rec["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
